@@ -1,0 +1,248 @@
+// Instance norm (+ fused activation) forward / backward / double-backward and the split batch norm of
+// the generator's h0.  All kernels are HBM/L2-bound reductions over the H*W positions of one
+// (sample, 32-channel group) slab; the slab is streamed twice (stats, apply) and the second pass
+// hits the 126 MB L2.
+//
+// Reference: nn/modules/normalization.py:10-29.
+#include "common.cuh"
+
+namespace {
+
+constexpr int CG = 32;   // channels per block (one 128-byte line of an NHWC row)
+constexpr int RY = 8;    // row-threads per channel
+
+// sum K quantities over the RY row-threads that share a channel; result broadcast to all of them
+template <int K>
+__device__ __forceinline__ void reduce_cols(float (&v)[K], float (*sm)[RY][CG]) {
+    const int cx = threadIdx.x, ry = threadIdx.y;
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < K; ++k) sm[k][ry][cx] = v[k];
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        float s = 0.f;
+#pragma unroll
+        for (int r = 0; r < RY; ++r) s += sm[k][r][cx];
+        v[k] = s;
+    }
+}
+
+__global__ void __launch_bounds__(CG * RY)
+instnorm_fwd_k(const float* __restrict__ x, float* __restrict__ y, float* __restrict__ stats, int P, int C,
+               float eps, int act) {
+    __shared__ float sm[1][RY][CG];
+    const int n = blockIdx.y, c = blockIdx.x * CG + threadIdx.x;
+    const bool ok = c < C;
+    const float* xp = x + (size_t)n * P * C + c;
+    float v[1] = {0.f};
+    if (ok) for (int p = threadIdx.y; p < P; p += RY) v[0] += xp[(size_t)p * C];
+    reduce_cols<1>(v, sm);
+    const float mean = v[0] / P;
+    v[0] = 0.f;
+    if (ok) for (int p = threadIdx.y; p < P; p += RY) { float d = xp[(size_t)p * C] - mean; v[0] = fmaf(d, d, v[0]); }
+    reduce_cols<1>(v, sm);
+    const float sd = sqrtf(v[0] / P);
+    const float r = 1.f / (sd + eps);
+    if (!ok) return;
+    if (threadIdx.y == 0) { stats[((size_t)n * C + c) * 2] = mean; stats[((size_t)n * C + c) * 2 + 1] = sd; }
+    float* yp = y + (size_t)n * P * C + c;
+    for (int p = threadIdx.y; p < P; p += RY) yp[(size_t)p * C] = act_fwd(act, (xp[(size_t)p * C] - mean) * r);
+}
+
+__global__ void __launch_bounds__(CG * RY)
+instnorm_bwd_k(const float* __restrict__ x, const float* __restrict__ stats, const float* __restrict__ gy,
+               const float* __restrict__ addend, float* __restrict__ gx, int P, int C, float eps, int act) {
+    __shared__ float sm[2][RY][CG];
+    const int n = blockIdx.y, c = blockIdx.x * CG + threadIdx.x;
+    const bool ok = c < C;
+    const size_t base = (size_t)n * P * C + c;
+    float mean = 0.f, sd = 1.f;
+    if (ok) { mean = stats[((size_t)n * C + c) * 2]; sd = stats[((size_t)n * C + c) * 2 + 1]; }
+    const float r = 1.f / (sd + eps);
+    float v[2] = {0.f, 0.f};
+    if (ok) for (int p = threadIdx.y; p < P; p += RY) {
+        const float cc = x[base + (size_t)p * C] - mean;
+        const float gn = gy[base + (size_t)p * C] * act_grad(act, cc * r);
+        v[0] += gn; v[1] = fmaf(gn, cc, v[1]);
+    }
+    reduce_cols<2>(v, sm);
+    if (!ok) return;
+    const float mg = v[0] / P, q = v[1] / P;
+    const float kq = r * r / sd * q;
+    for (int p = threadIdx.y; p < P; p += RY) {
+        const size_t i = base + (size_t)p * C;
+        const float cc = x[i] - mean;
+        const float gn = gy[i] * act_grad(act, cc * r);
+        float o = r * (gn - mg) - kq * cc;
+        if (addend != nullptr) o += addend[i];
+        gx[i] = o;
+    }
+}
+
+__global__ void __launch_bounds__(CG * RY)
+instnorm_bwd2_k(const float* __restrict__ x, const float* __restrict__ stats, const float* __restrict__ gy,
+                const float* __restrict__ t, float* __restrict__ out_gy, float* __restrict__ out_x, int P, int C,
+                float eps, int act) {
+    __shared__ float sm[5][RY][CG];
+    const int n = blockIdx.y, c = blockIdx.x * CG + threadIdx.x;
+    const bool ok = c < C;
+    const size_t base = (size_t)n * P * C + c;
+    float mean = 0.f, sd = 1.f;
+    if (ok) { mean = stats[((size_t)n * C + c) * 2]; sd = stats[((size_t)n * C + c) * 2 + 1]; }
+    const float r = 1.f / (sd + eps);
+    float v[5] = {0.f, 0.f, 0.f, 0.f, 0.f};   // sum gn, sum gn*c, sum t, sum t*c, sum t*gn
+    if (ok) for (int p = threadIdx.y; p < P; p += RY) {
+        const size_t i = base + (size_t)p * C;
+        const float cc = x[i] - mean;
+        const float gn = gy[i] * act_grad(act, cc * r);
+        const float tt = t[i];
+        v[0] += gn; v[1] = fmaf(gn, cc, v[1]); v[2] += tt; v[3] = fmaf(tt, cc, v[3]); v[4] = fmaf(tt, gn, v[4]);
+    }
+    reduce_cols<5>(v, sm);
+    if (!ok) return;
+    const float mg = v[0] / P, q = v[1] / P, mt = v[2] / P, u = v[3] / P, w = v[4] / P - mt * mg;
+    const float kap = r * r / sd;
+    const float coef_c = -kap * w + (2.f * r * r * r / (sd * sd) + r * r / (sd * sd * sd)) * q * u;
+    for (int p = threadIdx.y; p < P; p += RY) {
+        const size_t i = base + (size_t)p * C;
+        const float cc = x[i] - mean;
+        const float ag = act_grad(act, cc * r);
+        const float gn = gy[i] * ag;
+        const float tt = t[i];
+        out_gy[i] = ag * (r * (tt - mt) - kap * u * cc);
+        out_x[i] = cc * coef_c - kap * u * (gn - mg) - kap * q * (tt - mt);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// batch norm over rows of x[R, C]
+
+__global__ void __launch_bounds__(CG * RY)
+bn_stats_k(const float* __restrict__ x, float* __restrict__ sums, int R, int C) {
+    __shared__ float sm[2][RY][CG];
+    const int c = blockIdx.x * CG + threadIdx.x;
+    const bool ok = c < C;
+    float v[2] = {0.f, 0.f};
+    if (ok) for (int p = threadIdx.y; p < R; p += RY) { const float a = x[(size_t)p * C + c]; v[0] += a; v[1] = fmaf(a, a, v[1]); }
+    reduce_cols<2>(v, sm);
+    if (ok && threadIdx.y == 0) { sums[c] = v[0]; sums[C + c] = v[1]; }
+}
+
+__device__ __forceinline__ void bn_coeffs(const float* sums, float count, int C, int c, float eps, float& mu, float& rstd) {
+    mu = sums[c] / count;
+    const float var = fmaxf(sums[C + c] / count - mu * mu, 0.f);
+    rstd = rsqrtf(var + eps);
+}
+
+__global__ void bn_apply_k(const float* __restrict__ x, const float* __restrict__ sums, float count,
+                           const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ y,
+                           long long total, int C, float eps, int act) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int c = (int)(i % C);
+    float mu, rstd; bn_coeffs(sums, count, C, c, eps, mu, rstd);
+    y[i] = act_fwd(act, gamma[c] * (x[i] - mu) * rstd + beta[c]);
+}
+
+__global__ void __launch_bounds__(CG * RY)
+bn_bwd_reduce_k(const float* __restrict__ x, const float* __restrict__ sums, float count,
+                const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ gy,
+                float* __restrict__ red, int R, int C, float eps, int act) {
+    __shared__ float sm[2][RY][CG];
+    const int c = blockIdx.x * CG + threadIdx.x;
+    const bool ok = c < C;
+    float mu = 0.f, rstd = 1.f, g = 1.f, b = 0.f;
+    if (ok) { bn_coeffs(sums, count, C, c, eps, mu, rstd); g = gamma[c]; b = beta[c]; }
+    float v[2] = {0.f, 0.f};
+    if (ok) for (int p = threadIdx.y; p < R; p += RY) {
+        const size_t i = (size_t)p * C + c;
+        const float xh = (x[i] - mu) * rstd;
+        const float gp = gy[i] * act_grad(act, g * xh + b);
+        v[0] += gp; v[1] = fmaf(gp, xh, v[1]);
+    }
+    reduce_cols<2>(v, sm);
+    if (ok && threadIdx.y == 0) { red[c] = v[0]; red[C + c] = v[1]; }
+}
+
+__global__ void bn_bwd_apply_k(const float* __restrict__ x, const float* __restrict__ sums, float count,
+                               const float* __restrict__ gamma, const float* __restrict__ beta,
+                               const float* __restrict__ gy, const float* __restrict__ red, float* __restrict__ gx,
+                               long long total, int C, float eps, int act) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int c = (int)(i % C);
+    float mu, rstd; bn_coeffs(sums, count, C, c, eps, mu, rstd);
+    const float g = gamma[c];
+    const float xh = (x[i] - mu) * rstd;
+    const float gp = gy[i] * act_grad(act, g * xh + beta[c]);
+    gx[i] = g * rstd * (gp - red[c] / count - xh * red[C + c] / count);
+}
+
+}  // namespace
+
+extern "C" {
+
+int eg_instnorm_fwd(const float* x, float* y, float* stats, int N, int P, int C, float eps, int act, void* stream) {
+    EG_REQUIRE(x && y && stats && N > 0 && P > 0 && C > 0 && N <= 65535);
+    dim3 grid(eg_ceil_div(C, CG), N), block(CG, RY);
+    instnorm_fwd_k<<<grid, block, 0, (cudaStream_t)stream>>>(x, y, stats, P, C, eps, act);
+    EG_CHECK_LAUNCH();
+    return 0;
+}
+
+int eg_instnorm_bwd(const float* x, const float* stats, const float* gy, const float* addend, float* gx, int N,
+                    int P, int C, float eps, int act, void* stream) {
+    EG_REQUIRE(x && stats && gy && gx && N > 0 && P > 0 && C > 0 && N <= 65535);
+    dim3 grid(eg_ceil_div(C, CG), N), block(CG, RY);
+    instnorm_bwd_k<<<grid, block, 0, (cudaStream_t)stream>>>(x, stats, gy, addend, gx, P, C, eps, act);
+    EG_CHECK_LAUNCH();
+    return 0;
+}
+
+int eg_instnorm_bwd2(const float* x, const float* stats, const float* gy, const float* t, float* out_gy,
+                     float* out_x, int N, int P, int C, float eps, int act, void* stream) {
+    EG_REQUIRE(x && stats && gy && t && out_gy && out_x && N > 0 && P > 0 && C > 0 && N <= 65535);
+    EG_REQUIRE(act != EG_ACT_TANH);   // second derivative of the activation is taken as zero
+    dim3 grid(eg_ceil_div(C, CG), N), block(CG, RY);
+    instnorm_bwd2_k<<<grid, block, 0, (cudaStream_t)stream>>>(x, stats, gy, t, out_gy, out_x, P, C, eps, act);
+    EG_CHECK_LAUNCH();
+    return 0;
+}
+
+int eg_bn_stats(const float* x, float* sums, int R, int C, void* stream) {
+    EG_REQUIRE(x && sums && R > 0 && C > 0);
+    dim3 grid(eg_ceil_div(C, CG)), block(CG, RY);
+    bn_stats_k<<<grid, block, 0, (cudaStream_t)stream>>>(x, sums, R, C);
+    EG_CHECK_LAUNCH();
+    return 0;
+}
+
+int eg_bn_apply(const float* x, const float* sums, float count, const float* gamma, const float* beta, float* y,
+                int R, int C, float eps, int act, void* stream) {
+    EG_REQUIRE(x && sums && gamma && beta && y && R > 0 && C > 0 && count > 0.f);
+    const long long total = (long long)R * C;
+    bn_apply_k<<<eg_ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(x, sums, count, gamma, beta, y, total, C, eps, act);
+    EG_CHECK_LAUNCH();
+    return 0;
+}
+
+int eg_bn_bwd_reduce(const float* x, const float* sums, float count, const float* gamma, const float* beta,
+                     const float* gy, float* red, int R, int C, float eps, int act, void* stream) {
+    EG_REQUIRE(x && sums && gamma && beta && gy && red && R > 0 && C > 0 && count > 0.f);
+    dim3 grid(eg_ceil_div(C, CG)), block(CG, RY);
+    bn_bwd_reduce_k<<<grid, block, 0, (cudaStream_t)stream>>>(x, sums, count, gamma, beta, gy, red, R, C, eps, act);
+    EG_CHECK_LAUNCH();
+    return 0;
+}
+
+int eg_bn_bwd_apply(const float* x, const float* sums, float count, const float* gamma, const float* beta,
+                    const float* gy, const float* red, float* gx, int R, int C, float eps, int act, void* stream) {
+    EG_REQUIRE(x && sums && gamma && beta && gy && red && gx && R > 0 && C > 0 && count > 0.f);
+    const long long total = (long long)R * C;
+    bn_bwd_apply_k<<<eg_ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(x, sums, count, gamma, beta, gy, red, gx, total, C, eps, act);
+    EG_CHECK_LAUNCH();
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,290 @@
+"""Device operator set of the EdgeGAN hot path: thin wrappers that hand torch CUDA buffers to the
+C ABI (include/edgegan_b200.h).  torch is used for device memory and streams only -- no torch op
+computes anything here.  Every method writes into caller-provided output buffers and is
+asynchronous on the current CUDA stream.
+
+The same method surface is re-implemented on the CPU in ``tests/ref_ops.py`` (test infrastructure)
+so that the host-side derivations in ``edgegan_b200.models`` can be checked against the oracle's
+autograd without a GPU; the product never imports that file.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import ConvShape
+
+ACT = {None: 0, "none": 0, "relu": 1, "lrelu": 2, "tanh": 3, "sigmoid": 4}
+ALGO = {None: 0, "auto": 0, "simt": 1, "tc": 2, "tc3x": 3}
+IN_EPS = 1e-5      # normalization.py:15
+BN_EPS = 1e-5      # normalization.py:11 (epsilon default)
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+class DeviceOps:
+    """CUDA implementation (the only one the product has)."""
+
+    def __init__(self, device="cuda:0"):
+        self.lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise RuntimeError("edgegan_b200 needs a CUDA device (B200, sm_100a); there is no CPU path")
+        self.device = torch.device(device)
+        torch.cuda.set_device(self.device)
+        sm, maj, mnr = C.c_int(), C.c_int(), C.c_int()
+        _lib.check(self.lib.eg_device_info(C.byref(sm), C.byref(maj), C.byref(mnr)), "eg_device_info")
+        self.sm_count, self.cc = sm.value, (maj.value, mnr.value)
+        self._bufs = {}
+        self._shape_cache = {}
+        self.launches = 0
+
+    # ---- memory -----------------------------------------------------------------------------
+    def empty(self, shape):
+        return torch.empty(tuple(shape), dtype=torch.float32, device=self.device)
+
+    def zeros(self, shape):
+        return torch.zeros(tuple(shape), dtype=torch.float32, device=self.device)
+
+    def buf(self, key, shape):
+        """Persistent named scratch buffer (allocated once -> the step is CUDA-graph capturable)."""
+        shape = tuple(int(s) for s in shape)
+        t = self._bufs.get(key)
+        if t is None or t.shape != shape:
+            t = torch.empty(shape, dtype=torch.float32, device=self.device)
+            self._bufs[key] = t
+        return t
+
+    def from_numpy(self, a):
+        return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(self.device)
+
+    def to_numpy(self, t):
+        return t.detach().cpu().numpy()
+
+    def upload(self, dst, src_host):
+        """host (numpy / pinned torch) -> existing device buffer"""
+        if isinstance(src_host, np.ndarray):
+            src_host = torch.from_numpy(np.ascontiguousarray(src_host, dtype=np.float32))
+        dst.copy_(src_host.reshape(dst.shape), non_blocking=True)
+
+    def bytes_allocated(self):
+        return sum(t.numel() * 4 for t in self._bufs.values())
+
+    @property
+    def _st(self):
+        return torch.cuda.current_stream().cuda_stream
+
+    def set_default_algo(self, algo):
+        _lib.check(self.lib.eg_set_default_algo(ALGO[algo]), "eg_set_default_algo")
+
+    # ---- convolution trio -------------------------------------------------------------------
+    def _cs(self, xs, ws, ys, stride, pad):
+        key = (tuple(xs), tuple(ws), tuple(ys), stride, pad)
+        s = self._shape_cache.get(key)
+        if s is None:
+            N, H, W, Ci = xs
+            KH, KW, wci, Co = ws
+            N2, OH, OW, Co2 = ys
+            if not (N == N2 and wci == Ci and Co == Co2):
+                raise ValueError(f"conv shape mismatch x{tuple(xs)} w{tuple(ws)} y{tuple(ys)}")
+            pt, pl = (pad, pad) if isinstance(pad, int) else pad
+            s = ConvShape(N, H, W, Ci, OH, OW, Co, KH, KW, stride, pt, pl)
+            self._shape_cache[key] = s
+        return s
+
+    def conv_fwd(self, x, w, bias, y, stride, pad, algo=None):
+        """y = conv(x, w) (+bias): x[N,H,W,Ci] w[KH,KW,Ci,Co] y[N,OH,OW,Co]; zero pad `pad` before."""
+        s = self._cs(x.shape, w.shape, y.shape, stride, pad)
+        self.launches += 1
+        _lib.check(self.lib.eg_conv2d_fwd(C.byref(s), _p(x), _p(w), _p(bias), _p(y), ALGO[algo], self._st), "conv2d_fwd")
+
+    def conv_bwd_data(self, dy, w, bias, dx, stride, pad, algo=None):
+        """dx = conv input-gradient (== conv2d_transpose forward) (+bias over dx channels)."""
+        s = self._cs(dx.shape, w.shape, dy.shape, stride, pad)
+        self.launches += 1
+        _lib.check(self.lib.eg_conv2d_bwd_data(C.byref(s), _p(dy), _p(w), _p(bias), _p(dx), ALGO[algo], self._st), "conv2d_bwd_data")
+
+    def conv_bwd_weight(self, x, dy, dw, stride, pad, accumulate=False, algo=None):
+        """dw (+)= filter gradient."""
+        s = self._cs(x.shape, dw.shape, dy.shape, stride, pad)
+        self.launches += 2
+        _lib.check(self.lib.eg_conv2d_bwd_weight(C.byref(s), _p(x), _p(dy), _p(dw), int(accumulate), ALGO[algo], self._st), "conv2d_bwd_weight")
+
+    def bias_grad(self, dy, db, accumulate=False):
+        Cn = dy.shape[-1]
+        self.launches += 1
+        _lib.check(self.lib.eg_bias_grad(_p(dy), dy.numel() // Cn, Cn, _p(db), int(accumulate), self._st), "bias_grad")
+
+    # ---- norms / activations ----------------------------------------------------------------
+    @staticmethod
+    def _npc(x):
+        N, Cn = x.shape[0], x.shape[-1]
+        return N, x.numel() // (N * Cn), Cn
+
+    def instnorm_fwd(self, x, y, stats, act):
+        N, P, Cn = self._npc(x)
+        self.launches += 1
+        _lib.check(self.lib.eg_instnorm_fwd(_p(x), _p(y), _p(stats), N, P, Cn, IN_EPS, ACT[act], self._st), "instnorm_fwd")
+
+    def instnorm_bwd(self, x, stats, gy, addend, gx, act):
+        N, P, Cn = self._npc(x)
+        self.launches += 1
+        _lib.check(self.lib.eg_instnorm_bwd(_p(x), _p(stats), _p(gy), _p(addend), _p(gx), N, P, Cn, IN_EPS, ACT[act], self._st), "instnorm_bwd")
+
+    def instnorm_bwd2(self, x, stats, gy, t, out_gy, out_x, act):
+        N, P, Cn = self._npc(x)
+        self.launches += 1
+        _lib.check(self.lib.eg_instnorm_bwd2(_p(x), _p(stats), _p(gy), _p(t), _p(out_gy), _p(out_x), N, P, Cn, IN_EPS, ACT[act], self._st), "instnorm_bwd2")
+
+    def act_fwd(self, x, y, act):
+        self.launches += 1
+        _lib.check(self.lib.eg_act_fwd(_p(x), _p(y), x.numel(), ACT[act], self._st), "act_fwd")
+
+    def act_bwd(self, x_pre, gy, gx, act):
+        self.launches += 1
+        _lib.check(self.lib.eg_act_bwd(_p(x_pre), _p(gy), _p(gx), x_pre.numel(), ACT[act], self._st), "act_bwd")
+
+    def bn_stats(self, x, sums):
+        Cn = x.shape[-1]
+        self.launches += 1
+        _lib.check(self.lib.eg_bn_stats(_p(x), _p(sums), x.numel() // Cn, Cn, self._st), "bn_stats")
+
+    def bn_apply(self, x, sums, count, gamma, beta, y, act):
+        Cn = x.shape[-1]
+        self.launches += 1
+        _lib.check(self.lib.eg_bn_apply(_p(x), _p(sums), float(count), _p(gamma), _p(beta), _p(y), x.numel() // Cn, Cn, BN_EPS, ACT[act], self._st), "bn_apply")
+
+    def bn_bwd_reduce(self, x, sums, count, gamma, beta, gy, red, act):
+        Cn = x.shape[-1]
+        self.launches += 1
+        _lib.check(self.lib.eg_bn_bwd_reduce(_p(x), _p(sums), float(count), _p(gamma), _p(beta), _p(gy), _p(red), x.numel() // Cn, Cn, BN_EPS, ACT[act], self._st), "bn_bwd_reduce")
+
+    def bn_bwd_apply(self, x, sums, count, gamma, beta, gy, red, gx, act):
+        Cn = x.shape[-1]
+        self.launches += 1
+        _lib.check(self.lib.eg_bn_bwd_apply(_p(x), _p(sums), float(count), _p(gamma), _p(beta), _p(gy), _p(red), _p(gx), x.numel() // Cn, Cn, BN_EPS, ACT[act], self._st), "bn_bwd_apply")
+
+    # ---- discriminator head -------------------------------------------------------------------
+    def rowdot_fwd(self, h, w, bias, d):
+        B = h.shape[0]
+        self.launches += 1
+        _lib.check(self.lib.eg_rowdot_fwd(_p(h), _p(w), _p(bias), _p(d), B, h.numel() // B, self._st), "rowdot_fwd")
+
+    def rowdot_bwd_input(self, gd, w, gh):
+        B = gh.shape[0]
+        self.launches += 1
+        _lib.check(self.lib.eg_rowdot_bwd_input(_p(gd), _p(w), _p(gh), B, gh.numel() // B, self._st), "rowdot_bwd_input")
+
+    def rowdot_bwd_weight(self, gd, h, gw, gb, accumulate=False):
+        B = h.shape[0]
+        self.launches += 1
+        _lib.check(self.lib.eg_rowdot_bwd_weight(_p(gd), _p(h), _p(gw), _p(gb), B, h.numel() // B, int(accumulate), self._st), "rowdot_bwd_weight")
+
+    # ---- resize / slices ----------------------------------------------------------------------
+    def bicubic_up2_fwd(self, x, y):
+        N, H, W, Cn = x.shape
+        self.launches += 1
+        _lib.check(self.lib.eg_bicubic_up2_fwd(_p(x), _p(y), N, H, W, Cn, self._st), "bicubic_up2_fwd")
+
+    def bicubic_up2_bwd(self, gy, gx):
+        N, H, W, Cn = gx.shape
+        self.launches += 1
+        _lib.check(self.lib.eg_bicubic_up2_bwd(_p(gy), _p(gx), N, H, W, Cn, self._st), "bicubic_up2_bwd")
+
+    def copy_wslice(self, src, src_w0, dst, dst_w0, width):
+        """dst[:, :, dst_w0:dst_w0+width, :] = src[:, :, src_w0:src_w0+width, :]  (NHWC width slices)"""
+        N, H, Ws, Cn = src.shape
+        Wd = dst.shape[2]
+        self.launches += 1
+        _lib.check(self.lib.eg_copy2d(src.data_ptr() + 4 * src_w0 * Cn, Ws * Cn, dst.data_ptr() + 4 * dst_w0 * Cn,
+                                      Wd * Cn, N * H, width * Cn, self._st), "copy2d")
+
+    def copy(self, src, dst):
+        self.launches += 1
+        _lib.check(self.lib.eg_copy2d(_p(src), src.numel(), _p(dst), dst.numel(), 1, src.numel(), self._st), "copy2d")
+
+    def fill(self, dst, value):
+        self.launches += 1
+        _lib.check(self.lib.eg_fill(_p(dst), dst.numel(), float(value), self._st), "fill")
+
+    def axpby(self, x, y, a, b):
+        """y = a*x + b*y"""
+        self.launches += 1
+        _lib.check(self.lib.eg_axpby(_p(x), _p(y), x.numel(), float(a), float(b), self._st), "axpby")
+
+    # ---- WGAN-GP --------------------------------------------------------------------------------
+    def gp_interpolate(self, real, fake, alpha, xhat):
+        B = real.shape[0]
+        self.launches += 1
+        _lib.check(self.lib.eg_gp_interpolate(_p(real), _p(fake), _p(alpha), _p(xhat), B, real.numel() // B, self._st), "gp_interpolate")
+
+    def gp_seed(self, d, dd):
+        self.launches += 1
+        _lib.check(self.lib.eg_gp_seed(_p(d), _p(dd), d.numel(), self._st), "gp_seed")
+
+    def gp_penalty(self, g, gbar, norms, loss, weight, inv_global_batch):
+        B = g.shape[0]
+        self.launches += 1
+        _lib.check(self.lib.eg_gp_penalty(_p(g), _p(gbar), _p(norms), _p(loss), B, g.numel() // B, float(weight), float(inv_global_batch), self._st), "gp_penalty")
+
+    def gp_seed_bwd(self, d, ddbar, dbar):
+        self.launches += 1
+        _lib.check(self.lib.eg_gp_seed_bwd(_p(d), _p(ddbar), _p(dbar), d.numel(), self._st), "gp_seed_bwd")
+
+    def sum_scaled(self, x, scale, out, accumulate=False):
+        self.launches += 1
+        _lib.check(self.lib.eg_sum_scaled(_p(x), x.numel(), float(scale), _p(out), int(accumulate), self._st), "sum_scaled")
+
+    # ---- encoder pieces ---------------------------------------------------------------------------
+    def reflect_pad_fwd(self, x, y, p):
+        N, H, W, Cn = x.shape
+        self.launches += 1
+        _lib.check(self.lib.eg_reflect_pad_fwd(_p(x), _p(y), N, H, W, Cn, p, self._st), "reflect_pad_fwd")
+
+    def reflect_pad_bwd(self, gy, gx, p):
+        N, H, W, Cn = gx.shape
+        self.launches += 1
+        _lib.check(self.lib.eg_reflect_pad_bwd(_p(gy), _p(gx), N, H, W, Cn, p, self._st), "reflect_pad_bwd")
+
+    def addrelu_pool2_fwd(self, a, b, y):
+        N, H, W, Cn = a.shape
+        self.launches += 1
+        _lib.check(self.lib.eg_addrelu_pool2_fwd(_p(a), _p(b), _p(y), N, H, W, Cn, self._st), "addrelu_pool2_fwd")
+
+    def addrelu_pool2_bwd(self, a, b, gy, g):
+        N, H, W, Cn = a.shape
+        self.launches += 1
+        _lib.check(self.lib.eg_addrelu_pool2_bwd(_p(a), _p(b), _p(gy), _p(g), N, H, W, Cn, self._st), "addrelu_pool2_bwd")
+
+    def relu_globalmean_fwd(self, x, y):
+        N, P, Cn = self._npc(x)
+        self.launches += 1
+        _lib.check(self.lib.eg_relu_globalmean_fwd(_p(x), _p(y), N, P, Cn, self._st), "relu_globalmean_fwd")
+
+    def relu_globalmean_bwd(self, x, gy, gx):
+        N, P, Cn = self._npc(x)
+        self.launches += 1
+        _lib.check(self.lib.eg_relu_globalmean_bwd(_p(x), _p(gy), _p(gx), N, P, Cn, self._st), "relu_globalmean_bwd")
+
+    def reparam_fwd(self, mu, ls, eps, z):
+        self.launches += 1
+        _lib.check(self.lib.eg_reparam_fwd(_p(mu), _p(ls), float(eps), _p(z), mu.numel(), self._st), "reparam_fwd")
+
+    def zl1_loss_bwd(self, mu, ls, eps, target, weight, inv_global_count, gmu, gls, loss):
+        B, Z = mu.shape
+        self.launches += 1
+        _lib.check(self.lib.eg_zl1_loss_bwd(_p(mu), _p(ls), float(eps), _p(target), target.shape[1], B, Z, float(weight),
+                                            float(inv_global_count), _p(gmu), _p(gls), _p(loss), self._st), "zl1_loss_bwd")
+
+    def onehot_concat(self, z, zdim, classes, out):
+        self.launches += 1
+        _lib.check(self.lib.eg_onehot_concat(_p(z), z.shape[0], zdim, classes, _p(out), self._st), "onehot_concat")
+
+    # ---- optimizer ----------------------------------------------------------------------------------
+    def rmsprop(self, var, grad, ms, lr, decay=0.9, eps=1e-10):
+        self.launches += 1
+        _lib.check(self.lib.eg_rmsprop(_p(var), _p(grad), _p(ms), var.numel(), float(lr), float(decay), float(eps), self._st), "rmsprop")

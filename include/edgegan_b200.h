@@ -1,0 +1,164 @@
+/* edgegan_b200 -- C ABI of the B200 (sm_100a) EdgeGAN hot path.
+ *
+ * The reference (sysu-imsl/EdgeGAN) has no FFI: its arithmetic is TensorFlow-1.14 library calls made by the
+ * graph-building functions in edgegan/nn/modules/{conv,linear,normalization,activation}.py and edgegan/nn/functional.py.  Every entry point below
+ * replaces one of those TF call sites (cited as reference file:line, relative to /root/reference/edgegan/),
+ * plus the backward / double-backward passes TF derived implicitly through tf.gradients / minimize().
+ *
+ * Conventions
+ *   - all tensors are float32, NHWC, dense, device pointers owned by the caller (torch CUDA tensors);
+ *   - `stream` is a cudaStream_t passed as void*; every call is stream-ordered and asynchronous;
+ *   - return 0 on success, a negative value on error (eg_last_error() gives the text); nothing throws;
+ *   - no call allocates device memory; calls that need scratch take it as an explicit argument.
+ */
+#ifndef EDGEGAN_B200_H
+#define EDGEGAN_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EG_ABI_VERSION 1
+
+/* activation codes (nn/modules/activation.py:4-15; generator.py:74) */
+#define EG_ACT_NONE 0
+#define EG_ACT_RELU 1
+#define EG_ACT_LRELU_BLOCK 2 /* tf.maximum(x, 0.2x): slope 1 at x == 0 (activation.py:9) */
+#define EG_ACT_TANH 3
+#define EG_ACT_SIGMOID 4     /* discriminator.py:81 (the `prob` output) */
+
+/* conv algorithm selector */
+#define EG_ALGO_AUTO 0
+#define EG_ALGO_SIMT 1   /* fp32 FFMA implicit GEMM (exact fp32; thin-channel layers, on-GPU checker) */
+#define EG_ALGO_TC 2     /* tcgen05 kind::tf32, operands rounded to TF32 by the tensor core            */
+#define EG_ALGO_TC3X 3   /* tcgen05 3xTF32 split (hi*hi + hi*lo + lo*hi), fp32-class accuracy          */
+
+const char* eg_last_error(void);
+int eg_abi_version(void);
+int eg_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* What EG_ALGO_AUTO resolves to for layers the tensor-core kernels support (default EG_ALGO_TC);
+ * layers they do not support (thin channels) always take the fp32 SIMT kernel. */
+int eg_set_default_algo(int algo);
+int eg_get_default_algo(void);
+
+/* A strided convolution y[N,OH,OW,Co] = conv(x[N,H,W,Ci], w[KH,KW,Ci,Co]) with zero padding pad_t/pad_l before
+ * the first row/column (whatever is needed after the last one is implied by OH/OW):
+ *   y[n,oh,ow,co] = sum_{r,q,ci} x[n, oh*stride - pad_t + r, ow*stride - pad_l + q, ci] * w[r,q,ci,co]
+ * This one descriptor serves tf.nn.conv2d SAME/VALID (conv.py:26,29,279) and, with the roles of
+ * x and y swapped, tf.nn.conv2d_transpose (conv.py:49; SURVEY A2: SAME s2 k5 <=> pad_t = pad_l = 1). */
+typedef struct {
+    int N, H, W, Ci;
+    int OH, OW, Co;
+    int KH, KW, stride, pad_t, pad_l;
+} eg_conv_shape;
+
+/* the algorithm a call with (shape, pass, algo) will actually run: pass 0 fwd, 1 bwd_data, 2 bwd_weight */
+int eg_conv2d_algo_for(const eg_conv_shape* s, int pass, int algo);
+/* replaces tf.nn.conv2d (+ tf.nn.bias_add) -- conv.py:29,34 ; bias[Co] may be NULL */
+int eg_conv2d_fwd(const eg_conv_shape* s, const float* x, const float* w, const float* bias, float* y, int algo,
+                  void* stream);
+/* input gradient of the conv == tf.nn.conv2d_transpose forward (conv.py:49-53); bias[Ci] may be NULL */
+int eg_conv2d_bwd_data(const eg_conv_shape* s, const float* dy, const float* w, const float* bias, float* dx,
+                       int algo, void* stream);
+/* filter gradient dw[KH,KW,Ci,Co] (= or +=) sum_pixels x (x) dy */
+int eg_conv2d_bwd_weight(const eg_conv_shape* s, const float* x, const float* dy, float* dw, int accumulate,
+                         int algo, void* stream);
+/* column sums: db[c] (= or +=) sum_r dy[r, c]   (gradient of tf.nn.bias_add, conv.py:34,53; linear.py:29) */
+int eg_bias_grad(const float* dy, long long rows, int C, float* db, int accumulate, void* stream);
+
+/* instance norm (normalization.py:13-18) fused with the activation that follows it in
+ * conv_block / deconv_block / residual (conv.py:61-85,124-130).  x,y: [N,P,C] with P = H*W.
+ * stats[N,C,2] = (mean, sqrt(biased var)).  n = (x-mean)/(sd+eps); y = act(n). */
+int eg_instnorm_fwd(const float* x, float* y, float* stats, int N, int P, int C, float eps, int act, void* stream);
+/* gx = J^T (gy * act'(n)) [+ addend];  addend may be NULL */
+int eg_instnorm_bwd(const float* x, const float* stats, const float* gy, const float* addend, float* gx, int N,
+                    int P, int C, float eps, int act, void* stream);
+/* second-order pass used by the WGAN-GP penalty (edgegan.py:38-42, functional.py:26-29).  With
+ * gx = F(x, gy) the first-order backward above and `t` the cotangent arriving on gx:
+ *   out_gy = act'(n) * J t          (cotangent on gy)
+ *   out_x  = d<t, F(x, gy)>/dx      (cotangent on x through mean / sd; act' treated as locally constant) */
+int eg_instnorm_bwd2(const float* x, const float* stats, const float* gy, const float* t, float* out_gy,
+                     float* out_x, int N, int P, int C, float eps, int act, void* stream);
+
+/* plain activations (activation.py:4-15, generator.py:74) */
+int eg_act_fwd(const float* x, float* y, long long n, int act, void* stream);
+int eg_act_bwd(const float* x_pre, const float* gy, float* gx, long long n, int act, void* stream);
+
+/* batch norm of the generator's h0 (normalization.py:19-25 via generator.py:51-52), split so
+ * the [2C] sums can be all-reduced between ranks (sync-BN): x [R,C].
+ *   sums = (sum x, sum x^2) per channel                      -> eg_bn_stats
+ *   y = act(gamma * (x-mu)/sqrt(var+eps) + beta)              -> eg_bn_apply   (count = global rows)
+ *   red = (sum gpre, sum gpre*xhat) with gpre = gy*act'(pre)  -> eg_bn_bwd_reduce
+ *   gx = gamma*rstd*(gpre - red0/count - xhat*red1/count)     -> eg_bn_bwd_apply  */
+int eg_bn_stats(const float* x, float* sums, int R, int C, void* stream);
+int eg_bn_apply(const float* x, const float* sums, float count, const float* gamma, const float* beta, float* y,
+                int R, int C, float eps, int act, void* stream);
+int eg_bn_bwd_reduce(const float* x, const float* sums, float count, const float* gamma, const float* beta,
+                     const float* gy, float* red, int R, int C, float eps, int act, void* stream);
+int eg_bn_bwd_apply(const float* x, const float* sums, float count, const float* gamma, const float* beta,
+                    const float* gy, const float* red, float* gx, int R, int C, float eps, int act, void* stream);
+
+/* discriminator head d = h @ Matrix + bias with Matrix [F,1] (linear.py:29-31 via discriminator.py:76) */
+int eg_rowdot_fwd(const float* h, const float* w, const float* bias, float* d, int B, int F, void* stream);
+int eg_rowdot_bwd_input(const float* gd, const float* w, float* gh, int B, int F, void* stream);
+int eg_rowdot_bwd_weight(const float* gd, const float* h, float* gw, float* gb, int B, int F, int accumulate,
+                         void* stream);
+
+/* tf.image.resize_images(method=BICUBIC) 2x, legacy kernel (edgegan.py:211-213) */
+int eg_bicubic_up2_fwd(const float* x, float* y, int N, int H, int W, int C, void* stream);
+int eg_bicubic_up2_bwd(const float* gy, float* gx, int N, int H, int W, int C, void* stream);
+
+/* strided 2-D copy: tf.concat(axis=2) / width slices (edgegan.py:203-209,243-247) */
+int eg_copy2d(const float* src, long long src_stride, float* dst, long long dst_stride, long long rows,
+              long long cols, void* stream);
+int eg_fill(float* dst, long long n, float value, void* stream);
+/* y = a*x + b*y */
+int eg_axpby(const float* x, float* y, long long n, float a, float b, void* stream);
+
+/* WGAN-GP (edgegan.py:32-42, functional.py:26-29) */
+/* xhat = real + alpha[b] * (fake - real) */
+int eg_gp_interpolate(const float* real, const float* fake, const float* alpha, float* xhat, int B, long long per,
+                      void* stream);
+/* seed of the first-order backward: dd[b] = d/dd (sigmoid(d) + d) = 1 + s(1-s) */
+int eg_gp_seed(const float* d, float* dd, int B, void* stream);
+/* norms[b] = ||g_b||; gbar = weight * 2 (norm-1) / (Bglobal * norm) * g; loss[0] += weight * sum_b (norm-1)^2 / Bglobal */
+int eg_gp_penalty(const float* g, float* gbar, float* norms, float* loss, int B, long long per, float weight,
+                  float inv_global_batch, void* stream);
+/* dbar[b] = ddbar[b] * s(1-s)(1-2s)  (cotangent on the logit through the seed) */
+int eg_gp_seed_bwd(const float* d, const float* ddbar, float* dbar, int B, void* stream);
+
+/* out[0] (= or +=) scale * sum(x)  -- the reduce_mean's of functional.py:32-41 */
+int eg_sum_scaled(const float* x, long long n, float scale, float* out, int accumulate, void* stream);
+
+/* encoder pieces (encoder.py:54-84, conv.py:25,70-85) */
+int eg_reflect_pad_fwd(const float* x, float* y, int N, int H, int W, int C, int p, void* stream);
+int eg_reflect_pad_bwd(const float* gy, float* gx, int N, int H, int W, int C, int p, void* stream);
+/* y = avgpool2x2(relu(a + b))   (conv.py:85 + encoder.py:68); b may be NULL */
+int eg_addrelu_pool2_fwd(const float* a, const float* b, float* y, int N, int H, int W, int C, void* stream);
+/* g = relu'(a + b) * gy / 4 (same gradient for a and b) */
+int eg_addrelu_pool2_bwd(const float* a, const float* b, const float* gy, float* g, int N, int H, int W, int C,
+                         void* stream);
+/* y[n,c] = mean_p relu(x[n,p,c])   (encoder.py:69-71: relu, 8x8 SAME avg pool over a <=8x8 map, flatten) */
+int eg_relu_globalmean_fwd(const float* x, float* y, int N, int P, int C, void* stream);
+int eg_relu_globalmean_bwd(const float* x, const float* gy, float* gx, int N, int P, int C, void* stream);
+/* z = mu + eps * exp(log_sigma)   (encoder.py:78-82; eps is ONE scalar for the whole batch) */
+int eg_reparam_fwd(const float* mu, const float* ls, float eps, float* z, long long n, void* stream);
+/* loss[0] += weight * mean|target - z| ; gmu = dloss/dmu ; gls = dloss/dls   (functional.py:40-41, edgegan.py:337-342)
+ * target has row stride `target_stride` (z carries a trailing class-id column in multi-class mode) */
+int eg_zl1_loss_bwd(const float* mu, const float* ls, float eps, const float* target, int target_stride, int B,
+                    int Z, float weight, float inv_global_count, float* gmu, float* gls, float* loss, void* stream);
+
+/* generator input of the multi-class model (edgegan.py:188-197): out[n, zdim+classes] =
+ * z[:, :zdim] ++ one_hot(int(z[:, zdim]), classes);  z has zdim+1 columns */
+int eg_onehot_concat(const float* z, int n, int zdim, int classes, float* out, void* stream);
+
+/* tf.train.RMSPropOptimizer step on a flat parameter buffer (edgegan.py:105,117-120):
+ *   ms = decay*ms + (1-decay)*g^2 ; var -= lr * g / sqrt(ms + eps) */
+int eg_rmsprop(float* var, const float* grad, float* ms, long long n, float lr, float decay, float eps,
+               void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EDGEGAN_B200_H */
