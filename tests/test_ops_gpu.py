@@ -1,0 +1,232 @@
+"""Per-kernel parity (-m gpu): every C-ABI entry point, called through edgegan_b200.ops.DeviceOps, against
+the fp64 CPU operator reference in tests/ref_ops.py on the same seeded inputs.
+
+Tolerances: fp32 kernels must agree to ~1e-5 relative to the largest reference magnitude (fp32
+accumulation-order noise); the tcgen05 TF32 path is tested separately in test_conv_tc_gpu.py."""
+import numpy as np
+import pytest
+import torch
+
+from ref_ops import RefOps
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    from edgegan_b200.ops import DeviceOps
+    return DeviceOps()
+
+
+@pytest.fixture(scope="module")
+def ref():
+    return RefOps(torch.float64)
+
+
+def rnd(rs, *shape, scale=1.0):
+    return (rs.standard_normal(shape) * scale).astype(np.float32)
+
+
+def close(got, want, tol=2e-5, what=""):
+    got = np.asarray(got, np.float64)
+    want = np.asarray(want, np.float64)
+    assert got.shape == want.shape, (what, got.shape, want.shape)
+    assert np.isfinite(got).all(), what
+    err = np.abs(got - want).max() / (np.abs(want).max() + 1e-20)
+    assert err < tol, (what, err)
+
+
+def both(dev, ref, name, ins, outs, *args, tol=2e-5, **kw):
+    """ins: list of numpy arrays or None; outs: list of shapes (or numpy arrays = initial contents)."""
+    res = []
+    for o in (dev, ref):
+        ti = [None if a is None else o.from_numpy(a) for a in ins]
+        to = [o.from_numpy(s) if isinstance(s, np.ndarray) else o.zeros(s) for s in outs]
+        getattr(o, name)(*ti[:kw.get("n_in", len(ti))], *to, *args)
+        res.append([o.to_numpy(t) for t in to])
+    for k, (g, w) in enumerate(zip(*res)):
+        close(g, w, tol, f"{name}[{k}]")
+    return res[0]
+
+
+CONV_CASES = [
+    # N, H, W, Ci, Co, k, stride, pad, OH, OW
+    (2, 16, 32, 3, 64, 4, 2, 1, 8, 16),        # d_conv_0 (thin Cin, scalar path)
+    (3, 16, 16, 64, 128, 4, 2, 1, 8, 8),       # d_conv_1 style
+    (2, 8, 8, 128, 64, 5, 2, 1, 4, 4),         # deconv seen as a conv: x = deconv output [8x8], y = deconv input [4x4]
+    (2, 16, 16, 3, 64, 5, 2, 1, 8, 8),         # g_dconv_4 (Cout_g = 3)
+    (2, 10, 10, 64, 128, 3, 1, 0, 8, 8),       # encoder 3x3 VALID on the reflect-padded map
+    (2, 8, 8, 64, 128, 1, 1, 0, 8, 8),         # 1x1 shortcut
+    (5, 1, 1, 100, 512, 1, 1, 0, 1, 1),        # linear as a 1x1 conv
+    (2, 9, 7, 8, 20, 3, 1, 1, 9, 7),           # SAME 3x3 stride 1, odd sizes, ragged channels
+    (1, 12, 12, 16, 8, 7, 1, 3, 12, 12),       # 7x7 SAME (classifier h0 style)
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv_trio_simt(dev, ref, case):
+    N, H, W, Ci, Co, k, s, p, OH, OW = case
+    rs = np.random.RandomState(hash(case) % 2**31)
+    x, w, b = rnd(rs, N, H, W, Ci), rnd(rs, k, k, Ci, Co, scale=0.05), rnd(rs, Co)
+    dy = rnd(rs, N, OH, OW, Co)
+    bi = rnd(rs, Ci)
+    for o_name, ins, out, extra in (
+            ("conv_fwd", [x, w, b], (N, OH, OW, Co), (s, p, "simt")),
+            ("conv_fwd", [x, w, None], (N, OH, OW, Co), (s, p, "simt")),
+            ("conv_bwd_data", [dy, w, None], (N, H, W, Ci), (s, p, "simt")),
+            ("conv_bwd_data", [dy, w, bi], (N, H, W, Ci), (s, p, "simt"))):
+        both(dev, ref, o_name, ins, [out], *extra)
+    both(dev, ref, "conv_bwd_weight", [x, dy], [(k, k, Ci, Co)], s, p, False, "simt")
+    both(dev, ref, "conv_bwd_weight", [x, dy], [rnd(rs, k, k, Ci, Co)], s, p, True, "simt")
+
+
+def test_conv_large_splitk(dev, ref):
+    # big pixel count -> split-K wgrad with atomics
+    rs = np.random.RandomState(5)
+    N, H, W, Ci, Co = 8, 32, 32, 64, 64
+    x, dy = rnd(rs, N, H, W, Ci), rnd(rs, N, 16, 16, Co)
+    both(dev, ref, "conv_bwd_weight", [x, dy], [(4, 4, Ci, Co)], 2, 1, False, "simt", tol=5e-5)
+
+
+@pytest.mark.parametrize("shape", [(3, 8, 8, 64), (2, 16, 32, 128), (2, 4, 4, 40), (1, 2, 2, 512)])
+@pytest.mark.parametrize("act", ["none", "relu", "lrelu"])
+def test_instnorm(dev, ref, shape, act):
+    rs = np.random.RandomState(1)
+    N, C = shape[0], shape[-1]
+    x, gy, t, add = rnd(rs, *shape), rnd(rs, *shape), rnd(rs, *shape), rnd(rs, *shape)
+    y, st = both(dev, ref, "instnorm_fwd", [x], [shape, (N, C, 2)], act)
+    both(dev, ref, "instnorm_bwd", [x, st, gy, None], [shape], act, tol=1e-4)
+    both(dev, ref, "instnorm_bwd", [x, st, gy, add], [shape], act, tol=1e-4)
+    both(dev, ref, "instnorm_bwd2", [x, st, gy, t], [shape, shape], act, tol=2e-4)
+
+
+@pytest.mark.parametrize("act", ["none", "relu", "lrelu", "tanh", "sigmoid"])
+def test_activations(dev, ref, act):
+    rs = np.random.RandomState(2)
+    x, gy = rnd(rs, 1000), rnd(rs, 1000)
+    both(dev, ref, "act_fwd", [x], [(1000,)], act)
+    both(dev, ref, "act_bwd", [x, gy], [(1000,)], act)
+
+
+def test_batchnorm(dev, ref):
+    rs = np.random.RandomState(3)
+    R, C = 96, 80
+    x, gy = rnd(rs, R, C) + 0.3, rnd(rs, R, C)
+    gamma, beta = rnd(rs, C) + 1.0, rnd(rs, C) * 0.1
+    (sums,) = both(dev, ref, "bn_stats", [x], [(2 * C,)])
+    count = float(R)
+    # apply / bwd take (x, sums, count, gamma, beta, ...) with `count` a python scalar in the middle
+    res = []
+    for o in (dev, ref):
+        X, S, G, Bt, GY = (o.from_numpy(a) for a in (x, sums, gamma, beta, gy))
+        y, red, gx = o.zeros((R, C)), o.zeros((2 * C,)), o.zeros((R, C))
+        o.bn_apply(X, S, count, G, Bt, y, "relu")
+        o.bn_bwd_reduce(X, S, count, G, Bt, GY, red, "relu")
+        o.bn_bwd_apply(X, S, count, G, Bt, GY, red, gx, "relu")
+        res.append([o.to_numpy(t) for t in (y, red, gx)])
+    for g, w, nm in zip(res[0], res[1], ("y", "red", "gx")):
+        close(g, w, 5e-5, "bn_" + nm)
+
+
+def test_rowdot(dev, ref):
+    rs = np.random.RandomState(4)
+    B, F = 6, 4096
+    h, w, b, gd = rnd(rs, B, F), rnd(rs, F, 1, scale=0.02), rnd(rs, 1), rnd(rs, B)
+    both(dev, ref, "rowdot_fwd", [h, w, b], [(B,)])
+    both(dev, ref, "rowdot_fwd", [h, w, None], [(B,)])
+    both(dev, ref, "rowdot_bwd_input", [gd, w], [(B, F)])
+    both(dev, ref, "rowdot_bwd_weight", [gd, h], [(F, 1), (1,)], False)
+    both(dev, ref, "rowdot_bwd_weight", [gd, h], [rnd(rs, F, 1), rnd(rs, 1)], True)
+
+
+@pytest.mark.parametrize("shape", [(2, 8, 8, 3), (1, 5, 7, 4), (2, 64, 64, 3)])
+def test_bicubic(dev, ref, shape):
+    rs = np.random.RandomState(6)
+    N, H, W, C = shape
+    x, gy = rnd(rs, *shape), rnd(rs, N, 2 * H, 2 * W, C)
+    (y,) = both(dev, ref, "bicubic_up2_fwd", [x], [(N, 2 * H, 2 * W, C)])
+    assert np.array_equal(y[:, ::2, ::2, :], x)          # even output pixels are copies
+    both(dev, ref, "bicubic_up2_bwd", [gy], [shape])
+
+
+def test_slices_fill_axpby(dev, ref):
+    rs = np.random.RandomState(7)
+    src, dst = rnd(rs, 2, 4, 6, 3), rnd(rs, 2, 4, 10, 3)
+    res = []
+    for o in (dev, ref):
+        S, D = o.from_numpy(src), o.from_numpy(dst)
+        o.copy_wslice(S, 1, D, 3, 4)
+        Y = o.from_numpy(src)
+        o.axpby(o.from_numpy(src * 2), Y, 0.5, -1.5)
+        Fz = o.zeros((7,))
+        o.fill(Fz, 3.25)
+        res.append([o.to_numpy(t) for t in (D, Y, Fz)])
+    for g, w in zip(*res):
+        close(g, w, 1e-6)
+
+
+def test_gp_kernels(dev, ref):
+    rs = np.random.RandomState(8)
+    B, shape = 5, (5, 8, 16, 3)
+    real, fake, alpha = rnd(rs, *shape), rnd(rs, *shape), rs.uniform(size=B).astype(np.float32)
+    both(dev, ref, "gp_interpolate", [real, fake, alpha], [shape])
+    d = rnd(rs, B)
+    both(dev, ref, "gp_seed", [d], [(B,)])
+    both(dev, ref, "gp_seed_bwd", [d, rnd(rs, B)], [(B,)])
+    g = rnd(rs, *shape, scale=0.05)
+    both(dev, ref, "gp_penalty", [g], [shape, (B,), np.array([0.5], np.float32)], 10.0, 1.0 / 7)
+    res = []
+    for o in (dev, ref):
+        out = o.from_numpy(np.array([2.0], np.float32))
+        o.sum_scaled(o.from_numpy(d), 0.25, out, True)
+        out2 = o.from_numpy(np.array([2.0], np.float32))
+        o.sum_scaled(o.from_numpy(d), 0.25, out2, False)
+        res.append([o.to_numpy(out), o.to_numpy(out2)])
+    for g_, w_ in zip(*res):
+        close(g_, w_, 1e-5)
+
+
+def test_encoder_pieces(dev, ref):
+    rs = np.random.RandomState(9)
+    shape = (2, 6, 8, 5)
+    x = rnd(rs, *shape)
+    both(dev, ref, "reflect_pad_fwd", [x], [(2, 8, 10, 5)], 1)
+    both(dev, ref, "reflect_pad_bwd", [rnd(rs, 2, 8, 10, 5)], [shape], 1)
+    both(dev, ref, "reflect_pad_bwd", [rnd(rs, 1, 4, 4, 3)], [(1, 2, 2, 3)], 1)     # smallest map (4x4 block)
+    a, b = rnd(rs, *shape), rnd(rs, *shape)
+    both(dev, ref, "addrelu_pool2_fwd", [a, b], [(2, 3, 4, 5)])
+    both(dev, ref, "addrelu_pool2_bwd", [a, b, rnd(rs, 2, 3, 4, 5)], [shape])
+    both(dev, ref, "relu_globalmean_fwd", [x], [(2, 5)])
+    both(dev, ref, "relu_globalmean_bwd", [x, rnd(rs, 2, 5)], [shape])
+    mu, ls = rnd(rs, 4, 10), rnd(rs, 4, 10, scale=0.3)
+    res = []
+    tgt = rnd(rs, 4, 11)
+    for o in (dev, ref):
+        M, L, T = o.from_numpy(mu), o.from_numpy(ls), o.from_numpy(tgt)
+        z, gmu, gls, loss = o.zeros((4, 10)), o.zeros((4, 10)), o.zeros((4, 10)), o.zeros((1,))
+        o.reparam_fwd(M, L, 0.7, z)
+        o.zl1_loss_bwd(M, L, 0.7, T, 10.0, 1.0 / 40, gmu, gls, loss)
+        res.append([o.to_numpy(t) for t in (z, gmu, gls, loss)])
+    for g_, w_ in zip(*res):
+        close(g_, w_, 1e-5)
+
+
+def test_onehot_rmsprop_biasgrad(dev, ref):
+    rs = np.random.RandomState(10)
+    z = rnd(rs, 6, 11)
+    z[:, 10] = rs.randint(0, 14, 6)
+    res = []
+    for o in (dev, ref):
+        out = o.zeros((6, 24))
+        o.onehot_concat(o.from_numpy(z), 10, 14, out)
+        var, grad, ms = o.from_numpy(rnd(np.random.RandomState(1), 1000)), o.from_numpy(rnd(np.random.RandomState(2), 1000, scale=0.01)), o.zeros((1000,))
+        o.fill(ms, 1.0)
+        o.rmsprop(var, grad, ms, 2e-4)
+        o.rmsprop(var, grad, ms, 2e-4)
+        dy = o.from_numpy(rnd(np.random.RandomState(3), 3000, 40))
+        db, db2 = o.zeros((40,)), o.from_numpy(np.ones(40, np.float32))
+        o.bias_grad(dy, db, False)
+        o.bias_grad(dy, db2, True)
+        res.append([o.to_numpy(t) for t in (out, var, ms, db, db2)])
+    for g_, w_ in zip(*res):
+        close(g_, w_, 2e-5)
