@@ -1,8 +1,693 @@
-// placeholder until the tcgen05 kernels land
+// tcgen05 (5th-gen tensor core) implicit-GEMM convolution trio for sm_100a, kind::tf32.
+//
+//   forward / input-gradient  : D[128 pixels x BN channels] (TMEM, fp32) += A[128 px x 32 k] * B[BN x 32 k]^T
+//       A = one TMA box {32 channels, bw, bh, bn} of the NHWC activation per (filter tap, 32-channel chunk):
+//           the box lands in shared memory as 128 rows x 128 B with the 128-byte swizzle, which IS the
+//           canonical K-major UMMA operand layout -- no im2col buffer ever exists.  Zero padding comes from
+//           TMA out-of-bounds fill; stride 2 is handled by one tensor map per input-pixel parity.
+//       B = filter slice [BN x 32] (K-major): the HWIO filter itself for the input gradient, a per-call
+//           transposed copy (HWOI, <= 8 MB, L2 resident) for the forward.
+//   filter-gradient           : D[128 x BN] += X^T[128 ci x 8 px] * DY[8 px x BN co]: both operands are the same
+//       TMA pixel boxes, consumed as MN-major (channel-contiguous) UMMA operands; split over pixels with a
+//       red.global.add epilogue.
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane) + TMEM owner,
+// warps 2-5 = epilogue (tcgen05.ld 32x32b -> registers -> global).  smem ring of kStages stages with
+// full/empty mbarriers; accumulator hand-off through a tcgen05.commit mbarrier.
+//
+// Replaces tf.nn.conv2d / tf.nn.conv2d_transpose and their gradients
+// (reference nn/modules/conv.py:26,29,49).
 #include "common.cuh"
-int eg_tc_supported_fwd(const eg_conv_shape*) { return 0; }
-int eg_tc_supported_bwd_data(const eg_conv_shape*) { return 0; }
-int eg_tc_supported_bwd_weight(const eg_conv_shape*) { return 0; }
-int eg_tc_conv2d_fwd(const eg_conv_shape*, const float*, const float*, const float*, float*, int, cudaStream_t) { return -3; }
-int eg_tc_conv2d_bwd_data(const eg_conv_shape*, const float*, const float*, const float*, float*, int, cudaStream_t) { return -3; }
-int eg_tc_conv2d_bwd_weight(const eg_conv_shape*, const float*, const float*, float*, int, int, cudaStream_t) { return -3; }
+
+#include <cuda.h>
+#include <cudaTypedefs.h>
+#include <map>
+#include <mutex>
+#include <tuple>
+#include <vector>
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.b32 %0, 1, 0, P;\n\t}\n" : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred P;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P, [%0], %1;\n\t"
+        "@P bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const void* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const void* map, uint32_t bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const void* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish() {
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// D[tmem] (+)= A[smem desc] * B[smem desc]   (kind::tf32, fp32 accumulate)
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// arrive on an mbarrier when all previously issued MMAs have completed (implies fence::before_thread_sync)
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread (thread = TMEM lane = accumulator row)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ---------------------------------------------------------------------------------------------------
+// descriptors
+// ---------------------------------------------------------------------------------------------------
+// shared-memory matrix descriptor, 128-byte swizzle (cute::UMMA::SmemDescriptor, sm_100 version field = 1)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;      // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;      // SWIZZLE_128B
+    return d;
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): fp32 accumulate, tf32 x tf32
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, int b_mn_major) {
+    return (1u << 4)                       // c_format = F32
+         | (2u << 7)                       // a_format = TF32
+         | (2u << 10)                      // b_format = TF32
+         | ((uint32_t)a_mn_major << 15)    // a_major: 0 = K, 1 = MN
+         | ((uint32_t)b_mn_major << 16)
+         | ((uint32_t)(N >> 3) << 17)
+         | ((uint32_t)(M >> 4) << 24);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// kernel parameters
+// ---------------------------------------------------------------------------------------------------
+constexpr int kMaxTaps = 25;
+constexpr int kThreads = 192;
+
+struct __align__(64) TcMaps {
+    CUtensorMap a[4];     // activation maps (one per input-pixel parity for stride 2)
+    CUtensorMap b[4];     // K-major kernels: b[0] = filter map; wgrad: second activation operand maps
+};
+
+struct TcTap { signed char amap, ax, ay, bsel; };   // bsel: filter tap index (K-major kernels) / b map (wgrad)
+
+struct TcPhase {          // one GEMM problem (a dgrad parity phase, or the whole forward)
+    int ntaps, kchunks;   // k iterations = ntaps * kchunks (32 channels each)
+    TcTap taps[kMaxTaps];
+    int ext_w, ext_h, ext_n;          // extents of the pixel grid this phase covers
+    int tiles_w, tiles_h, tiles_n;
+    long long out_off, sn, sh, sw;    // output element offset of pixel (n,h,w) = out_off + n*sn + h*sh + w*sw
+};
+
+struct TcParams {
+    TcPhase ph[4];
+    int nphases;
+    int bw, bh, bn;       // pixel box: bw*bh*bn == 128
+    int BN;               // channel tile (UMMA N)
+    int ldn;              // number of output channels (columns)
+    const float* bias;
+    float* out;
+};
+
+template <int kStages>
+struct SmemLayout {
+    static constexpr int kATile = 128 * 128;          // 128 rows x 128 B
+    static constexpr int kBTileMax = 256 * 128;
+};
+
+// ---------------------------------------------------------------------------------------------------
+// forward / input-gradient kernel (both operands K-major)
+// ---------------------------------------------------------------------------------------------------
+template <int kStages>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_tc_kmajor(const __grid_constant__ TcMaps maps, const __grid_constant__ TcParams P) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const int BN = P.BN;
+    const uint32_t a_bytes = 128 * 128, b_bytes = (uint32_t)BN * 128;
+    const uint32_t stage_bytes = a_bytes + b_bytes;
+
+    __shared__ __align__(8) uint64_t full_bar[kStages];
+    __shared__ __align__(8) uint64_t empty_bar[kStages];
+    __shared__ __align__(8) uint64_t tmem_full_bar;
+    __shared__ uint32_t tmem_base_slot;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const TcPhase& ph = P.ph[blockIdx.z];
+    // tile -> pixel origin
+    int t = blockIdx.x;
+    if (t >= ph.tiles_w * ph.tiles_h * ph.tiles_n) return;      // uniform per block (phases may differ in size)
+    const int tw = t % ph.tiles_w; t /= ph.tiles_w;
+    const int th = t % ph.tiles_h; const int tn = t / ph.tiles_h;
+    const int w0 = tw * P.bw, h0 = th * P.bh, n0 = tn * P.bn;
+    const int col0 = blockIdx.y * BN;
+    const int niter = ph.ntaps * ph.kchunks;
+    const uint32_t tmem_cols = BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256));
+
+    if (warp == 0 && lane == 0) {
+        for (int i = 0; i < 4; ++i) prefetch_tmap(&maps.a[i]);
+        prefetch_tmap(&maps.b[0]);
+        for (int s = 0; s < kStages; ++s) { mbar_init(smem_u32(&full_bar[s]), 1); mbar_init(smem_u32(&empty_bar[s]), 1); }
+        mbar_init(smem_u32(&tmem_full_bar), 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) { tmem_alloc(smem_u32(&tmem_base_slot), tmem_cols); tmem_relinquish(); }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (elect_one()) {
+            int stage = 0; uint32_t phase = 0;
+            for (int it = 0; it < niter; ++it) {
+                const int tap = it / ph.kchunks, kc = it - tap * ph.kchunks;
+                const TcTap tp = ph.taps[tap];
+                mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+                const uint32_t sa = smem_base + stage * stage_bytes, sb = sa + a_bytes;
+                const uint32_t fb = smem_u32(&full_bar[stage]);
+                mbar_expect_tx(fb, stage_bytes);
+                tma_load_4d(sa, &maps.a[tp.amap], fb, kc * 32, w0 + tp.ax, h0 + tp.ay, n0);
+                tma_load_3d(sb, &maps.b[0], fb, kc * 32, col0, tp.bsel);
+                if (++stage == kStages) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (elect_one()) {
+            const uint32_t idesc = make_idesc(128, BN, 0, 0);
+            int stage = 0; uint32_t phase = 0;
+            for (int it = 0; it < niter; ++it) {
+                mbar_wait(smem_u32(&full_bar[stage]), phase);
+                tc_fence_after();
+                const uint32_t sa = smem_base + stage * stage_bytes, sb = sa + a_bytes;
+                const uint64_t ad = make_smem_desc(sa, 16, 1024), bd = make_smem_desc(sb, 16, 1024);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)       // 4 x (K = 8 tf32 = 32 B) inside the 128-byte swizzle span
+                    umma_tf32(tmem_base, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, (it | k) != 0);
+                umma_commit(smem_u32(&empty_bar[stage]));
+                if (++stage == kStages) { stage = 0; phase ^= 1; }
+            }
+            umma_commit(smem_u32(&tmem_full_bar));
+        }
+    } else {
+        // ===== epilogue: warps 2..5 own TMEM lane quarters (warp % 4) =====
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        const int wl = row % P.bw, hl = (row / P.bw) % P.bh, nl = row / (P.bw * P.bh);
+        const int ow = w0 + wl, oh = h0 + hl, on = n0 + nl;
+        const bool valid = ow < ph.ext_w && oh < ph.ext_h && on < ph.ext_n;
+        float* orow = P.out + ph.out_off + (long long)on * ph.sn + (long long)oh * ph.sh + (long long)ow * ph.sw + col0;
+        mbar_wait(smem_u32(&tmem_full_bar), 0);
+        tc_fence_after();
+        for (int c = 0; c < BN; c += 32) {
+            uint32_t r[32];
+            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, r);
+            tmem_ld_wait();
+            if (valid) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+                    if (P.bias != nullptr) {
+                        const float4 bb = __ldg(reinterpret_cast<const float4*>(P.bias + col0 + c + j));
+                        v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
+                    }
+                    *reinterpret_cast<float4*>(orow + c + j) = v;
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, tmem_cols); }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// filter-gradient kernel (both operands MN-major), split over pixels
+// ---------------------------------------------------------------------------------------------------
+struct WgParams {
+    int ntaps;
+    TcTap taps[kMaxTaps];             // amap/ax/ay: tap offset applied to operand X; bsel unused
+    int x_is_a;                       // 1: A (rows) = x channels, B (cols) = dy channels ; 0: swapped
+    int bw, bh, bn, pix;              // pixel box, pix = bw*bh*bn (64)
+    int tiles_w, tiles_h, tiles_n;    // pixel tiles
+    int chunks_per_split;             // pixel tiles per CTA
+    int BN;                           // column tile
+    long long tap_stride, sm, sn;     // dw element = tap*tap_stride + m*sm + n*sn
+    int rows_total, cols_total;       // valid rows / columns (channels)
+    float* out;
+};
+
+template <int kStages>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_tc_wgrad(const __grid_constant__ TcMaps maps, const __grid_constant__ WgParams P) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const int BN = P.BN, PIX = P.pix;
+    const uint32_t sub_bytes = (uint32_t)PIX * 128;          // one 32-channel slab: PIX rows x 128 B
+    const uint32_t a_bytes = 4 * sub_bytes, b_bytes = (uint32_t)(BN / 32) * sub_bytes;
+    const uint32_t stage_bytes = a_bytes + b_bytes;
+
+    __shared__ __align__(8) uint64_t full_bar[kStages];
+    __shared__ __align__(8) uint64_t empty_bar[kStages];
+    __shared__ __align__(8) uint64_t tmem_full_bar;
+    __shared__ uint32_t tmem_base_slot;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tap = blockIdx.z % P.ntaps, split = blockIdx.z / P.ntaps;
+    const TcTap tp = P.taps[tap];
+    const int row0 = blockIdx.x * 128, col0 = blockIdx.y * BN;
+    const int ntiles = P.tiles_w * P.tiles_h * P.tiles_n;
+    const int t_beg = split * P.chunks_per_split;
+    const int t_end = min(ntiles, t_beg + P.chunks_per_split);
+    const int niter = t_end - t_beg;
+    const uint32_t tmem_cols = BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256));
+    if (niter <= 0) return;
+
+    if (warp == 0 && lane == 0) {
+        for (int i = 0; i < 4; ++i) { prefetch_tmap(&maps.a[i]); }
+        prefetch_tmap(&maps.b[0]);
+        for (int s = 0; s < kStages; ++s) { mbar_init(smem_u32(&full_bar[s]), 1); mbar_init(smem_u32(&empty_bar[s]), 1); }
+        mbar_init(smem_u32(&tmem_full_bar), 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) { tmem_alloc(smem_u32(&tmem_base_slot), tmem_cols); tmem_relinquish(); }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_slot;
+
+    if (warp == 0) {
+        if (elect_one()) {
+            int stage = 0; uint32_t phase = 0;
+            for (int it = 0; it < niter; ++it) {
+                int t = t_beg + it;
+                const int tw = t % P.tiles_w; t /= P.tiles_w;
+                const int th = t % P.tiles_h; const int tn = t / P.tiles_h;
+                const int w0 = tw * P.bw, h0 = th * P.bh, n0 = tn * P.bn;
+                mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+                const uint32_t sa = smem_base + stage * stage_bytes, sb = sa + a_bytes;
+                const uint32_t fb = smem_u32(&full_bar[stage]);
+                mbar_expect_tx(fb, stage_bytes);
+                // rows operand: 4 slabs of 32 channels; cols operand: BN/32 slabs
+                for (int i = 0; i < 4; ++i) {
+                    if (P.x_is_a) tma_load_4d(sa + i * sub_bytes, &maps.a[tp.amap], fb, row0 + i * 32, w0 + tp.ax, h0 + tp.ay, n0);
+                    else          tma_load_4d(sa + i * sub_bytes, &maps.b[0], fb, row0 + i * 32, w0, h0, n0);
+                }
+                for (int j = 0; j < BN / 32; ++j) {
+                    if (P.x_is_a) tma_load_4d(sb + j * sub_bytes, &maps.b[0], fb, col0 + j * 32, w0, h0, n0);
+                    else          tma_load_4d(sb + j * sub_bytes, &maps.a[tp.amap], fb, col0 + j * 32, w0 + tp.ax, h0 + tp.ay, n0);
+                }
+                if (++stage == kStages) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        if (elect_one()) {
+            const uint32_t idesc = make_idesc(128, BN, 1, 1);
+            int stage = 0; uint32_t phase = 0;
+            for (int it = 0; it < niter; ++it) {
+                mbar_wait(smem_u32(&full_bar[stage]), phase);
+                tc_fence_after();
+                const uint32_t sa = smem_base + stage * stage_bytes, sb = sa + a_bytes;
+                // MN-major, 128B swizzle: 32 channels (128 B) x 8 pixels per atom; LBO = next 32-channel slab,
+                // SBO = next 8 pixels (1024 B)
+                const uint64_t ad = make_smem_desc(sa, sub_bytes, 1024), bd = make_smem_desc(sb, sub_bytes, 1024);
+                for (int k = 0; k < PIX / 8; ++k)
+                    umma_tf32(tmem_base, ad + (uint64_t)(k * 64), bd + (uint64_t)(k * 64), idesc, (it | k) != 0);
+                umma_commit(smem_u32(&empty_bar[stage]));
+                if (++stage == kStages) { stage = 0; phase ^= 1; }
+            }
+            umma_commit(smem_u32(&tmem_full_bar));
+        }
+    } else {
+        const int q = warp & 3;
+        const int row = row0 + q * 32 + lane;
+        const bool valid = row < P.rows_total;
+        float* obase = P.out + (long long)tap * P.tap_stride + (long long)row * P.sm;
+        mbar_wait(smem_u32(&tmem_full_bar), 0);
+        tc_fence_after();
+        for (int c = 0; c < BN; c += 32) {
+            uint32_t r[32];
+            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, r);
+            tmem_ld_wait();
+            if (valid) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const int col = col0 + c + j;
+                    if (col < P.cols_total) atomicAdd(obase + (long long)col * P.sn, __uint_as_float(r[j]));
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, tmem_cols); }
+}
+
+// HWIO -> HWOI transpose of the filter (the forward's K-major B operand)
+__global__ void transpose_filter_k(const float* __restrict__ w, float* __restrict__ wt, int taps, int Ci, int Co) {
+    __shared__ float tile[32][33];
+    const int tap = blockIdx.z;
+    const float* src = w + (size_t)tap * Ci * Co;
+    float* dst = wt + (size_t)tap * Ci * Co;
+    const int ci0 = blockIdx.y * 32, co0 = blockIdx.x * 32;
+    for (int i = threadIdx.y; i < 32; i += 8) {
+        const int ci = ci0 + i, co = co0 + threadIdx.x;
+        tile[i][threadIdx.x] = (ci < Ci && co < Co) ? src[(size_t)ci * Co + co] : 0.f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += 8) {
+        const int co = co0 + i, ci = ci0 + threadIdx.x;
+        if (ci < Ci && co < Co) dst[(size_t)co * Ci + ci] = tile[threadIdx.x][i];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------
+PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
+
+int get_encode() {
+    if (g_encode) return 0;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e != cudaSuccess) return eg_fail(e, __FILE__, __LINE__);
+    if (qres != cudaDriverEntryPointSuccess || fn == nullptr) return eg_fail_arg("cuTensorMapEncodeTiled entry point", __FILE__, __LINE__);
+    g_encode = (PFN_cuTensorMapEncodeTiled_v12000)fn;
+    return 0;
+}
+
+// 4-D NHWC activation map: dims {C, Wd, Hd, N} with element strides (1, sw, sh, sn) [floats], box {32, bw, bh, bn}
+int make_act_map(CUtensorMap* m, const float* base, int C, int Wd, int Hd, int N, long long sw, long long sh,
+                 long long sn, int bw, int bh, int bn) {
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)Wd, (cuuint64_t)Hd, (cuuint64_t)N};
+    cuuint64_t strides[3] = {(cuuint64_t)sw * 4, (cuuint64_t)sh * 4, (cuuint64_t)sn * 4};
+    cuuint32_t box[4] = {32, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)base, dims, strides, box, es,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return eg_fail_arg("cuTensorMapEncodeTiled(activation)", __FILE__, __LINE__);
+    return 0;
+}
+// 3-D filter map: dims {K, Nn, taps} (K contiguous), box {32, BN, 1}
+int make_filter_map(CUtensorMap* m, const float* base, int K, int Nn, int taps, int BN) {
+    cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)Nn, (cuuint64_t)taps};
+    cuuint64_t strides[2] = {(cuuint64_t)K * 4, (cuuint64_t)K * Nn * 4};
+    cuuint32_t box[3] = {32, (cuuint32_t)BN, 1};
+    cuuint32_t es[3] = {1, 1, 1};
+    CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)base, dims, strides, box, es,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return eg_fail_arg("cuTensorMapEncodeTiled(filter)", __FILE__, __LINE__);
+    return 0;
+}
+
+int gcd(int a, int b) { while (b) { int t = a % b; a = b; b = t; } return a; }
+
+// pixel box {bw, bh, bn} with bw*bh*bn == pix, bw | W, bh | H
+void pick_box(int W, int H, int pix, int& bw, int& bh, int& bn) {
+    bw = gcd(W, pix); bh = gcd(H, pix / bw); bn = pix / (bw * bh);
+}
+
+// per-stream scratch for the transposed filter
+struct Scratch { float* p = nullptr; size_t bytes = 0; };
+std::mutex g_mu;
+std::map<cudaStream_t, Scratch> g_scratch;
+
+int get_scratch(cudaStream_t st, size_t bytes, float** out) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    Scratch& s = g_scratch[st];
+    if (s.bytes < bytes) {
+        // growing is only legal outside stream capture; all shapes are seen during warm-up
+        if (s.p) { cudaStreamSynchronize(st); cudaFree(s.p); s.p = nullptr; s.bytes = 0; }
+        size_t want = bytes < (16u << 20) ? (16u << 20) : bytes;
+        cudaError_t e = cudaMalloc(&s.p, want);
+        if (e != cudaSuccess) return eg_fail(e, __FILE__, __LINE__);
+        s.bytes = want;
+    }
+    *out = s.p;
+    return 0;
+}
+
+constexpr int kStagesK = 3;      // K-major kernel: 3 x (16 KB + BN*128 B) -> two CTAs per SM
+constexpr int kStagesW = 3;      // wgrad kernel:   3 x (32 KB + BN/32 * 8 KB)
+
+bool g_attr_set = false;
+int set_attrs() {
+    if (g_attr_set) return 0;
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kmajor<kStagesK>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return eg_fail(e, __FILE__, __LINE__);
+    e = cudaFuncSetAttribute(conv_tc_wgrad<kStagesW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return eg_fail(e, __FILE__, __LINE__);
+    g_attr_set = true;
+    return 0;
+}
+
+int pick_bn(int n) { return n % 128 == 0 ? 128 : 64; }
+
+bool pow2_box_ok(int W, int H) {
+    int bw, bh, bn;
+    pick_box(W, H, 128, bw, bh, bn);
+    return bw * bh * bn == 128 && bn <= 256 && bw <= 256 && bh <= 256;
+}
+
+}  // namespace
+
+// ---- capability queries ------------------------------------------------------------------------------
+int eg_tc_supported_fwd(const eg_conv_shape* s) {
+    if (s->Ci % 32 || s->Co % 64) return 0;
+    if (s->stride != 1 && s->stride != 2) return 0;
+    if (s->KH * s->KW > kMaxTaps) return 0;
+    if (!pow2_box_ok(s->OW, s->OH)) return 0;
+    return 1;
+}
+int eg_tc_supported_bwd_data(const eg_conv_shape* s) {
+    if (s->Co % 32 || s->Ci % 64) return 0;
+    if (s->stride != 1 && s->stride != 2) return 0;
+    if (s->KH * s->KW > kMaxTaps) return 0;
+    if (s->H % s->stride || s->W % s->stride) return 0;
+    if (!pow2_box_ok(s->W / s->stride, s->H / s->stride)) return 0;
+    return 1;
+}
+int eg_tc_supported_bwd_weight(const eg_conv_shape* s) {
+    if (s->Ci % 32 || s->Co % 32) return 0;
+    if (s->Ci % 128 && s->Co % 128) return 0;      // one side must fill the 128 accumulator rows
+    if (s->stride != 1 && s->stride != 2) return 0;
+    if (s->KH * s->KW > kMaxTaps) return 0;
+    int bw, bh, bn;
+    pick_box(s->OW, s->OH, 64, bw, bh, bn);
+    if (bw * bh * bn != 64) return 0;
+    return 1;
+}
+
+// maps of x seen through the conv's stride: one per parity (ph, pw); returns count
+static int make_x_maps(CUtensorMap* maps, const eg_conv_shape* s, const float* x, int bw, int bh, int bn) {
+    const int S = s->stride;
+    for (int ph = 0; ph < S; ++ph)
+        for (int pw = 0; pw < S; ++pw) {
+            const int Hp = (s->H - ph + S - 1) / S, Wp = (s->W - pw + S - 1) / S;
+            const float* base = x + ((long long)ph * s->W + pw) * s->Ci;
+            if (int r = make_act_map(&maps[ph * S + pw], base, s->Ci, Wp, Hp, s->N, (long long)S * s->Ci,
+                                     (long long)S * s->W * s->Ci, (long long)s->H * s->W * s->Ci, bw, bh, bn))
+                return r;
+        }
+    return 0;
+}
+// tap (r, q) of a stride-S conv -> (parity map, offset) of the input pixel it reads for output pixel (oh, ow)
+static TcTap x_tap(const eg_conv_shape* s, int r, int q, int bsel) {
+    const int S = s->stride;
+    const int ty = r - s->pad_t, tx = q - s->pad_l;
+    const int ph = ((ty % S) + S) % S, pw = ((tx % S) + S) % S;
+    TcTap t;
+    t.amap = (signed char)(ph * S + pw);
+    t.ay = (signed char)((ty - ph) / S);
+    t.ax = (signed char)((tx - pw) / S);
+    t.bsel = (signed char)bsel;
+    return t;
+}
+
+int eg_tc_conv2d_fwd(const eg_conv_shape* s, const float* x, const float* w, const float* bias, float* y, int three_x,
+                     cudaStream_t st) {
+    (void)three_x;
+    if (int r = get_encode()) return r;
+    if (int r = set_attrs()) return r;
+    const int taps = s->KH * s->KW;
+    float* wt = nullptr;
+    if (int r = get_scratch(st, sizeof(float) * (size_t)taps * s->Ci * s->Co, &wt)) return r;
+    {
+        dim3 grid(eg_ceil_div(s->Co, 32), eg_ceil_div(s->Ci, 32), taps), block(32, 8);
+        transpose_filter_k<<<grid, block, 0, st>>>(w, wt, taps, s->Ci, s->Co);
+        EG_CHECK_LAUNCH();
+    }
+    TcMaps maps;
+    TcParams P{};
+    pick_box(s->OW, s->OH, 128, P.bw, P.bh, P.bn);
+    P.BN = pick_bn(s->Co);
+    if (int r = make_x_maps(maps.a, s, x, P.bw, P.bh, P.bn)) return r;
+    for (int i = s->stride * s->stride; i < 4; ++i) maps.a[i] = maps.a[0];
+    if (int r = make_filter_map(&maps.b[0], wt, s->Ci, s->Co, taps, P.BN)) return r;
+    for (int i = 1; i < 4; ++i) maps.b[i] = maps.b[0];
+    P.nphases = 1; P.ldn = s->Co; P.bias = bias; P.out = y;
+    TcPhase& ph = P.ph[0];
+    ph.ntaps = taps; ph.kchunks = s->Ci / 32;
+    for (int r = 0; r < s->KH; ++r)
+        for (int q = 0; q < s->KW; ++q) ph.taps[r * s->KW + q] = x_tap(s, r, q, r * s->KW + q);
+    ph.ext_w = s->OW; ph.ext_h = s->OH; ph.ext_n = s->N;
+    ph.tiles_w = s->OW / P.bw; ph.tiles_h = s->OH / P.bh; ph.tiles_n = eg_ceil_div(s->N, P.bn);
+    ph.out_off = 0; ph.sw = s->Co; ph.sh = (long long)s->OW * s->Co; ph.sn = (long long)s->OH * s->OW * s->Co;
+    dim3 grid(ph.tiles_w * ph.tiles_h * ph.tiles_n, s->Co / P.BN, 1);
+    const size_t smem = (size_t)kStagesK * (128 * 128 + P.BN * 128) + 1024;
+    conv_tc_kmajor<kStagesK><<<grid, kThreads, smem, st>>>(maps, P);
+    EG_CHECK_LAUNCH();
+    return 0;
+}
+
+int eg_tc_conv2d_bwd_data(const eg_conv_shape* s, const float* dy, const float* w, const float* bias, float* dx,
+                          int three_x, cudaStream_t st) {
+    (void)three_x;
+    if (int r = get_encode()) return r;
+    if (int r = set_attrs()) return r;
+    const int S = s->stride;
+    TcMaps maps;
+    TcParams P{};
+    const int Hp = s->H / S, Wp = s->W / S;
+    pick_box(Wp, Hp, 128, P.bw, P.bh, P.bn);
+    P.BN = pick_bn(s->Ci);
+    // A = dy, dense stride-1 window
+    if (int r = make_act_map(&maps.a[0], dy, s->Co, s->OW, s->OH, s->N, s->Co, (long long)s->OW * s->Co,
+                             (long long)s->OH * s->OW * s->Co, P.bw, P.bh, P.bn)) return r;
+    for (int i = 1; i < 4; ++i) maps.a[i] = maps.a[0];
+    // B = HWIO filter viewed as [tap][Ci rows][Co contiguous] -- already K-major for this GEMM
+    if (int r = make_filter_map(&maps.b[0], w, s->Co, s->Ci, s->KH * s->KW, P.BN)) return r;
+    for (int i = 1; i < 4; ++i) maps.b[i] = maps.b[0];
+    P.nphases = S * S; P.ldn = s->Ci; P.bias = bias; P.out = dx;
+    int max_tiles = 0;
+    for (int py = 0; py < S; ++py)
+        for (int px = 0; px < S; ++px) {
+            TcPhase& ph = P.ph[py * S + px];
+            const int r0 = (py + s->pad_t) % S, q0 = (px + s->pad_l) % S;
+            const int nr = r0 < s->KH ? (s->KH - r0 + S - 1) / S : 0, nq = q0 < s->KW ? (s->KW - q0 + S - 1) / S : 0;
+            const int d0y = (py + s->pad_t - r0) / S, d0x = (px + s->pad_l - q0) / S;
+            ph.ntaps = nr * nq; ph.kchunks = s->Co / 32;
+            for (int j = 0; j < nr; ++j)
+                for (int jq = 0; jq < nq; ++jq) {
+                    TcTap t;
+                    t.amap = 0; t.ay = (signed char)(d0y - j); t.ax = (signed char)(d0x - jq);
+                    t.bsel = (signed char)((r0 + S * j) * s->KW + (q0 + S * jq));
+                    ph.taps[j * nq + jq] = t;
+                }
+            ph.ext_w = Wp; ph.ext_h = Hp; ph.ext_n = s->N;
+            ph.tiles_w = Wp / P.bw; ph.tiles_h = Hp / P.bh; ph.tiles_n = eg_ceil_div(s->N, P.bn);
+            ph.out_off = ((long long)py * s->W + px) * s->Ci;
+            ph.sw = (long long)S * s->Ci; ph.sh = (long long)S * s->W * s->Ci; ph.sn = (long long)s->H * s->W * s->Ci;
+            const int nt = ph.tiles_w * ph.tiles_h * ph.tiles_n;
+            if (nt > max_tiles) max_tiles = nt;
+            if (ph.ntaps == 0) return eg_fail_arg("dgrad phase without taps", __FILE__, __LINE__);
+        }
+    dim3 grid(max_tiles, s->Ci / P.BN, S * S);
+    const size_t smem = (size_t)kStagesK * (128 * 128 + P.BN * 128) + 1024;
+    conv_tc_kmajor<kStagesK><<<grid, kThreads, smem, st>>>(maps, P);
+    EG_CHECK_LAUNCH();
+    return 0;
+}
+
+int eg_tc_conv2d_bwd_weight(const eg_conv_shape* s, const float* x, const float* dy, float* dw, int accumulate,
+                            int three_x, cudaStream_t st) {
+    (void)three_x;
+    if (int r = get_encode()) return r;
+    if (int r = set_attrs()) return r;
+    TcMaps maps;
+    WgParams P{};
+    P.pix = 64;
+    pick_box(s->OW, s->OH, P.pix, P.bw, P.bh, P.bn);
+    if (int r = make_x_maps(maps.a, s, x, P.bw, P.bh, P.bn)) return r;
+    for (int i = s->stride * s->stride; i < 4; ++i) maps.a[i] = maps.a[0];
+    if (int r = make_act_map(&maps.b[0], dy, s->Co, s->OW, s->OH, s->N, s->Co, (long long)s->OW * s->Co,
+                             (long long)s->OH * s->OW * s->Co, P.bw, P.bh, P.bn)) return r;
+    for (int i = 1; i < 4; ++i) maps.b[i] = maps.b[0];
+    P.ntaps = s->KH * s->KW;
+    for (int r = 0; r < s->KH; ++r)
+        for (int q = 0; q < s->KW; ++q) P.taps[r * s->KW + q] = x_tap(s, r, q, 0);
+    // rows = whichever channel count fills 128 accumulator rows; prefer the wider one as rows
+    P.x_is_a = (s->Ci % 128 == 0 && (s->Co % 128 != 0 || s->Ci >= s->Co)) ? 1 : 0;
+    const int rows = P.x_is_a ? s->Ci : s->Co, cols = P.x_is_a ? s->Co : s->Ci;
+    P.BN = cols % 128 == 0 ? 128 : (cols % 64 == 0 ? 64 : 32);
+    P.rows_total = rows; P.cols_total = cols;
+    P.tap_stride = (long long)s->Ci * s->Co;
+    P.sm = P.x_is_a ? s->Co : 1; P.sn = P.x_is_a ? 1 : s->Co;
+    P.tiles_w = s->OW / P.bw; P.tiles_h = s->OH / P.bh; P.tiles_n = eg_ceil_div(s->N, P.bn);
+    const int ntiles = P.tiles_w * P.tiles_h * P.tiles_n;
+    const int base_ctas = (rows / 128) * (cols / P.BN) * P.ntaps;
+    int splits = eg_ceil_div(2 * 148, base_ctas);
+    if (splits > ntiles) splits = ntiles;
+    if (splits < 1) splits = 1;
+    P.chunks_per_split = eg_ceil_div(ntiles, splits);
+    splits = eg_ceil_div(ntiles, P.chunks_per_split);
+    P.out = dw;
+    if (!accumulate) {
+        cudaError_t e = cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)P.ntaps * s->Ci * s->Co, st);
+        if (e != cudaSuccess) return eg_fail(e, __FILE__, __LINE__);
+    }
+    dim3 grid(rows / 128, cols / P.BN, P.ntaps * splits);
+    const size_t smem = (size_t)kStagesW * ((4 + P.BN / 32) * P.pix * 128) + 1024;
+    conv_tc_wgrad<kStagesW><<<grid, kThreads, smem, st>>>(maps, P);
+    EG_CHECK_LAUNCH();
+    return 0;
+}

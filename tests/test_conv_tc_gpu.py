@@ -1,0 +1,97 @@
+"""tcgen05 (kind::tf32) implicit-GEMM conv kernels vs the fp64 operator reference (-m gpu).
+
+Tolerance: TF32 keeps 10 explicit mantissa bits per operand, fp32 accumulation -> the error of a length-K dot
+product of O(1) terms is ~ 2^-10 * sqrt(K) * |x||w|; asserted as max-abs error <= 4e-3 * max|reference|."""
+import numpy as np
+import pytest
+import torch
+
+from ref_ops import RefOps
+
+pytestmark = pytest.mark.gpu
+
+TOL = 4e-3
+
+CASES = [
+    # N, H, W, Ci, Co, k, stride, pad, OH, OW
+    (4, 32, 64, 64, 128, 4, 2, 1, 16, 32),     # d_conv_1
+    (4, 16, 32, 128, 256, 4, 2, 1, 8, 16),     # d_conv_3
+    (8, 8, 16, 256, 512, 4, 2, 1, 4, 8),       # d_conv_4
+    (4, 8, 8, 256, 512, 5, 2, 1, 4, 4),        # g_dconv_1 seen as a conv (x = deconv output)
+    (2, 32, 32, 64, 128, 5, 2, 1, 16, 16),     # g_dconv_3 seen as a conv
+    (2, 34, 34, 64, 128, 3, 1, 0, 32, 32),     # encoder res1 (VALID on reflect-padded input)
+    (4, 6, 6, 512, 512, 3, 1, 0, 4, 4),        # encoder last block
+    (2, 32, 32, 64, 128, 1, 1, 0, 32, 32),     # 1x1 shortcut
+    (3, 16, 16, 128, 128, 3, 1, 1, 16, 16),    # SAME 3x3 stride 1 (classifier style), batch not a tile multiple
+]
+
+
+@pytest.fixture(scope="module")
+def dev():
+    from edgegan_b200.ops import DeviceOps
+    return DeviceOps()
+
+
+@pytest.fixture(scope="module")
+def ref():
+    return RefOps(torch.float64)
+
+
+def rnd(rs, *shape, scale=1.0):
+    return (rs.standard_normal(shape) * scale).astype(np.float32)
+
+
+def relerr(got, want):
+    return float(np.abs(got.astype(np.float64) - want).max() / (np.abs(want).max() + 1e-20))
+
+
+def run(o, name, ins, out_shape, *args, init=None):
+    ti = [None if a is None else o.from_numpy(a) for a in ins]
+    out = o.from_numpy(init) if init is not None else o.zeros(out_shape)
+    getattr(o, name)(*ti, out, *args)
+    return o.to_numpy(out)
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_tc_conv_trio(dev, ref, case):
+    import ctypes as C
+    N, H, W, Ci, Co, k, s, p, OH, OW = case
+    rs = np.random.RandomState(abs(hash(case)) % 2**31)
+    x, w, b = rnd(rs, N, H, W, Ci), rnd(rs, k, k, Ci, Co, scale=0.05), rnd(rs, Co)
+    dy, bi = rnd(rs, N, OH, OW, Co), rnd(rs, Ci)
+    cs = dev._cs(x.shape, w.shape, dy.shape, s, p)
+    used = [dev.lib.eg_conv2d_algo_for(C.byref(cs), i, 2) for i in range(3)]
+    # these shapes are the ones the tensor-core path must cover
+    assert used == [2, 2, 2], used
+    want = run(ref, "conv_fwd", [x, w, b], (N, OH, OW, Co), s, p)
+    got = run(dev, "conv_fwd", [x, w, b], (N, OH, OW, Co), s, p, "tc")
+    assert relerr(got, want) < TOL, ("fwd", relerr(got, want))
+    want = run(ref, "conv_bwd_data", [dy, w, bi], (N, H, W, Ci), s, p)
+    got = run(dev, "conv_bwd_data", [dy, w, bi], (N, H, W, Ci), s, p, "tc")
+    assert relerr(got, want) < TOL, ("bwd_data", relerr(got, want))
+    want = run(ref, "conv_bwd_weight", [x, dy], (k, k, Ci, Co), s, p, False)
+    got = run(dev, "conv_bwd_weight", [x, dy], (k, k, Ci, Co), s, p, False, "tc")
+    assert relerr(got, want) < TOL, ("bwd_weight", relerr(got, want))
+    init = rnd(rs, k, k, Ci, Co)
+    want = run(ref, "conv_bwd_weight", [x, dy], None, s, p, True, init=init)
+    got = run(dev, "conv_bwd_weight", [x, dy], None, s, p, True, "tc", init=init)
+    assert relerr(got, want) < TOL, ("bwd_weight+acc", relerr(got, want))
+
+
+def test_tc_matches_simt_at_full_size(dev):
+    """d_conv_3 at the bench batch (3*64 samples): tensor-core result vs the fp32 SIMT kernel on the GPU."""
+    rs = np.random.RandomState(0)
+    N, H, W, Ci, Co = 192, 16, 32, 128, 256
+    x = dev.from_numpy(rnd(rs, N, H, W, Ci))
+    w = dev.from_numpy(rnd(rs, 4, 4, Ci, Co, scale=0.02))
+    dy = dev.from_numpy(rnd(rs, N, 8, 16, Co))
+    for name, args, shape in (("conv_fwd", (x, w, None), (N, 8, 16, Co)),
+                              ("conv_bwd_data", (dy, w, None), (N, H, W, Ci))):
+        a, b = dev.zeros(shape), dev.zeros(shape)
+        getattr(dev, name)(*args, a, 2, 1, "simt")
+        getattr(dev, name)(*args, b, 2, 1, "tc")
+        assert relerr(dev.to_numpy(b), dev.to_numpy(a).astype(np.float64)) < TOL, name
+    a, b = dev.zeros((4, 4, Ci, Co)), dev.zeros((4, 4, Ci, Co))
+    dev.conv_bwd_weight(x, dy, a, 2, 1, False, "simt")
+    dev.conv_bwd_weight(x, dy, b, 2, 1, False, "tc")
+    assert relerr(dev.to_numpy(b), dev.to_numpy(a).astype(np.float64)) < TOL
