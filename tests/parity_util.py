@@ -1,0 +1,60 @@
+"""Shared parity helpers (test infrastructure).
+
+The reference graph is fp32 and parts of it are ill-conditioned (the WGAN-GP double backward divides by the
+per-channel standard deviation up to the third power), so an fp32 run is only reproducible up to its own
+rounding noise.  We therefore evaluate the oracle twice -- fp64 ("truth") and fp32 (the reference precision) --
+and accept a device result when its distance to the fp64 truth is within `tol` of the tensor's magnitude OR
+within `noise_factor` x the fp32 oracle's own distance to that truth."""
+import numpy as np
+import torch
+
+from oracle import edgegan_oracle as O
+
+
+def cancelled(name):
+    """gradients that are mathematically zero (a bias feeding an instance norm)"""
+    return (name.endswith("deconv2d/b") and "g_dconv_4" not in name) or ("/res" in name and name.endswith("conv2d/b"))
+
+
+def oracle_pair(ocfg, v, u, inp, runs=None):
+    out = {}
+    for dt in (torch.float64, torch.float32):
+        st = O.OracleState(ocfg, v, u, dtype=dt)
+        col = {}
+        O.update_model(st, inp, runs=runs, collect=col)
+        out[dt] = (st, col)
+    return out[torch.float64], out[torch.float32]
+
+
+def maxabs(a):
+    return float(np.abs(np.asarray(a, np.float64)).max())
+
+
+def check_grads(mine, truth, ref32, tol, noise_factor=4.0):
+    """mine/truth/ref32: run -> name -> array.  Returns (worst ratio report, list of failures)."""
+    fails, report = [], {}
+    for run, rec in truth.items():
+        worst = 0.0
+        for name, g64 in rec["grads"].items():
+            if cancelled(name):
+                continue
+            scale = maxabs(g64) + 1e-30
+            e = maxabs(np.asarray(mine[run][name], np.float64) - g64) / scale
+            noise = maxabs(np.asarray(ref32[run]["grads"][name], np.float64) - g64) / scale
+            worst = max(worst, e)
+            if not (e <= tol or e <= noise_factor * noise):
+                fails.append((run, name, e, noise))
+        report[run] = worst
+    return report, fails
+
+
+def check_weights(new, st64, st32, lr, tol, noise_factor=4.0):
+    fails = []
+    for name, t in st64.v.items():
+        if cancelled(name):
+            continue
+        e = maxabs(np.asarray(new[name], np.float64) - t.numpy()) / lr
+        noise = maxabs(st32.v[name].numpy().astype(np.float64) - t.numpy()) / lr
+        if not (e <= tol or e <= noise_factor * noise):
+            fails.append((name, e, noise))
+    return fails

@@ -45,41 +45,33 @@ def relmax(a, b):
     return float(np.abs(np.asarray(a, np.float64) - np.asarray(b, np.float64)).max() / (np.abs(b).max() + 1e-30))
 
 
-@pytest.mark.parametrize("algo,tol", [("simt", 2e-3)])
+@pytest.mark.parametrize("algo,tol", [("simt", 2e-3), ("tc", 2e-2)])
 def test_single_class_step_matches_oracle(algo, tol):
+    """tol: max-abs gradient error relative to max|g| per tensor (fp32 kernels 2e-3, TF32 tensor-core kernels
+    2e-2), or within 4x the fp32 oracle's own rounding noise for ill-conditioned tensors (parity_util)."""
+    from parity_util import check_grads, check_weights, oracle_pair
     B = 4
     ocfg, v, u, m, ops = make(B, False, algo)
     inp = O.make_inputs(ocfg, seed=11)
-    st = O.OracleState(ocfg, v, u)
-    collect = {}
-    O.update_model(st, inp, collect=collect)
+    (st64, col64), (st32, col32) = oracle_pair(ocfg, v, u, inp)
     grads = {}
     m.run_hook = lambda run, model: grads.__setitem__(run, model.export_variables("grad"))
     m.update_model(ops.from_numpy(inp.images), ops.from_numpy(inp.z), ops.from_numpy(inp.alpha), inp.eps)
     torch.cuda.synchronize()
-    worst = {}
-    for run, rec in collect.items():
-        for name, g in rec["grads"].items():
-            if cancelled(name):
-                continue
-            e = relmax(grads[run][name], g)
-            worst[run] = max(worst.get(run, 0.0), e)
-            assert e < tol, (run, name, e)
+    report, fails = check_grads(grads, col64, col32, tol)
+    print("worst relative gradient error per run:", report)
+    assert not fails, fails[:5]
     new = m.export_variables("var")
-    lr = ocfg.learning_rate
-    for name, t in st.v.items():
-        if cancelled(name):
-            continue
-        err = np.abs(new[name] - t.numpy()).max()
-        assert err < tol * 3 * lr + 1e-7, (name, err)      # each run moves a weight by <= ~1.05*lr
+    # every run moves a weight by at most ~3.2*lr; allow tol * 10 lr-units of disagreement
+    wf = check_weights(new, st64, st32, ocfg.learning_rate, tol * 10)
+    assert not wf, wf[:5]
     losses = m.read_losses()
     for mine, ref in (("joint_dis_dloss", "d_optim"), ("image_dis_dloss", "d_optim_patch2"),
                       ("edge_dis_dloss", "d_optim_patch3"), ("zl_loss", "e_optim")):
-        assert abs(losses[mine] - st.losses[ref]) < 1e-3 * max(1.0, abs(st.losses[ref])), (mine, losses[mine], st.losses[ref])
-    print("worst relative gradient error per run:", worst)
+        assert abs(losses[mine] - st64.losses[ref]) < max(tol, 1e-3) * max(1.0, abs(st64.losses[ref])), (mine, losses[mine], st64.losses[ref])
 
 
-@pytest.mark.parametrize("algo", ["simt"])
+@pytest.mark.parametrize("algo", ["simt", "tc"])
 def test_inference_matches_oracle(algo):
     """config 1: E(sketch) -> z -> G1, G2 at batch 1 (edgegan.test), generator output within 1e-3 max-abs."""
     ocfg, v, u, m, ops = make(1, False, algo)
