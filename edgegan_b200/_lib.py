@@ -27,6 +27,7 @@ SIGNATURES = {
     "eg_device_info": [C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)],
     "eg_set_default_algo": [i32],
     "eg_get_default_algo": [],
+    "eg_debug_set": [i32, i32],
     "eg_conv2d_algo_for": [_csp, i32, i32],
     "eg_conv2d_fwd": [_csp, vp, vp, vp, vp, i32, vp],
     "eg_conv2d_bwd_data": [_csp, vp, vp, vp, vp, i32, vp],

@@ -112,13 +112,14 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // descriptors
 // ---------------------------------------------------------------------------------------------------
 // shared-memory matrix descriptor, 128-byte swizzle (cute::UMMA::SmemDescriptor, sm_100 version field = 1)
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                                   uint32_t layout_type = 2) {
     uint64_t d = 0;
     d |= (uint64_t)((saddr >> 4) & 0x3FFF);
     d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
     d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
     d |= (uint64_t)1 << 46;      // descriptor version (Blackwell)
-    d |= (uint64_t)2 << 61;      // SWIZZLE_128B
+    d |= (uint64_t)layout_type << 61;      // 2 = SWIZZLE_128B, 1 = SWIZZLE_128B_BASE32B (MN-major tf32)
     return d;
 }
 // instruction descriptor (cute::UMMA::InstrDescriptor): fp32 accumulate, tf32 x tf32
@@ -290,6 +291,7 @@ struct WgParams {
     int BN;                           // column tile
     long long tap_stride, sm, sn;     // dw element = tap*tap_stride + m*sm + n*sn
     int rows_total, cols_total;       // valid rows / columns (channels)
+    int layout_type, sbo;             // UMMA smem descriptor layout type / stride-byte-offset
     float* out;
 };
 
@@ -364,9 +366,10 @@ conv_tc_wgrad(const __grid_constant__ TcMaps maps, const __grid_constant__ WgPar
                 mbar_wait(smem_u32(&full_bar[stage]), phase);
                 tc_fence_after();
                 const uint32_t sa = smem_base + stage * stage_bytes, sb = sa + a_bytes;
-                // MN-major, 128B swizzle: 32 channels (128 B) x 8 pixels per atom; LBO = next 32-channel slab,
-                // SBO = next 8 pixels (1024 B)
-                const uint64_t ad = make_smem_desc(sa, sub_bytes, 1024), bd = make_smem_desc(sb, sub_bytes, 1024);
+                // MN-major tf32 operands must use the "128B swizzle with 32B atoms" layout (Swizzle<2,5,2>): an atom is
+                // 32 channels (128 B) x 4 pixels; LBO = next 32-channel slab, SBO = next 4 pixels (512 B)
+                const uint64_t ad = make_smem_desc(sa, sub_bytes, P.sbo, P.layout_type);
+                const uint64_t bd = make_smem_desc(sb, sub_bytes, P.sbo, P.layout_type);
                 for (int k = 0; k < PIX / 8; ++k)
                     umma_tf32(tmem_base, ad + (uint64_t)(k * 64), bd + (uint64_t)(k * 64), idesc, (it | k) != 0);
                 umma_commit(smem_u32(&empty_bar[stage]));
@@ -435,13 +438,13 @@ int get_encode() {
 
 // 4-D NHWC activation map: dims {C, Wd, Hd, N} with element strides (1, sw, sh, sn) [floats], box {32, bw, bh, bn}
 int make_act_map(CUtensorMap* m, const float* base, int C, int Wd, int Hd, int N, long long sw, long long sh,
-                 long long sn, int bw, int bh, int bn) {
+                 long long sn, int bw, int bh, int bn, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
     cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)Wd, (cuuint64_t)Hd, (cuuint64_t)N};
     cuuint64_t strides[3] = {(cuuint64_t)sw * 4, (cuuint64_t)sh * 4, (cuuint64_t)sn * 4};
     cuuint32_t box[4] = {32, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn};
     cuuint32_t es[4] = {1, 1, 1, 1};
     CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)base, dims, strides, box, es,
-                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return eg_fail_arg("cuTensorMapEncodeTiled(activation)", __FILE__, __LINE__);
     return 0;
@@ -502,6 +505,9 @@ int set_attrs() {
 
 int pick_bn(int n) { return n % 128 == 0 ? 128 : 64; }
 
+// wgrad operand layout knobs: {TMA swizzle enum, UMMA layout type, SBO bytes} (tools/tc_probe.py can sweep them)
+int g_dbg[8] = {(int)CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, 1, 512, 0, 0, 0, 0, 0};
+
 bool pow2_box_ok(int W, int H) {
     int bw, bh, bn;
     pick_box(W, H, 128, bw, bh, bn);
@@ -509,6 +515,12 @@ bool pow2_box_ok(int W, int H) {
 }
 
 }  // namespace
+
+extern "C" int eg_debug_set(int key, int value) {
+    if (key < 0 || key >= 8) return -2;
+    g_dbg[key] = value;
+    return 0;
+}
 
 // ---- capability queries ------------------------------------------------------------------------------
 int eg_tc_supported_fwd(const eg_conv_shape* s) {
@@ -538,14 +550,15 @@ int eg_tc_supported_bwd_weight(const eg_conv_shape* s) {
 }
 
 // maps of x seen through the conv's stride: one per parity (ph, pw); returns count
-static int make_x_maps(CUtensorMap* maps, const eg_conv_shape* s, const float* x, int bw, int bh, int bn) {
+static int make_x_maps(CUtensorMap* maps, const eg_conv_shape* s, const float* x, int bw, int bh, int bn,
+                       CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
     const int S = s->stride;
     for (int ph = 0; ph < S; ++ph)
         for (int pw = 0; pw < S; ++pw) {
             const int Hp = (s->H - ph + S - 1) / S, Wp = (s->W - pw + S - 1) / S;
             const float* base = x + ((long long)ph * s->W + pw) * s->Ci;
             if (int r = make_act_map(&maps[ph * S + pw], base, s->Ci, Wp, Hp, s->N, (long long)S * s->Ci,
-                                     (long long)S * s->W * s->Ci, (long long)s->H * s->W * s->Ci, bw, bh, bn))
+                                     (long long)S * s->W * s->Ci, (long long)s->H * s->W * s->Ci, bw, bh, bn, swz))
                 return r;
         }
     return 0;
@@ -657,10 +670,12 @@ int eg_tc_conv2d_bwd_weight(const eg_conv_shape* s, const float* x, const float*
     WgParams P{};
     P.pix = 64;
     pick_box(s->OW, s->OH, P.pix, P.bw, P.bh, P.bn);
-    if (int r = make_x_maps(maps.a, s, x, P.bw, P.bh, P.bn)) return r;
+    const CUtensorMapSwizzle swz = (CUtensorMapSwizzle)g_dbg[0];
+    P.layout_type = g_dbg[1]; P.sbo = g_dbg[2];
+    if (int r = make_x_maps(maps.a, s, x, P.bw, P.bh, P.bn, swz)) return r;
     for (int i = s->stride * s->stride; i < 4; ++i) maps.a[i] = maps.a[0];
     if (int r = make_act_map(&maps.b[0], dy, s->Co, s->OW, s->OH, s->N, s->Co, (long long)s->OW * s->Co,
-                             (long long)s->OH * s->OW * s->Co, P.bw, P.bh, P.bn)) return r;
+                             (long long)s->OH * s->OW * s->Co, P.bw, P.bh, P.bn, swz)) return r;
     for (int i = 1; i < 4; ++i) maps.b[i] = maps.b[0];
     P.ntaps = s->KH * s->KW;
     for (int r = 0; r < s->KH; ++r)

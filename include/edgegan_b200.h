@@ -42,6 +42,9 @@ int eg_device_info(int* sm_count, int* cc_major, int* cc_minor);
 int eg_set_default_algo(int algo);
 int eg_get_default_algo(void);
 
+/* development knob (kernel layout experiments from tools/tc_probe.py); not part of the stable surface */
+int eg_debug_set(int key, int value);
+
 /* A strided convolution y[N,OH,OW,Co] = conv(x[N,H,W,Ci], w[KH,KW,Ci,Co]) with zero padding pad_t/pad_l before
  * the first row/column (whatever is needed after the last one is implied by OH/OW):
  *   y[n,oh,ow,co] = sum_{r,q,ci} x[n, oh*stride - pad_t + r, ow*stride - pad_l + q, ci] * w[r,q,ci,co]

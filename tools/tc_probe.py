@@ -38,6 +38,20 @@ CASES = [
     (4, 8, 8, 256, 512, 5, 2, 1, 4, 4),
 ]
 which = sys.argv[1:] or ["fwd", "dgrad", "wgrad"]
+if "sweep" in which:
+    N, H, W, Ci, Co, k, s, p, OH, OW = (4, 32, 64, 64, 128, 4, 2, 1, 16, 32)
+    x, dy = rnd(N, H, W, Ci), rnd(N, OH, OW, Co)
+    a = dev.zeros((k, k, Ci, Co))
+    dev.conv_bwd_weight(x, dy, a, s, p, False, "simt")
+    for swz in (3, 4, 5):
+        for lt in (1, 2):
+            for sbo in (512, 1024):
+                dev.lib.eg_debug_set(0, swz); dev.lib.eg_debug_set(1, lt); dev.lib.eg_debug_set(2, sbo)
+                b = dev.zeros((k, k, Ci, Co))
+                dev.conv_bwd_weight(x, dy, b, s, p, False, "tc")
+                torch.cuda.synchronize()
+                stats(f"wgrad swz={swz} layout={lt} sbo={sbo}", b, a)
+    sys.exit(0)
 for case in CASES:
     N, H, W, Ci, Co, k, s, p, OH, OW = case
     print("case", case, flush=True)
