@@ -54,6 +54,37 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "bra WAIT_LOOP;\n\t"
         "DONE:\n\t}\n" ::"r"(bar), "r"(parity) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t a) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts128(uint32_t a, uint4 v) {
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+// The tensor core reads the top 19 bits of an fp32 word (sign, 8 exponent, 10 mantissa) and IGNORES the rest
+// (measured: tools/tc_probe.py, raw vs pre-truncated operands are bit-identical).  Truncation is biased, so:
+//   mode 1 (EG_ALGO_TC):   round to nearest in place  -> unbiased TF32 (what cvt.rna.tf32.f32 would give)
+//   mode 3 (EG_ALGO_TC3X): keep x as the "hi" operand and write lo = x - trunc(x) (exact in fp32) next to it;
+//                          hi*hi + lo*hi + hi*lo then carries ~21 mantissa bits (fp32-class accuracy).
+__device__ __forceinline__ uint32_t tf32_rna(uint32_t x) { return (x + 0x1000u) & 0xFFFFE000u; }
+__device__ __forceinline__ uint32_t tf32_lo(uint32_t x) { return __float_as_uint(__uint_as_float(x) - __uint_as_float(x & 0xFFFFE000u)); }
+// elementwise pass over `bytes` of shared memory by 128 threads (the swizzle is irrelevant: same offset in/out)
+__device__ __forceinline__ void condition_tile(uint32_t src, uint32_t dst_lo, uint32_t bytes, int tid, int mode) {
+    for (uint32_t off = (uint32_t)tid * 16u; off < bytes; off += 128u * 16u) {
+        uint4 v = lds128(src + off);
+        if (mode == 3) {
+            v.x = tf32_lo(v.x); v.y = tf32_lo(v.y); v.z = tf32_lo(v.z); v.w = tf32_lo(v.w);
+            sts128(dst_lo + off, v);
+        } else {
+            v.x = tf32_rna(v.x); v.y = tf32_rna(v.y); v.z = tf32_rna(v.z); v.w = tf32_rna(v.w);
+            sts128(src + off, v);
+        }
+    }
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
@@ -160,6 +191,8 @@ struct TcParams {
     int bw, bh, bn;       // pixel box: bw*bh*bn == 128
     int BN;               // channel tile (UMMA N)
     int ldn;              // number of output channels (columns)
+    int mode;             // 1 = TF32 (operands rounded to nearest), 3 = 3xTF32 split
+    int b_lo_tap_off;     // 3x: tap offset of the filter's lo copy inside the filter map
     const float* bias;
     float* out;
 };
@@ -178,18 +211,21 @@ __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kmajor(const __grid_constant__ TcMaps maps, const __grid_constant__ TcParams P) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const int BN = P.BN;
+    const int BN = P.BN, mode = P.mode;
     const uint32_t a_bytes = 128 * 128, b_bytes = (uint32_t)BN * 128;
-    const uint32_t stage_bytes = a_bytes + b_bytes;
+    // stage: [A][A_lo (3x)][B][B_lo (3x)]
+    const uint32_t a_lo_off = a_bytes, b_off = (mode == 3 ? 2 : 1) * a_bytes, b_lo_off = b_off + b_bytes;
+    const uint32_t stage_bytes = (mode == 3 ? 2 : 1) * (a_bytes + b_bytes);
+    const uint32_t tx_bytes = a_bytes + (mode == 3 ? 2 : 1) * b_bytes;
 
-    __shared__ __align__(8) uint64_t full_bar[kStages];
-    __shared__ __align__(8) uint64_t empty_bar[kStages];
+    __shared__ __align__(8) uint64_t full_bar[kStages];      // TMA bytes landed
+    __shared__ __align__(8) uint64_t ready_bar[kStages];     // operands conditioned (4 warp arrivals)
+    __shared__ __align__(8) uint64_t empty_bar[kStages];     // MMAs that read the stage have completed
     __shared__ __align__(8) uint64_t tmem_full_bar;
     __shared__ uint32_t tmem_base_slot;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const TcPhase& ph = P.ph[blockIdx.z];
-    // tile -> pixel origin
     int t = blockIdx.x;
     if (t >= ph.tiles_w * ph.tiles_h * ph.tiles_n) return;      // uniform per block (phases may differ in size)
     const int tw = t % ph.tiles_w; t /= ph.tiles_w;
@@ -202,7 +238,9 @@ conv_tc_kmajor(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
     if (warp == 0 && lane == 0) {
         for (int i = 0; i < 4; ++i) prefetch_tmap(&maps.a[i]);
         prefetch_tmap(&maps.b[0]);
-        for (int s = 0; s < kStages; ++s) { mbar_init(smem_u32(&full_bar[s]), 1); mbar_init(smem_u32(&empty_bar[s]), 1); }
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(smem_u32(&full_bar[s]), 1); mbar_init(smem_u32(&ready_bar[s]), 4); mbar_init(smem_u32(&empty_bar[s]), 1);
+        }
         mbar_init(smem_u32(&tmem_full_bar), 1);
         fence_barrier_init();
     }
@@ -220,11 +258,12 @@ conv_tc_kmajor(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
                 const int tap = it / ph.kchunks, kc = it - tap * ph.kchunks;
                 const TcTap tp = ph.taps[tap];
                 mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
-                const uint32_t sa = smem_base + stage * stage_bytes, sb = sa + a_bytes;
+                const uint32_t sa = smem_base + stage * stage_bytes;
                 const uint32_t fb = smem_u32(&full_bar[stage]);
-                mbar_expect_tx(fb, stage_bytes);
+                mbar_expect_tx(fb, tx_bytes);
                 tma_load_4d(sa, &maps.a[tp.amap], fb, kc * 32, w0 + tp.ax, h0 + tp.ay, n0);
-                tma_load_3d(sb, &maps.b[0], fb, kc * 32, col0, tp.bsel);
+                tma_load_3d(sa + b_off, &maps.b[0], fb, kc * 32, col0, tp.bsel);
+                if (mode == 3) tma_load_3d(sa + b_lo_off, &maps.b[0], fb, kc * 32, col0, tp.bsel + P.b_lo_tap_off);
                 if (++stage == kStages) { stage = 0; phase ^= 1; }
             }
         }
@@ -234,21 +273,41 @@ conv_tc_kmajor(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
             const uint32_t idesc = make_idesc(128, BN, 0, 0);
             int stage = 0; uint32_t phase = 0;
             for (int it = 0; it < niter; ++it) {
-                mbar_wait(smem_u32(&full_bar[stage]), phase);
+                mbar_wait(smem_u32(&ready_bar[stage]), phase);
                 tc_fence_after();
-                const uint32_t sa = smem_base + stage * stage_bytes, sb = sa + a_bytes;
-                const uint64_t ad = make_smem_desc(sa, 16, 1024), bd = make_smem_desc(sb, 16, 1024);
+                const uint32_t sa = smem_base + stage * stage_bytes;
+                const uint64_t ad = make_smem_desc(sa, 16, 1024), bd = make_smem_desc(sa + b_off, 16, 1024);
 #pragma unroll
                 for (int k = 0; k < 4; ++k)       // 4 x (K = 8 tf32 = 32 B) inside the 128-byte swizzle span
                     umma_tf32(tmem_base, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, (it | k) != 0);
+                if (mode == 3) {
+                    const uint64_t ald = make_smem_desc(sa + a_lo_off, 16, 1024), bld = make_smem_desc(sa + b_lo_off, 16, 1024);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) umma_tf32(tmem_base, ald + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, 1);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) umma_tf32(tmem_base, ad + (uint64_t)(k * 2), bld + (uint64_t)(k * 2), idesc, 1);
+                }
                 umma_commit(smem_u32(&empty_bar[stage]));
                 if (++stage == kStages) { stage = 0; phase ^= 1; }
             }
             umma_commit(smem_u32(&tmem_full_bar));
         }
     } else {
-        // ===== epilogue: warps 2..5 own TMEM lane quarters (warp % 4) =====
-        const int q = warp & 3;
+        // ===== warps 2..5: operand conditioning during the main loop, then the epilogue =====
+        const int ctid = threadIdx.x - 64;
+        {
+            int stage = 0; uint32_t phase = 0;
+            for (int it = 0; it < niter; ++it) {
+                mbar_wait(smem_u32(&full_bar[stage]), phase);
+                const uint32_t sa = smem_base + stage * stage_bytes;
+                condition_tile(sa, sa + a_lo_off, a_bytes, ctid, mode);     // the filter operand was prepared in global
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(&ready_bar[stage]));
+                if (++stage == kStages) { stage = 0; phase ^= 1; }
+            }
+        }
+        const int q = warp & 3;                                  // TMEM lane quarter this warp may access
         const int row = q * 32 + lane;
         const int wl = row % P.bw, hl = (row / P.bw) % P.bh, nl = row / (P.bw * P.bh);
         const int ow = w0 + wl, oh = h0 + hl, on = n0 + nl;
@@ -285,13 +344,14 @@ struct WgParams {
     int ntaps;
     TcTap taps[kMaxTaps];             // amap/ax/ay: tap offset applied to operand X; bsel unused
     int x_is_a;                       // 1: A (rows) = x channels, B (cols) = dy channels ; 0: swapped
-    int bw, bh, bn, pix;              // pixel box, pix = bw*bh*bn (64)
+    int bw, bh, bn, pix;              // pixel box, pix = bw*bh*bn (64; 32 in 3x mode)
     int tiles_w, tiles_h, tiles_n;    // pixel tiles
     int chunks_per_split;             // pixel tiles per CTA
     int BN;                           // column tile
     long long tap_stride, sm, sn;     // dw element = tap*tap_stride + m*sm + n*sn
     int rows_total, cols_total;       // valid rows / columns (channels)
     int layout_type, sbo;             // UMMA smem descriptor layout type / stride-byte-offset
+    int mode;                         // 1 = TF32 rounded, 3 = 3xTF32
     float* out;
 };
 
@@ -300,12 +360,14 @@ __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_wgrad(const __grid_constant__ TcMaps maps, const __grid_constant__ WgParams P) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const int BN = P.BN, PIX = P.pix;
+    const int BN = P.BN, PIX = P.pix, mode = P.mode;
     const uint32_t sub_bytes = (uint32_t)PIX * 128;          // one 32-channel slab: PIX rows x 128 B
     const uint32_t a_bytes = 4 * sub_bytes, b_bytes = (uint32_t)(BN / 32) * sub_bytes;
-    const uint32_t stage_bytes = a_bytes + b_bytes;
+    const uint32_t ab_bytes = a_bytes + b_bytes;             // stage: [A slabs][B slabs][A_lo][B_lo] (lo: 3x only)
+    const uint32_t stage_bytes = (mode == 3 ? 2 : 1) * ab_bytes;
 
     __shared__ __align__(8) uint64_t full_bar[kStages];
+    __shared__ __align__(8) uint64_t ready_bar[kStages];
     __shared__ __align__(8) uint64_t empty_bar[kStages];
     __shared__ __align__(8) uint64_t tmem_full_bar;
     __shared__ uint32_t tmem_base_slot;
@@ -324,7 +386,9 @@ conv_tc_wgrad(const __grid_constant__ TcMaps maps, const __grid_constant__ WgPar
     if (warp == 0 && lane == 0) {
         for (int i = 0; i < 4; ++i) { prefetch_tmap(&maps.a[i]); }
         prefetch_tmap(&maps.b[0]);
-        for (int s = 0; s < kStages; ++s) { mbar_init(smem_u32(&full_bar[s]), 1); mbar_init(smem_u32(&empty_bar[s]), 1); }
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(smem_u32(&full_bar[s]), 1); mbar_init(smem_u32(&ready_bar[s]), 4); mbar_init(smem_u32(&empty_bar[s]), 1);
+        }
         mbar_init(smem_u32(&tmem_full_bar), 1);
         fence_barrier_init();
     }
@@ -345,7 +409,7 @@ conv_tc_wgrad(const __grid_constant__ TcMaps maps, const __grid_constant__ WgPar
                 mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
                 const uint32_t sa = smem_base + stage * stage_bytes, sb = sa + a_bytes;
                 const uint32_t fb = smem_u32(&full_bar[stage]);
-                mbar_expect_tx(fb, stage_bytes);
+                mbar_expect_tx(fb, ab_bytes);
                 // rows operand: 4 slabs of 32 channels; cols operand: BN/32 slabs
                 for (int i = 0; i < 4; ++i) {
                     if (P.x_is_a) tma_load_4d(sa + i * sub_bytes, &maps.a[tp.amap], fb, row0 + i * 32, w0 + tp.ax, h0 + tp.ay, n0);
@@ -363,7 +427,7 @@ conv_tc_wgrad(const __grid_constant__ TcMaps maps, const __grid_constant__ WgPar
             const uint32_t idesc = make_idesc(128, BN, 1, 1);
             int stage = 0; uint32_t phase = 0;
             for (int it = 0; it < niter; ++it) {
-                mbar_wait(smem_u32(&full_bar[stage]), phase);
+                mbar_wait(smem_u32(&ready_bar[stage]), phase);
                 tc_fence_after();
                 const uint32_t sa = smem_base + stage * stage_bytes, sb = sa + a_bytes;
                 // MN-major tf32 operands must use the "128B swizzle with 32B atoms" layout (Swizzle<2,5,2>): an atom is
@@ -372,12 +436,31 @@ conv_tc_wgrad(const __grid_constant__ TcMaps maps, const __grid_constant__ WgPar
                 const uint64_t bd = make_smem_desc(sb, sub_bytes, P.sbo, P.layout_type);
                 for (int k = 0; k < PIX / 8; ++k)
                     umma_tf32(tmem_base, ad + (uint64_t)(k * 64), bd + (uint64_t)(k * 64), idesc, (it | k) != 0);
+                if (mode == 3) {
+                    const uint64_t ald = make_smem_desc(sa + ab_bytes, sub_bytes, P.sbo, P.layout_type);
+                    const uint64_t bld = make_smem_desc(sb + ab_bytes, sub_bytes, P.sbo, P.layout_type);
+                    for (int k = 0; k < PIX / 8; ++k) umma_tf32(tmem_base, ald + (uint64_t)(k * 64), bd + (uint64_t)(k * 64), idesc, 1);
+                    for (int k = 0; k < PIX / 8; ++k) umma_tf32(tmem_base, ad + (uint64_t)(k * 64), bld + (uint64_t)(k * 64), idesc, 1);
+                }
                 umma_commit(smem_u32(&empty_bar[stage]));
                 if (++stage == kStages) { stage = 0; phase ^= 1; }
             }
             umma_commit(smem_u32(&tmem_full_bar));
         }
     } else {
+        const int ctid = threadIdx.x - 64;
+        {
+            int stage = 0; uint32_t phase = 0;
+            for (int it = 0; it < niter; ++it) {
+                mbar_wait(smem_u32(&full_bar[stage]), phase);
+                const uint32_t sa = smem_base + stage * stage_bytes;
+                condition_tile(sa, sa + ab_bytes, ab_bytes, ctid, mode);       // both operands are activations
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(&ready_bar[stage]));
+                if (++stage == kStages) { stage = 0; phase ^= 1; }
+            }
+        }
         const int q = warp & 3;
         const int row = row0 + q * 32 + lane;
         const bool valid = row < P.rows_total;
@@ -402,21 +485,28 @@ conv_tc_wgrad(const __grid_constant__ TcMaps maps, const __grid_constant__ WgPar
     if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, tmem_cols); }
 }
 
-// HWIO -> HWOI transpose of the filter (the forward's K-major B operand)
-__global__ void transpose_filter_k(const float* __restrict__ w, float* __restrict__ wt, int taps, int Ci, int Co) {
+// Filter operand preparation (global -> global, the filter is small and L2 resident):
+//   dst_hi[tap][r][c] = cond(src)   with optional [Ci][Co] -> [Co][Ci] transpose per tap
+//   mode 1: cond = round-to-nearest TF32 ; mode 3: hi = src unchanged, lo = src - trunc(src) written to dst_lo
+__global__ void prep_filter_k(const float* __restrict__ w, float* __restrict__ hi, float* __restrict__ lo, int taps,
+                              int Ci, int Co, int transpose, int mode) {
     __shared__ float tile[32][33];
     const int tap = blockIdx.z;
-    const float* src = w + (size_t)tap * Ci * Co;
-    float* dst = wt + (size_t)tap * Ci * Co;
+    const size_t tb = (size_t)tap * Ci * Co;
     const int ci0 = blockIdx.y * 32, co0 = blockIdx.x * 32;
     for (int i = threadIdx.y; i < 32; i += 8) {
         const int ci = ci0 + i, co = co0 + threadIdx.x;
-        tile[i][threadIdx.x] = (ci < Ci && co < Co) ? src[(size_t)ci * Co + co] : 0.f;
+        tile[i][threadIdx.x] = (ci < Ci && co < Co) ? w[tb + (size_t)ci * Co + co] : 0.f;
     }
     __syncthreads();
     for (int i = threadIdx.y; i < 32; i += 8) {
-        const int co = co0 + i, ci = ci0 + threadIdx.x;
-        if (ci < Ci && co < Co) dst[(size_t)co * Ci + ci] = tile[threadIdx.x][i];
+        float v; size_t o; bool ok;
+        if (transpose) { const int co = co0 + i, ci = ci0 + threadIdx.x; v = tile[threadIdx.x][i]; o = tb + (size_t)co * Ci + ci; ok = ci < Ci && co < Co; }
+        else           { const int ci = ci0 + i, co = co0 + threadIdx.x; v = tile[i][threadIdx.x]; o = tb + (size_t)ci * Co + co; ok = ci < Ci && co < Co; }
+        if (!ok) continue;
+        const uint32_t u = __float_as_uint(v);
+        if (mode == 3) { hi[o] = v; lo[o] = __uint_as_float(tf32_lo(u)); }
+        else hi[o] = __uint_as_float(tf32_rna(u));
     }
 }
 
@@ -469,7 +559,8 @@ void pick_box(int W, int H, int pix, int& bw, int& bh, int& bn) {
     bw = gcd(W, pix); bh = gcd(H, pix / bw); bn = pix / (bw * bh);
 }
 
-// per-stream scratch for the transposed filter
+// per-stream scratch for the prepared filter copies (the only memory the library owns; grown at first use,
+// i.e. during warm-up, never inside a captured region)
 struct Scratch { float* p = nullptr; size_t bytes = 0; };
 std::mutex g_mu;
 std::map<cudaStream_t, Scratch> g_scratch;
@@ -478,9 +569,8 @@ int get_scratch(cudaStream_t st, size_t bytes, float** out) {
     std::lock_guard<std::mutex> lk(g_mu);
     Scratch& s = g_scratch[st];
     if (s.bytes < bytes) {
-        // growing is only legal outside stream capture; all shapes are seen during warm-up
         if (s.p) { cudaStreamSynchronize(st); cudaFree(s.p); s.p = nullptr; s.bytes = 0; }
-        size_t want = bytes < (16u << 20) ? (16u << 20) : bytes;
+        size_t want = bytes < (32u << 20) ? (32u << 20) : bytes;
         cudaError_t e = cudaMalloc(&s.p, want);
         if (e != cudaSuccess) return eg_fail(e, __FILE__, __LINE__);
         s.bytes = want;
@@ -489,8 +579,8 @@ int get_scratch(cudaStream_t st, size_t bytes, float** out) {
     return 0;
 }
 
-constexpr int kStagesK = 3;      // K-major kernel: 3 x (16 KB + BN*128 B) -> two CTAs per SM
-constexpr int kStagesW = 3;      // wgrad kernel:   3 x (32 KB + BN/32 * 8 KB)
+constexpr int kStagesK = 3;
+constexpr int kStagesW = 3;
 
 bool g_attr_set = false;
 int set_attrs() {
@@ -508,10 +598,17 @@ int pick_bn(int n) { return n % 128 == 0 ? 128 : 64; }
 // wgrad operand layout knobs: {TMA swizzle enum, UMMA layout type, SBO bytes} (tools/tc_probe.py can sweep them)
 int g_dbg[8] = {(int)CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, 1, 512, 0, 0, 0, 0, 0};
 
-bool pow2_box_ok(int W, int H) {
-    int bw, bh, bn;
-    pick_box(W, H, 128, bw, bh, bn);
-    return bw * bh * bn == 128 && bn <= 256 && bw <= 256 && bh <= 256;
+// prepared filter: returns the base of [hi copy (taps*Ci*Co)][lo copy (3x only)]
+int prep_filter(const eg_conv_shape* s, const float* w, int transpose, int mode, cudaStream_t st, float** out) {
+    const int taps = s->KH * s->KW;
+    const size_t n = (size_t)taps * s->Ci * s->Co;
+    float* buf = nullptr;
+    if (int r = get_scratch(st, sizeof(float) * n * 2, &buf)) return r;
+    dim3 grid(eg_ceil_div(s->Co, 32), eg_ceil_div(s->Ci, 32), taps), block(32, 8);
+    prep_filter_k<<<grid, block, 0, st>>>(w, buf, buf + n, taps, s->Ci, s->Co, transpose, mode);
+    EG_CHECK_LAUNCH();
+    *out = buf;
+    return 0;
 }
 
 }  // namespace
@@ -527,7 +624,6 @@ int eg_tc_supported_fwd(const eg_conv_shape* s) {
     if (s->Ci % 32 || s->Co % 64) return 0;
     if (s->stride != 1 && s->stride != 2) return 0;
     if (s->KH * s->KW > kMaxTaps) return 0;
-    if (!pow2_box_ok(s->OW, s->OH)) return 0;
     return 1;
 }
 int eg_tc_supported_bwd_data(const eg_conv_shape* s) {
@@ -535,7 +631,6 @@ int eg_tc_supported_bwd_data(const eg_conv_shape* s) {
     if (s->stride != 1 && s->stride != 2) return 0;
     if (s->KH * s->KW > kMaxTaps) return 0;
     if (s->H % s->stride || s->W % s->stride) return 0;
-    if (!pow2_box_ok(s->W / s->stride, s->H / s->stride)) return 0;
     return 1;
 }
 int eg_tc_supported_bwd_weight(const eg_conv_shape* s) {
@@ -543,13 +638,10 @@ int eg_tc_supported_bwd_weight(const eg_conv_shape* s) {
     if (s->Ci % 128 && s->Co % 128) return 0;      // one side must fill the 128 accumulator rows
     if (s->stride != 1 && s->stride != 2) return 0;
     if (s->KH * s->KW > kMaxTaps) return 0;
-    int bw, bh, bn;
-    pick_box(s->OW, s->OH, 64, bw, bh, bn);
-    if (bw * bh * bn != 64) return 0;
     return 1;
 }
 
-// maps of x seen through the conv's stride: one per parity (ph, pw); returns count
+// maps of x seen through the conv's stride: one per parity (ph, pw)
 static int make_x_maps(CUtensorMap* maps, const eg_conv_shape* s, const float* x, int bw, int bh, int bn,
                        CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
     const int S = s->stride;
@@ -576,26 +668,23 @@ static TcTap x_tap(const eg_conv_shape* s, int r, int q, int bsel) {
     return t;
 }
 
+static size_t kmajor_smem(int BN, int mode) { return (size_t)kStagesK * (mode == 3 ? 2 : 1) * (128 * 128 + BN * 128) + 1024; }
+
 int eg_tc_conv2d_fwd(const eg_conv_shape* s, const float* x, const float* w, const float* bias, float* y, int three_x,
                      cudaStream_t st) {
-    (void)three_x;
     if (int r = get_encode()) return r;
     if (int r = set_attrs()) return r;
-    const int taps = s->KH * s->KW;
+    const int taps = s->KH * s->KW, mode = three_x ? 3 : 1;
     float* wt = nullptr;
-    if (int r = get_scratch(st, sizeof(float) * (size_t)taps * s->Ci * s->Co, &wt)) return r;
-    {
-        dim3 grid(eg_ceil_div(s->Co, 32), eg_ceil_div(s->Ci, 32), taps), block(32, 8);
-        transpose_filter_k<<<grid, block, 0, st>>>(w, wt, taps, s->Ci, s->Co);
-        EG_CHECK_LAUNCH();
-    }
+    if (int r = prep_filter(s, w, 1, mode, st, &wt)) return r;       // HWIO -> HWOI (K-major B operand)
     TcMaps maps;
     TcParams P{};
     pick_box(s->OW, s->OH, 128, P.bw, P.bh, P.bn);
     P.BN = pick_bn(s->Co);
+    P.mode = mode; P.b_lo_tap_off = taps;
     if (int r = make_x_maps(maps.a, s, x, P.bw, P.bh, P.bn)) return r;
     for (int i = s->stride * s->stride; i < 4; ++i) maps.a[i] = maps.a[0];
-    if (int r = make_filter_map(&maps.b[0], wt, s->Ci, s->Co, taps, P.BN)) return r;
+    if (int r = make_filter_map(&maps.b[0], wt, s->Ci, s->Co, 2 * taps, P.BN)) return r;
     for (int i = 1; i < 4; ++i) maps.b[i] = maps.b[0];
     P.nphases = 1; P.ldn = s->Co; P.bias = bias; P.out = y;
     TcPhase& ph = P.ph[0];
@@ -606,29 +695,30 @@ int eg_tc_conv2d_fwd(const eg_conv_shape* s, const float* x, const float* w, con
     ph.tiles_w = s->OW / P.bw; ph.tiles_h = s->OH / P.bh; ph.tiles_n = eg_ceil_div(s->N, P.bn);
     ph.out_off = 0; ph.sw = s->Co; ph.sh = (long long)s->OW * s->Co; ph.sn = (long long)s->OH * s->OW * s->Co;
     dim3 grid(ph.tiles_w * ph.tiles_h * ph.tiles_n, s->Co / P.BN, 1);
-    const size_t smem = (size_t)kStagesK * (128 * 128 + P.BN * 128) + 1024;
-    conv_tc_kmajor<kStagesK><<<grid, kThreads, smem, st>>>(maps, P);
+    conv_tc_kmajor<kStagesK><<<grid, kThreads, kmajor_smem(P.BN, mode), st>>>(maps, P);
     EG_CHECK_LAUNCH();
     return 0;
 }
 
 int eg_tc_conv2d_bwd_data(const eg_conv_shape* s, const float* dy, const float* w, const float* bias, float* dx,
                           int three_x, cudaStream_t st) {
-    (void)three_x;
     if (int r = get_encode()) return r;
     if (int r = set_attrs()) return r;
-    const int S = s->stride;
+    const int S = s->stride, taps = s->KH * s->KW, mode = three_x ? 3 : 1;
+    float* wp = nullptr;
+    if (int r = prep_filter(s, w, 0, mode, st, &wp)) return r;       // HWIO is already K-major for this GEMM
     TcMaps maps;
     TcParams P{};
     const int Hp = s->H / S, Wp = s->W / S;
     pick_box(Wp, Hp, 128, P.bw, P.bh, P.bn);
     P.BN = pick_bn(s->Ci);
+    P.mode = mode; P.b_lo_tap_off = taps;
     // A = dy, dense stride-1 window
     if (int r = make_act_map(&maps.a[0], dy, s->Co, s->OW, s->OH, s->N, s->Co, (long long)s->OW * s->Co,
                              (long long)s->OH * s->OW * s->Co, P.bw, P.bh, P.bn)) return r;
     for (int i = 1; i < 4; ++i) maps.a[i] = maps.a[0];
-    // B = HWIO filter viewed as [tap][Ci rows][Co contiguous] -- already K-major for this GEMM
-    if (int r = make_filter_map(&maps.b[0], w, s->Co, s->Ci, s->KH * s->KW, P.BN)) return r;
+    // B = filter viewed as [tap][Ci rows][Co contiguous]
+    if (int r = make_filter_map(&maps.b[0], wp, s->Co, s->Ci, 2 * taps, P.BN)) return r;
     for (int i = 1; i < 4; ++i) maps.b[i] = maps.b[0];
     P.nphases = S * S; P.ldn = s->Ci; P.bias = bias; P.out = dx;
     int max_tiles = 0;
@@ -655,20 +745,19 @@ int eg_tc_conv2d_bwd_data(const eg_conv_shape* s, const float* dy, const float* 
             if (ph.ntaps == 0) return eg_fail_arg("dgrad phase without taps", __FILE__, __LINE__);
         }
     dim3 grid(max_tiles, s->Ci / P.BN, S * S);
-    const size_t smem = (size_t)kStagesK * (128 * 128 + P.BN * 128) + 1024;
-    conv_tc_kmajor<kStagesK><<<grid, kThreads, smem, st>>>(maps, P);
+    conv_tc_kmajor<kStagesK><<<grid, kThreads, kmajor_smem(P.BN, mode), st>>>(maps, P);
     EG_CHECK_LAUNCH();
     return 0;
 }
 
 int eg_tc_conv2d_bwd_weight(const eg_conv_shape* s, const float* x, const float* dy, float* dw, int accumulate,
                             int three_x, cudaStream_t st) {
-    (void)three_x;
     if (int r = get_encode()) return r;
     if (int r = set_attrs()) return r;
     TcMaps maps;
     WgParams P{};
-    P.pix = 64;
+    P.mode = three_x ? 3 : 1;
+    P.pix = three_x ? 32 : 64;
     pick_box(s->OW, s->OH, P.pix, P.bw, P.bh, P.bn);
     const CUtensorMapSwizzle swz = (CUtensorMapSwizzle)g_dbg[0];
     P.layout_type = g_dbg[1]; P.sbo = g_dbg[2];
@@ -701,7 +790,7 @@ int eg_tc_conv2d_bwd_weight(const eg_conv_shape* s, const float* x, const float*
         if (e != cudaSuccess) return eg_fail(e, __FILE__, __LINE__);
     }
     dim3 grid(rows / 128, cols / P.BN, P.ntaps * splits);
-    const size_t smem = (size_t)kStagesW * ((4 + P.BN / 32) * P.pix * 128) + 1024;
+    const size_t smem = (size_t)kStagesW * (P.mode == 3 ? 2 : 1) * ((4 + P.BN / 32) * P.pix * 128) + 1024;
     conv_tc_wgrad<kStagesW><<<grid, kThreads, smem, st>>>(maps, P);
     EG_CHECK_LAUNCH();
     return 0;

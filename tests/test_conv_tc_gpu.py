@@ -52,9 +52,15 @@ def run(o, name, ins, out_shape, *args, init=None):
     return o.to_numpy(out)
 
 
+# tc: operands rounded to nearest TF32; tc3x: 3xTF32 split (hi*hi + lo*hi + hi*lo), fp32-class accuracy
+ALGO_TOL = {"tc": 2e-3, "tc3x": 2e-5}
+
+
+@pytest.mark.parametrize("algo", ["tc", "tc3x"])
 @pytest.mark.parametrize("case", CASES)
-def test_tc_conv_trio(dev, ref, case):
+def test_tc_conv_trio(dev, ref, case, algo):
     import ctypes as C
+    TOL = ALGO_TOL[algo]
     N, H, W, Ci, Co, k, s, p, OH, OW = case
     rs = np.random.RandomState(abs(hash(case)) % 2**31)
     x, w, b = rnd(rs, N, H, W, Ci), rnd(rs, k, k, Ci, Co, scale=0.05), rnd(rs, Co)
@@ -64,17 +70,17 @@ def test_tc_conv_trio(dev, ref, case):
     # these shapes are the ones the tensor-core path must cover
     assert used == [2, 2, 2], used
     want = run(ref, "conv_fwd", [x, w, b], (N, OH, OW, Co), s, p)
-    got = run(dev, "conv_fwd", [x, w, b], (N, OH, OW, Co), s, p, "tc")
+    got = run(dev, "conv_fwd", [x, w, b], (N, OH, OW, Co), s, p, algo)
     assert relerr(got, want) < TOL, ("fwd", relerr(got, want))
     want = run(ref, "conv_bwd_data", [dy, w, bi], (N, H, W, Ci), s, p)
-    got = run(dev, "conv_bwd_data", [dy, w, bi], (N, H, W, Ci), s, p, "tc")
+    got = run(dev, "conv_bwd_data", [dy, w, bi], (N, H, W, Ci), s, p, algo)
     assert relerr(got, want) < TOL, ("bwd_data", relerr(got, want))
     want = run(ref, "conv_bwd_weight", [x, dy], (k, k, Ci, Co), s, p, False)
-    got = run(dev, "conv_bwd_weight", [x, dy], (k, k, Ci, Co), s, p, False, "tc")
+    got = run(dev, "conv_bwd_weight", [x, dy], (k, k, Ci, Co), s, p, False, algo)
     assert relerr(got, want) < TOL, ("bwd_weight", relerr(got, want))
     init = rnd(rs, k, k, Ci, Co)
     want = run(ref, "conv_bwd_weight", [x, dy], None, s, p, True, init=init)
-    got = run(dev, "conv_bwd_weight", [x, dy], None, s, p, True, "tc", init=init)
+    got = run(dev, "conv_bwd_weight", [x, dy], None, s, p, True, algo, init=init)
     assert relerr(got, want) < TOL, ("bwd_weight+acc", relerr(got, want))
 
 

@@ -97,4 +97,4 @@ def test_step_is_deterministic_enough_and_finite():
         outs.append(m.export_variables("var"))
     for k in outs[0]:
         assert np.isfinite(outs[0][k]).all(), k
-        assert np.abs(outs[0][k] - outs[1][k]).max() < 1e-6, k
+        assert np.abs(outs[0][k] - outs[1][k]).max() < 2e-5, k      # split-K atomics reorder fp32 sums
