@@ -71,7 +71,8 @@ __device__ __forceinline__ void sts128(uint32_t a, uint4 v) {
 //   mode 3 (EG_ALGO_TC3X): keep x as the "hi" operand and write lo = x - trunc(x) (exact in fp32) next to it;
 //                          hi*hi + lo*hi + hi*lo then carries ~21 mantissa bits (fp32-class accuracy).
 __device__ __forceinline__ uint32_t tf32_rna(uint32_t x) { return (x + 0x1000u) & 0xFFFFE000u; }
-__device__ __forceinline__ uint32_t tf32_lo(uint32_t x) { return __float_as_uint(__uint_as_float(x) - __uint_as_float(x & 0xFFFFE000u)); }
+// lo is rounded to nearest too: its own truncation would otherwise leave a biased 2^-20 relative residual
+__device__ __forceinline__ uint32_t tf32_lo(uint32_t x) { return tf32_rna(__float_as_uint(__uint_as_float(x) - __uint_as_float(x & 0xFFFFE000u))); }
 // elementwise pass over `bytes` of shared memory by 128 threads (the swizzle is irrelevant: same offset in/out)
 __device__ __forceinline__ void condition_tile(uint32_t src, uint32_t dst_lo, uint32_t bytes, int tid, int mode) {
     for (uint32_t off = (uint32_t)tid * 16u; off < bytes; off += 128u * 16u) {

@@ -91,17 +91,27 @@ instnorm_bwd2_k(const float* __restrict__ x, const float* __restrict__ stats, co
     float mean = 0.f, sd = 1.f;
     if (ok) { mean = stats[((size_t)n * C + c) * 2]; sd = stats[((size_t)n * C + c) * 2 + 1]; }
     const float r = 1.f / (sd + eps);
-    float v[5] = {0.f, 0.f, 0.f, 0.f, 0.f};   // sum gn, sum gn*c, sum t, sum t*c, sum t*gn
+    // pass 1: means of gn and t ; pass 2: centred second moments (a one-pass E[t*gn] - E[t]E[gn] cancels badly
+    // in fp32 and the penalty gradient amplifies that error ~1000x, see tools/parity_report.py)
+    float v0[2] = {0.f, 0.f};
+    if (ok) for (int p = threadIdx.y; p < P; p += RY) {
+        const size_t i = base + (size_t)p * C;
+        const float cc = x[i] - mean;
+        v0[0] += gy[i] * act_grad(act, cc * r); v0[1] += t[i];
+    }
+    reduce_cols<2>(v0, reinterpret_cast<float (*)[RY][CG]>(sm));
+    const float mg = v0[0] / P, mt = v0[1] / P;
+    float v[3] = {0.f, 0.f, 0.f};             // sum gn*c, sum t*c, sum (t-mt)*(gn-mg)
     if (ok) for (int p = threadIdx.y; p < P; p += RY) {
         const size_t i = base + (size_t)p * C;
         const float cc = x[i] - mean;
         const float gn = gy[i] * act_grad(act, cc * r);
         const float tt = t[i];
-        v[0] += gn; v[1] = fmaf(gn, cc, v[1]); v[2] += tt; v[3] = fmaf(tt, cc, v[3]); v[4] = fmaf(tt, gn, v[4]);
+        v[0] = fmaf(gn, cc, v[0]); v[1] = fmaf(tt, cc, v[1]); v[2] = fmaf(tt - mt, gn - mg, v[2]);
     }
-    reduce_cols<5>(v, sm);
+    reduce_cols<3>(v, reinterpret_cast<float (*)[RY][CG]>(sm));
     if (!ok) return;
-    const float mg = v[0] / P, q = v[1] / P, mt = v[2] / P, u = v[3] / P, w = v[4] / P - mt * mg;
+    const float q = v[0] / P, u = v[1] / P, w = v[2] / P;
     const float kap = r * r / sd;
     const float coef_c = -kap * w + (2.f * r * r * r / (sd * sd) + r * r / (sd * sd * sd)) * q * u;
     for (int p = threadIdx.y; p < P; p += RY) {
