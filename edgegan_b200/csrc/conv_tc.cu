@@ -198,16 +198,16 @@ struct TcParams {
     float* out;
 };
 
-template <int kStages>
-struct SmemLayout {
-    static constexpr int kATile = 128 * 128;          // 128 rows x 128 B
-    static constexpr int kBTileMax = 256 * 128;
-};
-
 // ---------------------------------------------------------------------------------------------------
 // forward / input-gradient kernel (both operands K-major)
 // ---------------------------------------------------------------------------------------------------
-template <int kStages>
+// kChunked (3xTF32 mode): the tensor core accumulates with truncation (measured: tools/tc_probe.py, the error of a
+// length-K chain grows ~K * 2^-24 with a sign bias), so the accumulation is cut into chunks of kChunkStages smem
+// stages that ping-pong between two TMEM accumulators; warps 2-5 drain each finished chunk into fp32 registers
+// with round-to-nearest adds while the next chunk is being multiplied.
+constexpr int kChunkStages = 4;
+
+template <int kStages, bool kChunked>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kmajor(const __grid_constant__ TcMaps maps, const __grid_constant__ TcParams P) {
     extern __shared__ uint8_t smem_raw[];
@@ -223,6 +223,8 @@ conv_tc_kmajor(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
     __shared__ __align__(8) uint64_t ready_bar[kStages];     // operands conditioned (4 warp arrivals)
     __shared__ __align__(8) uint64_t empty_bar[kStages];     // MMAs that read the stage have completed
     __shared__ __align__(8) uint64_t tmem_full_bar;
+    __shared__ __align__(8) uint64_t acc_full_bar[2];        // chunk accumulator complete (tcgen05.commit)
+    __shared__ __align__(8) uint64_t acc_empty_bar[2];       // chunk accumulator drained (4 warp arrivals)
     __shared__ uint32_t tmem_base_slot;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -234,7 +236,8 @@ conv_tc_kmajor(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
     const int w0 = tw * P.bw, h0 = th * P.bh, n0 = tn * P.bn;
     const int col0 = blockIdx.y * BN;
     const int niter = ph.ntaps * ph.kchunks;
-    const uint32_t tmem_cols = BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256));
+    const int acc_cols = kChunked ? 2 * BN : BN;
+    const uint32_t tmem_cols = acc_cols <= 32 ? 32 : (acc_cols <= 64 ? 64 : (acc_cols <= 128 ? 128 : 256));
 
     if (warp == 0 && lane == 0) {
         for (int i = 0; i < 4; ++i) prefetch_tmap(&maps.a[i]);
@@ -243,6 +246,7 @@ conv_tc_kmajor(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
             mbar_init(smem_u32(&full_bar[s]), 1); mbar_init(smem_u32(&ready_bar[s]), 4); mbar_init(smem_u32(&empty_bar[s]), 1);
         }
         mbar_init(smem_u32(&tmem_full_bar), 1);
+        for (int b = 0; b < 2; ++b) { mbar_init(smem_u32(&acc_full_bar[b]), 1); mbar_init(smem_u32(&acc_empty_bar[b]), 4); }
         fence_barrier_init();
     }
     if (warp == 1) { tmem_alloc(smem_u32(&tmem_base_slot), tmem_cols); tmem_relinquish(); }
@@ -274,28 +278,62 @@ conv_tc_kmajor(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
             const uint32_t idesc = make_idesc(128, BN, 0, 0);
             int stage = 0; uint32_t phase = 0;
             for (int it = 0; it < niter; ++it) {
+                uint32_t dst = tmem_base;
+                bool first = (it == 0);
+                if (kChunked) {
+                    const int c = it / kChunkStages, buf = c & 1;
+                    first = (it % kChunkStages == 0);
+                    dst = tmem_base + (uint32_t)(buf * BN);
+                    if (first && c >= 2) { mbar_wait(smem_u32(&acc_empty_bar[buf]), (uint32_t)(((c >> 1) - 1) & 1)); tc_fence_after(); }
+                }
                 mbar_wait(smem_u32(&ready_bar[stage]), phase);
                 tc_fence_after();
                 const uint32_t sa = smem_base + stage * stage_bytes;
                 const uint64_t ad = make_smem_desc(sa, 16, 1024), bd = make_smem_desc(sa + b_off, 16, 1024);
 #pragma unroll
                 for (int k = 0; k < 4; ++k)       // 4 x (K = 8 tf32 = 32 B) inside the 128-byte swizzle span
-                    umma_tf32(tmem_base, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, (it | k) != 0);
+                    umma_tf32(dst, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, !(first && k == 0));
                 if (mode == 3) {
                     const uint64_t ald = make_smem_desc(sa + a_lo_off, 16, 1024), bld = make_smem_desc(sa + b_lo_off, 16, 1024);
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) umma_tf32(tmem_base, ald + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, 1);
+                    for (int k = 0; k < 4; ++k) umma_tf32(dst, ald + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, 1);
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) umma_tf32(tmem_base, ad + (uint64_t)(k * 2), bld + (uint64_t)(k * 2), idesc, 1);
+                    for (int k = 0; k < 4; ++k) umma_tf32(dst, ad + (uint64_t)(k * 2), bld + (uint64_t)(k * 2), idesc, 1);
                 }
                 umma_commit(smem_u32(&empty_bar[stage]));
+                if (kChunked && (it % kChunkStages == kChunkStages - 1 || it == niter - 1))
+                    umma_commit(smem_u32(&acc_full_bar[(it / kChunkStages) & 1]));
                 if (++stage == kStages) { stage = 0; phase ^= 1; }
             }
-            umma_commit(smem_u32(&tmem_full_bar));
+            if (!kChunked) umma_commit(smem_u32(&tmem_full_bar));
         }
     } else {
-        // ===== warps 2..5: operand conditioning during the main loop, then the epilogue =====
+        // ===== warps 2..5: operand conditioning during the main loop (+ chunk draining), then the epilogue =====
         const int ctid = threadIdx.x - 64;
+        const int q = warp & 3;                                  // TMEM lane quarter this warp may access
+        float acc[kChunked ? 128 : 1];
+        if (kChunked) {
+#pragma unroll
+            for (int j = 0; j < (kChunked ? 128 : 1); ++j) acc[j] = 0.f;
+        }
+        auto drain = [&](int c) {                                // add chunk c's TMEM accumulator into registers
+            const int buf = c & 1;
+            mbar_wait(smem_u32(&acc_full_bar[buf]), (uint32_t)((c >> 1) & 1));
+            tc_fence_after();
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                if (g * 32 < BN) {
+                    uint32_t r[32];
+                    tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + g * 32), r);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) acc[kChunked ? g * 32 + j : 0] += __uint_as_float(r[j]);
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&acc_empty_bar[buf]));
+        };
         {
             int stage = 0; uint32_t phase = 0;
             for (int it = 0; it < niter; ++it) {
@@ -306,29 +344,44 @@ conv_tc_kmajor(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
                 __syncwarp();
                 if (lane == 0) mbar_arrive(smem_u32(&ready_bar[stage]));
                 if (++stage == kStages) { stage = 0; phase ^= 1; }
+                if (kChunked && (it % kChunkStages == kChunkStages - 1 || it == niter - 1)) {
+                    const int c = it / kChunkStages;
+                    if (c >= 1) drain(c - 1);                    // lag by one chunk: never wait on MMAs still in flight
+                }
             }
+            if (kChunked) drain((niter - 1) / kChunkStages);
         }
-        const int q = warp & 3;                                  // TMEM lane quarter this warp may access
         const int row = q * 32 + lane;
         const int wl = row % P.bw, hl = (row / P.bw) % P.bh, nl = row / (P.bw * P.bh);
         const int ow = w0 + wl, oh = h0 + hl, on = n0 + nl;
         const bool valid = ow < ph.ext_w && oh < ph.ext_h && on < ph.ext_n;
         float* orow = P.out + ph.out_off + (long long)on * ph.sn + (long long)oh * ph.sh + (long long)ow * ph.sw + col0;
-        mbar_wait(smem_u32(&tmem_full_bar), 0);
-        tc_fence_after();
-        for (int c = 0; c < BN; c += 32) {
-            uint32_t r[32];
-            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, r);
-            tmem_ld_wait();
-            if (valid) {
+        if (!kChunked) {
+            mbar_wait(smem_u32(&tmem_full_bar), 0);
+            tc_fence_after();
+        }
 #pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
-                    if (P.bias != nullptr) {
-                        const float4 bb = __ldg(reinterpret_cast<const float4*>(P.bias + col0 + c + j));
-                        v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
+        for (int g = 0; g < 4; ++g) {
+            const int c = g * 32;
+            if (c < BN) {
+                uint32_t r[32];
+                if (!kChunked) {
+                    tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, r);
+                    tmem_ld_wait();
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(acc[kChunked ? g * 32 + j : 0]);
+                }
+                if (valid) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+                        if (P.bias != nullptr) {
+                            const float4 bb = __ldg(reinterpret_cast<const float4*>(P.bias + col0 + c + j));
+                            v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
+                        }
+                        *reinterpret_cast<float4*>(orow + c + j) = v;
                     }
-                    *reinterpret_cast<float4*>(orow + c + j) = v;
                 }
             }
         }
@@ -586,7 +639,9 @@ constexpr int kStagesW = 3;
 bool g_attr_set = false;
 int set_attrs() {
     if (g_attr_set) return 0;
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_kmajor<kStagesK>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kmajor<kStagesK, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return eg_fail(e, __FILE__, __LINE__);
+    e = cudaFuncSetAttribute(conv_tc_kmajor<kStagesK, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return eg_fail(e, __FILE__, __LINE__);
     e = cudaFuncSetAttribute(conv_tc_wgrad<kStagesW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return eg_fail(e, __FILE__, __LINE__);
@@ -696,7 +751,8 @@ int eg_tc_conv2d_fwd(const eg_conv_shape* s, const float* x, const float* w, con
     ph.tiles_w = s->OW / P.bw; ph.tiles_h = s->OH / P.bh; ph.tiles_n = eg_ceil_div(s->N, P.bn);
     ph.out_off = 0; ph.sw = s->Co; ph.sh = (long long)s->OW * s->Co; ph.sn = (long long)s->OH * s->OW * s->Co;
     dim3 grid(ph.tiles_w * ph.tiles_h * ph.tiles_n, s->Co / P.BN, 1);
-    conv_tc_kmajor<kStagesK><<<grid, kThreads, kmajor_smem(P.BN, mode), st>>>(maps, P);
+    if (mode == 3) conv_tc_kmajor<kStagesK, true><<<grid, kThreads, kmajor_smem(P.BN, mode), st>>>(maps, P);
+    else           conv_tc_kmajor<kStagesK, false><<<grid, kThreads, kmajor_smem(P.BN, mode), st>>>(maps, P);
     EG_CHECK_LAUNCH();
     return 0;
 }
@@ -746,7 +802,8 @@ int eg_tc_conv2d_bwd_data(const eg_conv_shape* s, const float* dy, const float* 
             if (ph.ntaps == 0) return eg_fail_arg("dgrad phase without taps", __FILE__, __LINE__);
         }
     dim3 grid(max_tiles, s->Ci / P.BN, S * S);
-    conv_tc_kmajor<kStagesK><<<grid, kThreads, kmajor_smem(P.BN, mode), st>>>(maps, P);
+    if (mode == 3) conv_tc_kmajor<kStagesK, true><<<grid, kThreads, kmajor_smem(P.BN, mode), st>>>(maps, P);
+    else           conv_tc_kmajor<kStagesK, false><<<grid, kThreads, kmajor_smem(P.BN, mode), st>>>(maps, P);
     EG_CHECK_LAUNCH();
     return 0;
 }
@@ -784,6 +841,7 @@ int eg_tc_conv2d_bwd_weight(const eg_conv_shape* s, const float* x, const float*
     if (splits > ntiles) splits = ntiles;
     if (splits < 1) splits = 1;
     P.chunks_per_split = eg_ceil_div(ntiles, splits);
+    if (P.mode == 3 && P.chunks_per_split > 16) P.chunks_per_split = 16;   // bound the truncating accumulation chain
     splits = eg_ceil_div(ntiles, P.chunks_per_split);
     P.out = dw;
     if (!accumulate) {

@@ -42,6 +42,7 @@ class DeviceOps:
         self._bufs = {}
         self._shape_cache = {}
         self.launches = 0
+        self.pass_algo = {}          # debugging: per-pass algorithm override {'fwd'|'dgrad'|'wgrad': name}
 
     # ---- memory -----------------------------------------------------------------------------
     def empty(self, shape):
@@ -100,19 +101,19 @@ class DeviceOps:
         """y = conv(x, w) (+bias): x[N,H,W,Ci] w[KH,KW,Ci,Co] y[N,OH,OW,Co]; zero pad `pad` before."""
         s = self._cs(x.shape, w.shape, y.shape, stride, pad)
         self.launches += 1
-        _lib.check(self.lib.eg_conv2d_fwd(C.byref(s), _p(x), _p(w), _p(bias), _p(y), ALGO[algo], self._st), "conv2d_fwd")
+        _lib.check(self.lib.eg_conv2d_fwd(C.byref(s), _p(x), _p(w), _p(bias), _p(y), ALGO[algo or self.pass_algo.get("fwd")], self._st), "conv2d_fwd")
 
     def conv_bwd_data(self, dy, w, bias, dx, stride, pad, algo=None):
         """dx = conv input-gradient (== conv2d_transpose forward) (+bias over dx channels)."""
         s = self._cs(dx.shape, w.shape, dy.shape, stride, pad)
         self.launches += 1
-        _lib.check(self.lib.eg_conv2d_bwd_data(C.byref(s), _p(dy), _p(w), _p(bias), _p(dx), ALGO[algo], self._st), "conv2d_bwd_data")
+        _lib.check(self.lib.eg_conv2d_bwd_data(C.byref(s), _p(dy), _p(w), _p(bias), _p(dx), ALGO[algo or self.pass_algo.get("dgrad")], self._st), "conv2d_bwd_data")
 
     def conv_bwd_weight(self, x, dy, dw, stride, pad, accumulate=False, algo=None):
         """dw (+)= filter gradient."""
         s = self._cs(x.shape, dw.shape, dy.shape, stride, pad)
         self.launches += 2
-        _lib.check(self.lib.eg_conv2d_bwd_weight(C.byref(s), _p(x), _p(dy), _p(dw), int(accumulate), ALGO[algo], self._st), "conv2d_bwd_weight")
+        _lib.check(self.lib.eg_conv2d_bwd_weight(C.byref(s), _p(x), _p(dy), _p(dw), int(accumulate), ALGO[algo or self.pass_algo.get("wgrad")], self._st), "conv2d_bwd_weight")
 
     def bias_grad(self, dy, db, accumulate=False):
         Cn = dy.shape[-1]

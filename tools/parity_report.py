@@ -9,13 +9,19 @@ from parity_util import oracle_pair, cancelled, maxabs
 from test_step_gpu import make
 
 B = int(os.environ.get("B", "4"))
+SEED = int(os.environ.get("SEED", "11"))
+WSEED = int(os.environ.get("WSEED", "3"))
 algos = sys.argv[1:] or ["simt", "tc"]
 ocfg = O.Config(batch_size=B, multiclasses=False)
-v, u = O.init_variables(ocfg, seed=3)
-inp = O.make_inputs(ocfg, seed=11)
+v, u = O.init_variables(ocfg, seed=WSEED)
+inp = O.make_inputs(ocfg, seed=SEED)
 (st64, col64), (st32, col32) = oracle_pair(ocfg, v, u, inp)
 for algo in algos:
-    _, _, _, m, ops = make(B, False, algo)
+    _, _, _, m, ops = make(B, False, algo.split(":")[0], seed=WSEED)
+    if ":" in algo:       # e.g. simt:fwd=tc3x,wgrad=tc3x  -> per-pass override on top of the default
+        for kv in algo.split(":")[1].split(","):
+            k, val = kv.split("=")
+            ops.pass_algo[k] = val
     grads = {}
     m.run_hook = lambda run, model: grads.__setitem__(run, model.export_variables("grad"))
     m.update_model(ops.from_numpy(inp.images), ops.from_numpy(inp.z), ops.from_numpy(inp.alpha), inp.eps)
@@ -43,7 +49,7 @@ for algo in algos:
     print("weights (x lr):", ["%s e=%.3f noise=%.3f" % (r[2], r[0], r[1]) for r in rows[:5]])
     # inference
     ocfg1 = O.Config(batch_size=1, multiclasses=False)
-    _, _, _, m1, ops1 = make(1, False, algo)
+    _, _, _, m1, ops1 = make(1, False, algo.split(":")[0], seed=WSEED)
     x = np.random.RandomState(2333).uniform(-1, 1, (1, 64, 128, 3)).astype(np.float32)
     s64, s32 = O.OracleState(ocfg1, v, u, dtype=torch.float64), O.OracleState(ocfg1, v, u)
     for eps in (0.0, 1.0):

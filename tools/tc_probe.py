@@ -79,3 +79,24 @@ dev.conv_fwd(x, w, None, a, 1, 1, "tc"); dev.conv_fwd(xt, wt, None, b, 1, 1, "tc
 torch.cuda.synchronize()
 print("tf32 operand handling: raw vs pre-truncated inputs identical:", bool(torch.equal(a, b)),
       " max diff", float((a - b).abs().max()))
+
+# ---- accumulator precision: operands exactly representable in TF32 (multiples of 2^-8 below 4), so the only
+# error source is the fp32 accumulation inside the tensor core vs round-to-nearest FFMA chains
+import math
+print("accumulation test (tf32-exact operands): relerr vs fp64 for K = taps*Ci")
+for (N, H, W, Ci, Co, k) in ((2, 16, 16, 64, 64, 1), (2, 16, 16, 64, 64, 3), (2, 16, 16, 256, 64, 3), (2, 12, 12, 512, 64, 5)):
+    xh = (np.round(rs.uniform(-4, 4, (N, H, W, Ci)) * 256) / 256).astype(np.float32)
+    wh = (np.round(rs.uniform(-4, 4, (k, k, Ci, Co)) * 256) / 256).astype(np.float32)
+    x, w = dev.from_numpy(xh), dev.from_numpy(wh)
+    p = k // 2
+    xt = torch.from_numpy(xh).double().permute(0, 3, 1, 2)
+    wt = torch.from_numpy(wh).double().permute(3, 2, 0, 1)
+    want = torch.nn.functional.conv2d(xt, wt, padding=p).permute(0, 2, 3, 1).numpy()
+    out = {}
+    for algo in ("simt", "tc", "tc3x"):
+        y = dev.zeros((N, H, W, Co))
+        dev.conv_fwd(x, w, None, y, 1, p, algo)
+        torch.cuda.synchronize()
+        g = y.cpu().numpy().astype(np.float64)
+        out[algo] = (np.abs(g - want).max() / np.abs(want).max(), float(np.mean(np.sign(want) * (g - want))) / np.abs(want).max())
+    print(f"  K={k*k*Ci:5d}: " + "  ".join(f"{a}: max {e[0]:.2e} signed-mean {e[1]:+.2e}" for a, e in out.items()), flush=True)
