@@ -180,7 +180,7 @@ def main():
     if not multiclass:
         flags.num_classes = None
     ops = DeviceOps(f"cuda:{local}")
-    algo = "tc" if args.algo == "auto" else args.algo
+    algo = "tc3x" if args.algo == "auto" else args.algo
     ops.set_default_algo(algo)
     model = EdgeGAN(None, flags, None, ops=ops, comm=comm, seed=1234)
     model.build_train_model()

@@ -72,7 +72,7 @@ int eg_get_default_algo(void) { return g_default_algo; }
 
 static int resolve(int algo, int supported) {
     if (algo == EG_ALGO_AUTO) algo = g_default_algo;
-    if (algo == EG_ALGO_AUTO) algo = EG_ALGO_TC;
+    if (algo == EG_ALGO_AUTO) algo = EG_ALGO_TC3X;    // parity first: fp32-class accuracy on the tensor cores
     if (algo != EG_ALGO_SIMT && !supported) algo = EG_ALGO_SIMT;
     return algo;
 }

@@ -37,7 +37,7 @@ const char* eg_last_error(void);
 int eg_abi_version(void);
 int eg_device_info(int* sm_count, int* cc_major, int* cc_minor);
 
-/* What EG_ALGO_AUTO resolves to for layers the tensor-core kernels support (default EG_ALGO_TC);
+/* What EG_ALGO_AUTO resolves to for layers the tensor-core kernels support (default EG_ALGO_TC3X);
  * layers they do not support (thin channels) always take the fp32 SIMT kernel. */
 int eg_set_default_algo(int algo);
 int eg_get_default_algo(void);
