@@ -42,6 +42,7 @@ def parse():
     ap.add_argument("--multiclass", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile-pass", action="store_true")
+    ap.add_argument("--ncu", action="store_true", help="profiling run: warmup/steps as given, no e2e / cpu / roofline passes; the printed number is NOT a bench value")
     return ap.parse_args()
 
 
@@ -244,6 +245,12 @@ def main():
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    if args.ncu:
+        for k in range(args.warmup + args.steps):
+            step_resident(k)
+        torch.cuda.synchronize()
+        print(json.dumps({"ncu_run": True, "launches_per_step": ops.launches // (args.warmup + args.steps)}))
+        return
     ms_step, launches = timed(step_resident, args.steps, max(args.warmup, 3))
     clocks = sampler.stop() if rank == 0 else None
     ms_e2e, _ = timed(step_e2e, args.steps, 1)
