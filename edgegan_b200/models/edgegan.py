@@ -91,7 +91,11 @@ class EdgeGAN(object):
         self.encoder = Encoder("E", True, cfg.E_norm, image_size=cfg.input_height, latent_dim=self.z_dim,
                                ops=ops, store=self._store("E", encoder_specs("E", cfg.input_height, self.z_dim, self.c_dim), rs))
         if train and self.multiclass:
-            from .classifier import Classifier, classifier_specs
+            try:
+                from .classifier import Classifier, classifier_specs
+            except ImportError as e:
+                raise NotImplementedError("the multi-class classifier run (d_optim2, BASELINE configs[2:]) is not "
+                                          "built yet; use multiclasses=False") from e
             st = self._store("D2", classifier_specs("D2", cfg.num_classes, self.c_dim), rs)
             self.classifier = Classifier("D2", cfg.SPECTRAL_NORM_UPDATE_OPS, ops=ops, store=st, rs=rs,
                                          num_classes=cfg.num_classes)
@@ -325,7 +329,12 @@ class EdgeGAN(object):
 
     def read_losses(self):
         """host copy of the loss scalars of the last step (one device->host read)."""
-        host = self.ops.to_numpy(self.losses)
+        t = self.losses
+        if self.comm.world_size > 1:      # each rank holds its shard's share (already divided by the global batch)
+            t = self.ops.buf("step/losses_global", self.losses.shape)
+            self.ops.copy(self.losses, t)
+            self.comm.allreduce(t)
+        host = self.ops.to_numpy(t)
         return {k: float(host[i]) for k, i in LOSS_SLOTS.items()}
 
     # ---- inference (edgegan.py:492-517) -----------------------------------------------------------
