@@ -63,6 +63,20 @@ SIGNATURES = {
     "eg_relu_globalmean_bwd": [vp, vp, vp, i32, i32, i32, vp],
     "eg_reparam_fwd": [vp, vp, f32, vp, i64, vp],
     "eg_zl1_loss_bwd": [vp, vp, f32, vp, i32, i32, i32, f32, f32, vp, vp, vp, vp],
+    "eg_prelu_fwd": [vp, vp, vp, i64, vp],
+    "eg_prelu_bwd": [vp, vp, vp, vp, vp, i64, i32, vp],
+    "eg_minmax_fwd": [vp, vp, vp, i32, i32, i32, vp],
+    "eg_minmax_bwd": [vp, vp, vp, vp, i32, i32, i32, vp],
+    "eg_fma3": [vp, vp, vp, vp, i64, vp],
+    "eg_mul": [vp, vp, vp, i64, vp],
+    "eg_add_pool2_fwd": [vp, vp, vp, i32, i32, i32, i32, vp],
+    "eg_pool2_bwd": [vp, vp, i32, i32, i32, i32, i32, vp],
+    "eg_globalmean_fwd": [vp, vp, i32, i32, i32, vp],
+    "eg_globalmean_bwd": [vp, vp, i32, i32, i32, vp],
+    "eg_spectral_norm_ws_floats": [i32, i32],
+    "eg_spectral_norm_fwd": [vp, vp, vp, vp, i32, i32, vp],
+    "eg_spectral_norm_bwd": [vp, vp, vp, vp, vp, i32, i32, vp],
+    "eg_softmax_ce_bwd": [vp, vp, i32, i32, i32, i32, i32, f32, f32, vp, vp, vp],
     "eg_onehot_concat": [vp, i32, i32, i32, vp, vp],
     "eg_rmsprop": [vp, vp, vp, i64, f32, f32, f32, vp],
 }

@@ -50,6 +50,7 @@ __device__ __forceinline__ float act_fwd(int act, float x) {
         case EG_ACT_LRELU_BLOCK: return x >= 0.f ? x : 0.2f * x;   // tf.maximum(x, 0.2x)
         case EG_ACT_TANH: return tanhf(x);
         case EG_ACT_SIGMOID: return 1.f / (1.f + expf(-x));
+        case EG_ACT_LRELU: return x > 0.f ? x : 0.2f * x;            // tf.maximum(0.2x, x)
         default: return x;
     }
 }
@@ -60,6 +61,7 @@ __device__ __forceinline__ float act_grad(int act, float x) {
         case EG_ACT_LRELU_BLOCK: return x >= 0.f ? 1.f : 0.2f;
         case EG_ACT_TANH: { float t = tanhf(x); return 1.f - t * t; }
         case EG_ACT_SIGMOID: { float s = 1.f / (1.f + expf(-x)); return s * (1.f - s); }
+        case EG_ACT_LRELU: return x > 0.f ? 1.f : 0.2f;              // tie at 0 -> first argument (0.2x)
         default: return 1.f;
     }
 }

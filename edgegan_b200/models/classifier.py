@@ -1,0 +1,304 @@
+"""Multi-class classifier D2 (reference edgegan/models/classifier.py:7-119; MRU block nn/modules/conv.py:133-243,
+298-357; conv2d2 conv.py:246-295; fully_connected linear.py:34-76; spectral norm normalization.py:38-76) with
+explicit backward passes.
+
+Structure (hidden, filter) = (8,128), (128,256), (256,512), (512,768), one MRU unit per pyramid level:
+    h0   = prelu(SNconv7x7(x, 3->8) + b)
+    unit: a_in = prelu(ht);  full = concat(a_in, inp)                  inp = image mean-pooled to ht's resolution
+          rg   = minmax_HW(lrelu(SNconv3x3(full -> hd) + b))           (update gate, bias init 0.5)
+          img  = SNconv3x3(inp -> hd) + b
+          hin  = prelu(ht + rg * img)
+          hn   = SNconv3x3(prelu(SNconv3x3(hin -> fd) + b) -> fd) + b
+          ht'  = mean_pool(SNconv1x1(ht -> fd) + b + hn)
+    logits = SNfc(mean_HW(prelu(ht_4))) + b
+The reference runs this network in NCHW (classifier.py:13); that is an API-only layout: EdgeGAN transposes its
+NHWC tensors right before the call (edgegan.py:28-29,231), so the NHWC tensors are consumed directly here and
+`__call__` accepts the reference's NCHW view.  The 1x1 "disc" head (classifier.py:107-109) is built but never
+used by any loss; its variables exist (and stay at their initial values) for variable-list compatibility.
+
+Every weight is spectrally normalised with ONE power iteration from a frozen `u` that the reference never
+updates; the gradient flows through sigma (eg_spectral_norm_bwd).
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+
+from ..variables import ParamStore, VarSpec
+
+UNITS = ((8, 128), (128, 256), (256, 512), (512, 768))
+
+
+def _conv_specs(scope, k, ci, co, bias_init=0.0, prelu=False):
+    v = [VarSpec(f"{scope}/weights", (k, k, ci, co), "normal"),
+         VarSpec(f"{scope}/biases", (1, co, 1, 1), "const", value=bias_init)]
+    if prelu:
+        v.append(VarSpec(f"{scope}/prelu/param", (), "const", value=0.2))
+    return v
+
+
+def classifier_specs(name, num_classes=14, c_dim=3):
+    """trainables that receive gradients, in the reference's creation order"""
+    v = _conv_specs(f"{name}/Conv", 7, c_dim, 8, prelu=True)
+    for t, (hd, fd) in enumerate(UNITS, start=1):
+        p = f"{name}/mru_conv_unit_t_{t}_layer_0"
+        v.append(VarSpec(f"{p}/norm_activation_in/prelu/param", (), "const", value=0.2))
+        v += _conv_specs(f"{p}/update_gate", 3, hd + c_dim, hd, bias_init=0.5)
+        v += _conv_specs(f"{p}/Conv", 3, c_dim, hd)
+        v.append(VarSpec(f"{p}/norm_activation_merge_1/prelu/param", (), "const", value=0.2))
+        v += _conv_specs(f"{p}/Conv_1", 3, hd, fd, prelu=True)
+        v += _conv_specs(f"{p}/Conv_2", 3, fd, fd)
+        v += _conv_specs(f"{p}/Conv_3", 1, hd, fd)
+    v.append(VarSpec(f"{name}/mru_conv_unit_last_norm/prelu/param", (), "const", value=0.2))
+    lim = math.sqrt(6.0 / (768 + num_classes))
+    v.append(VarSpec(f"{name}/fully_connected/weights", (768, num_classes), "uniform", std=lim))
+    v.append(VarSpec(f"{name}/fully_connected/biases", (num_classes,), "zeros"))
+    return v
+
+
+def classifier_aux_specs(name, num_classes=14, c_dim=3):
+    """variables no gradient reaches: the unused disc head and the frozen spectral-norm vectors u [1, Cout]"""
+    v = _conv_specs(f"{name}/Conv_1", 1, 768, 1)
+    for s in classifier_specs(name, num_classes, c_dim) + v[:1]:
+        if s.name.endswith("/weights"):
+            v.append(VarSpec(s.name[:-len("weights")] + "u", (1, s.shape[-1]), "trunc_normal", std=1.0))
+    return v
+
+
+class Classifier(object):
+    def __init__(self, name, SPECTRAL_NORM_UPDATE_OPS="spectral_norm_update_ops", *, ops=None, store=None, rs=None,
+                 num_classes=14, c_dim=3):
+        self.name, self.ops, self.store = name, ops, store
+        self.SPECTRAL_NORM_UPDATE_OPS = SPECTRAL_NORM_UPDATE_OPS
+        self.num_classes, self.c_dim = num_classes, c_dim
+        self.aux = ParamStore(ops, classifier_aux_specs(name, num_classes, c_dim), rs or np.random.RandomState(0))
+        self.var_list = store.names() + [n for n in self.aux.names() if not n.endswith("/u")]
+        self.layers = [s.name[:-len("/weights")] for s in store.specs if s.name.endswith("/weights")]
+        self._wbar_valid = False
+        self.cache = None
+        biggest = max(int(np.prod(s.shape)) for s in store.specs if s.name.endswith("/weights"))
+        self._gbar = ops.buf(f"{name}/gbar", (biggest,))       # dL/dWbar scratch shared by all layers
+
+    # ---- variables -----------------------------------------------------------------------------------
+    def load_u(self, values):
+        sub = {k: v for k, v in values.items() if k in self.aux.offsets}
+        if sub:
+            self.aux.load(sub, strict=False)
+        self._wbar_valid = False
+
+    def invalidate(self):
+        self._wbar_valid = False
+
+    def _v(self, s):
+        return self.store.var[f"{self.name}/{s}"]
+
+    def _g(self, s):
+        return self.store.g[f"{self.name}/{s}"]
+
+    def _normalise_weights(self):
+        """Wbar = W / sigma(W) for every layer (normalization.py:38-76); cached until the weights change."""
+        if self._wbar_valid:
+            return
+        ops = self.ops
+        self.wbar, self.ws = {}, {}
+        for scope in self.layers:
+            W = self.store.var[scope + "/weights"]
+            Cn = W.shape[-1]
+            K = W.numel() // Cn
+            wb = ops.buf(scope + "/wbar", W.shape)
+            ws = ops.buf(scope + "/sn_ws", (ops.sn_ws_floats(K, Cn),))
+            ops.spectral_norm_fwd(W, self.aux.var[scope + "/u"], wb, ws)
+            self.wbar[scope], self.ws[scope] = wb, ws
+        self._wbar_valid = True
+
+    # ---- forward -------------------------------------------------------------------------------------
+    def _conv(self, scope, x, y, k):
+        full = f"{self.name}/{scope}"
+        self.ops.conv_fwd(x, self.wbar[full], self.store.var[full + "/biases"].view(-1), y, 1, (k - 1) // 2)
+
+    def forward(self, x, tag="fwd"):
+        """x [n,S,S,3] NHWC -> logits [n, num_classes]"""
+        ops, nm = self.ops, self.name
+        self._normalise_weights()
+        n, S = x.shape[0], x.shape[1]
+        B = lambda key, shape: ops.buf(f"{nm}/{tag}/{key}", shape)
+        pyr = [x]
+        for l in range(1, 4):
+            p = B(f"pyr{l}", (n, S >> l, S >> l, self.c_dim))
+            ops.add_pool2_fwd(pyr[-1], None, p)
+            pyr.append(p)
+        c0 = B("c0", (n, S, S, 8))
+        self._conv("Conv", x, c0, 7)
+        ht = B("h0", c0.shape)
+        ops.prelu_fwd(c0, self._v("Conv/prelu/param"), ht)
+        units = []
+        for t, (hd, fd) in enumerate(UNITS, start=1):
+            p = f"mru_conv_unit_t_{t}_layer_0"
+            inp = pyr[t - 1]
+            H = inp.shape[1]
+            U = lambda key, c: B(f"u{t}/{key}", (n, H, H, c))
+            a_in = U("a_in", hd)
+            ops.prelu_fwd(ht, self._v(f"{p}/norm_activation_in/prelu/param"), a_in)
+            full = U("full", hd + self.c_dim)
+            ops.copy_cslice(a_in, 0, full, 0, hd)
+            ops.copy_cslice(inp, 0, full, hd, self.c_dim)
+            cg, rgl, rg = U("cg", hd), U("rgl", hd), U("rg", hd)
+            self._conv(f"{p}/update_gate", full, cg, 3)
+            ops.act_fwd(cg, rgl, "lrelu2")
+            mm = B(f"u{t}/mm", (n, hd, 2))
+            ops.minmax_fwd(rgl, rg, mm)
+            img = U("img", hd)
+            self._conv(f"{p}/Conv", inp, img, 3)
+            plus, hin = U("plus", hd), U("hin", hd)
+            ops.fma3(ht, rg, img, plus)
+            ops.prelu_fwd(plus, self._v(f"{p}/norm_activation_merge_1/prelu/param"), hin)
+            c1, hn1, hn2, ho = U("c1", fd), U("hn1", fd), U("hn2", fd), U("ho", fd)
+            self._conv(f"{p}/Conv_1", hin, c1, 3)
+            ops.prelu_fwd(c1, self._v(f"{p}/Conv_1/prelu/param"), hn1)
+            self._conv(f"{p}/Conv_2", hn1, hn2, 3)
+            self._conv(f"{p}/Conv_3", ht, ho, 1)
+            out = B(f"u{t}/out", (n, H // 2, H // 2, fd))
+            ops.add_pool2_fwd(ho, hn2, out)
+            units.append(dict(p=p, hd=hd, fd=fd, ht=ht, inp=inp, a_in=a_in, full=full, cg=cg, rgl=rgl, rg=rg, mm=mm,
+                              img=img, plus=plus, hin=hin, c1=c1, hn1=hn1))
+            ht = out
+        hl = B("hlast", ht.shape)
+        ops.prelu_fwd(ht, self._v("mru_conv_unit_last_norm/prelu/param"), hl)
+        feat = B("feat", (n, ht.shape[3]))
+        ops.globalmean_fwd(hl, feat)
+        logits = B("logits", (n, self.num_classes))
+        C = feat.shape[1]
+        ops.conv_fwd(feat.view(n, 1, 1, C), self.wbar[f"{nm}/fully_connected"].view(1, 1, C, self.num_classes),
+                     self._v("fully_connected/biases"), logits.view(n, 1, 1, self.num_classes), 1, 0)
+        self.cache = dict(x=x, pyr=pyr, c0=c0, units=units, ht_last=ht, hl=hl, feat=feat, logits=logits, n=n, tag=tag)
+        return logits
+
+    def __call__(self, x, num_classes=None, labels=None, reuse=False, data_format="NCHW"):
+        """Reference signature (classifier.py:12): x NCHW view of an NHWC buffer -> (disc, prob, logits).
+        `disc` (the unused head) is not computed."""
+        assert data_format == "NCHW"
+        xn = x.permute(0, 2, 3, 1)
+        if not xn.is_contiguous():
+            raise ValueError("pass the NCHW *view* of an NHWC buffer (edgegan.py:28-29 transposes right before the call)")
+        logits = self.forward(xn, "call")
+        prob = self.ops.buf(f"{self.name}/call/prob", logits.shape)
+        self.ops.act_fwd(logits, prob, "sigmoid")
+        return None, prob, logits
+
+    # ---- backward ------------------------------------------------------------------------------------
+    def _wgrad(self, scope, x, dy, k, tag):
+        """dL/dWbar by the conv filter-gradient kernel, then through the spectral norm into the gradient store"""
+        ops, full = self.ops, f"{self.name}/{scope}"
+        W = self.store.var[full + "/weights"]
+        gbar = self._gbar[:W.numel()].view(W.shape)
+        ops.conv_bwd_weight(x, dy, gbar, 1, (k - 1) // 2, False)
+        ops.spectral_norm_bwd(W, self.aux.var[full + "/u"], self.ws[full], gbar, self.store.g[full + "/weights"])
+        ops.bias_grad(dy, self.store.g[full + "/biases"].view(-1), False)
+
+    def backward(self, glogits, param_grads, input_grad, tag="bwd"):
+        ops, nm, c = self.ops, self.name, self.cache
+        n = c["n"]
+        B = lambda key, shape: ops.buf(f"{nm}/{tag}/{key}", shape)
+        feat, hl, ht = c["feat"], c["hl"], c["ht_last"]
+        C, K = feat.shape[1], self.num_classes
+        fc = f"{nm}/fully_connected"
+        if param_grads:
+            Wfc = self.store.var[fc + "/weights"]
+            gbar = self._gbar[:Wfc.numel()].view(Wfc.shape)
+            ops.conv_bwd_weight(feat.view(n, 1, 1, C), glogits.view(n, 1, 1, K), gbar.view(1, 1, C, K), 1, 0, False)
+            ops.spectral_norm_bwd(Wfc, self.aux.var[fc + "/u"], self.ws[fc], gbar, self.store.g[fc + "/weights"])
+            ops.bias_grad(glogits, self._g("fully_connected/biases"), False)
+        gfeat = B("gfeat", feat.shape)
+        ops.conv_bwd_data(glogits.view(n, 1, 1, K), self.wbar[fc].view(1, 1, C, K), None, gfeat.view(n, 1, 1, C), 1, 0)
+        ghl = B("ghl", hl.shape)
+        ops.globalmean_bwd(gfeat, ghl)
+        g_out = B("g_ht4", ht.shape)
+        ops.prelu_bwd(ht, self._v("mru_conv_unit_last_norm/prelu/param"), ghl, g_out,
+                      self._g("mru_conv_unit_last_norm/prelu/param") if param_grads else None)
+        g_pyr = [None] * 4
+        for t in range(4, 0, -1):
+            u = c["units"][t - 1]
+            p, hd, fd, htu, inp = u["p"], u["hd"], u["fd"], u["ht"], u["inp"]
+            H = inp.shape[1]
+            U = lambda key, ch: B(f"u{t}/{key}", (n, H, H, ch))
+            g_sum = U("g_sum", fd)
+            ops.pool2_bwd(g_out, g_sum, False)
+            wb = lambda s: self.wbar[f"{nm}/{p}/{s}"]
+            # ho = Conv_3(ht), hn2 = Conv_2(hn1)
+            g_ht, g_hn1 = U("g_ht", hd), U("g_hn1", fd)
+            if param_grads:
+                self._wgrad(f"{p}/Conv_3", htu, g_sum, 1, tag)
+                self._wgrad(f"{p}/Conv_2", u["hn1"], g_sum, 3, tag)
+            ops.conv_bwd_data(g_sum, wb("Conv_3"), None, g_ht, 1, 0)
+            ops.conv_bwd_data(g_sum, wb("Conv_2"), None, g_hn1, 1, 1)
+            g_c1 = U("g_c1", fd)
+            ops.prelu_bwd(u["c1"], self._v(f"{p}/Conv_1/prelu/param"), g_hn1, g_c1,
+                          self._g(f"{p}/Conv_1/prelu/param") if param_grads else None)
+            if param_grads:
+                self._wgrad(f"{p}/Conv_1", u["hin"], g_c1, 3, tag)
+            g_hin, g_plus = U("g_hin", hd), U("g_plus", hd)
+            ops.conv_bwd_data(g_c1, wb("Conv_1"), None, g_hin, 1, 1)
+            ops.prelu_bwd(u["plus"], self._v(f"{p}/norm_activation_merge_1/prelu/param"), g_hin, g_plus,
+                          self._g(f"{p}/norm_activation_merge_1/prelu/param") if param_grads else None)
+            # plus = ht + rg * img
+            ops.axpby(g_plus, g_ht, 1.0, 1.0)
+            g_rg, g_img = U("g_rg", hd), U("g_img", hd)
+            ops.mul(g_plus, u["img"], g_rg)
+            ops.mul(g_plus, u["rg"], g_img)
+            if param_grads:
+                self._wgrad(f"{p}/Conv", inp, g_img, 3, tag)
+            g_rgl, g_cg = U("g_rgl", hd), U("g_cg", hd)
+            ops.minmax_bwd(u["rgl"], u["mm"], g_rg, g_rgl)
+            ops.act_bwd(u["cg"], g_rgl, g_cg, "lrelu2")
+            if param_grads:
+                self._wgrad(f"{p}/update_gate", u["full"], g_cg, 3, tag)
+            g_full = U("g_full", hd + self.c_dim)
+            ops.conv_bwd_data(g_cg, wb("update_gate"), None, g_full, 1, 1)
+            g_ain, g_ht2 = U("g_ain", hd), U("g_ht2", hd)
+            ops.copy_cslice(g_full, 0, g_ain, 0, hd)
+            ops.prelu_bwd(htu, self._v(f"{p}/norm_activation_in/prelu/param"), g_ain, g_ht2,
+                          self._g(f"{p}/norm_activation_in/prelu/param") if param_grads else None)
+            ops.axpby(g_ht2, g_ht, 1.0, 1.0)
+            if input_grad:
+                gi = B(f"g_pyr{t - 1}", inp.shape)
+                ops.conv_bwd_data(g_img, wb("Conv"), None, gi, 1, 1)
+                gi2 = U("g_inp2", self.c_dim)
+                ops.copy_cslice(g_full, hd, gi2, 0, self.c_dim)
+                ops.axpby(gi2, gi, 1.0, 1.0)
+                g_pyr[t - 1] = gi
+            g_out = g_ht
+        # h0 = prelu(Conv(x))
+        g_c0 = B("g_c0", c["c0"].shape)
+        ops.prelu_bwd(c["c0"], self._v("Conv/prelu/param"), g_out, g_c0, self._g("Conv/prelu/param") if param_grads else None)
+        if param_grads:
+            self._wgrad("Conv", c["x"], g_c0, 7, tag)
+        if not input_grad:
+            return None
+        for l in range(3, 0, -1):                      # pyramid: pyr[l] = mean_pool(pyr[l-1])
+            ops.pool2_bwd(g_pyr[l], g_pyr[l - 1], True)
+        gx = g_pyr[0]
+        gx7 = B("g_x7", c["x"].shape)
+        ops.conv_bwd_data(g_c0, self.wbar[f"{nm}/Conv"], None, gx7, 1, 3)
+        ops.axpby(gx7, gx, 1.0, 1.0)
+        return gx
+
+    # ---- the two uses in the step ----------------------------------------------------------------------
+    def real_loss_step(self, real_pic, z, inv_global_batch, loss):
+        """run 4 (d_optim2): focal loss of the REAL image (functional.py:8-11), gradients of every D2 trainable."""
+        ops = self.ops
+        logits = self.forward(real_pic, "real")
+        gl = ops.buf(f"{self.name}/real/glogits", logits.shape)
+        ops.fill(loss, 0.0)
+        ops.softmax_ce_bwd(logits, z, z.shape[1] - 1, True, 1.0, inv_global_batch, gl, loss)
+        self.backward(gl, param_grads=True, input_grad=False, tag="real_bwd")
+        self._wbar_valid = False          # the caller applies RMSProp next
+
+    def fake_loss_input_grad(self, fake, z, weight, inv_global_batch, loss):
+        """runs 5/7: weight * mean CE(C(G2(z)), class) (functional.py:13-15) and its gradient w.r.t. the image."""
+        ops = self.ops
+        logits = self.forward(fake, "fake")
+        gl = ops.buf(f"{self.name}/fake/glogits", logits.shape)
+        ops.fill(loss, 0.0)
+        ops.softmax_ce_bwd(logits, z, z.shape[1] - 1, False, weight, inv_global_batch, gl, loss)
+        return self.backward(gl, param_grads=False, input_grad=True, tag="fake_bwd")

@@ -99,6 +99,7 @@ class EdgeGAN(object):
             st = self._store("D2", classifier_specs("D2", cfg.num_classes, self.c_dim), rs)
             self.classifier = Classifier("D2", cfg.SPECTRAL_NORM_UPDATE_OPS, ops=ops, store=st, rs=rs,
                                          num_classes=cfg.num_classes)
+            self.stores["D2/aux"] = self.classifier.aux      # unused disc head + frozen spectral-norm vectors
         self.losses = ops.zeros((16,))
         self._built = "train" if train else "test"
 
@@ -114,7 +115,7 @@ class EdgeGAN(object):
             sub = {k: v for k, v in values.items() if k in st.offsets}
             st.load(sub, strict=strict)
         if hasattr(self, "classifier"):
-            self.classifier.load_u(values)
+            self.classifier.invalidate()
 
     def export_variables(self, what="var"):
         out = {}

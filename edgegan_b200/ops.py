@@ -17,7 +17,7 @@ import torch
 from . import _lib
 from ._lib import ConvShape
 
-ACT = {None: 0, "none": 0, "relu": 1, "lrelu": 2, "tanh": 3, "sigmoid": 4}
+ACT = {None: 0, "none": 0, "relu": 1, "lrelu": 2, "tanh": 3, "sigmoid": 4, "lrelu2": 5}
 ALGO = {None: 0, "auto": 0, "simt": 1, "tc": 2, "tc3x": 3}
 IN_EPS = 1e-5      # normalization.py:15
 BN_EPS = 1e-5      # normalization.py:11 (epsilon default)
@@ -284,6 +284,79 @@ class DeviceOps:
     def onehot_concat(self, z, zdim, classes, out):
         self.launches += 1
         _lib.check(self.lib.eg_onehot_concat(_p(z), z.shape[0], zdim, classes, _p(out), self._st), "onehot_concat")
+
+    # ---- classifier pieces ------------------------------------------------------------------------
+    def prelu_fwd(self, x, leak, y):
+        self.launches += 1
+        _lib.check(self.lib.eg_prelu_fwd(_p(x), _p(leak), _p(y), x.numel(), self._st), "prelu_fwd")
+
+    def prelu_bwd(self, x, leak, gy, gx, gleak, accumulate_leak=False):
+        self.launches += 1
+        _lib.check(self.lib.eg_prelu_bwd(_p(x), _p(leak), _p(gy), _p(gx), _p(gleak), x.numel(), int(accumulate_leak), self._st), "prelu_bwd")
+
+    def minmax_fwd(self, x, y, stats):
+        N, P, Cn = self._npc(x)
+        self.launches += 1
+        _lib.check(self.lib.eg_minmax_fwd(_p(x), _p(y), _p(stats), N, P, Cn, self._st), "minmax_fwd")
+
+    def minmax_bwd(self, x, stats, gy, gx):
+        N, P, Cn = self._npc(x)
+        self.launches += 1
+        _lib.check(self.lib.eg_minmax_bwd(_p(x), _p(stats), _p(gy), _p(gx), N, P, Cn, self._st), "minmax_bwd")
+
+    def fma3(self, a, b, c, out):
+        self.launches += 1
+        _lib.check(self.lib.eg_fma3(_p(a), _p(b), _p(c), _p(out), a.numel(), self._st), "fma3")
+
+    def mul(self, a, b, out):
+        self.launches += 1
+        _lib.check(self.lib.eg_mul(_p(a), _p(b), _p(out), a.numel(), self._st), "mul")
+
+    def add_pool2_fwd(self, a, b, y):
+        N, H, W, Cn = a.shape
+        self.launches += 1
+        _lib.check(self.lib.eg_add_pool2_fwd(_p(a), _p(b), _p(y), N, H, W, Cn, self._st), "add_pool2_fwd")
+
+    def pool2_bwd(self, gy, gx, accumulate=False):
+        N, H, W, Cn = gx.shape
+        self.launches += 1
+        _lib.check(self.lib.eg_pool2_bwd(_p(gy), _p(gx), N, H, W, Cn, int(accumulate), self._st), "pool2_bwd")
+
+    def globalmean_fwd(self, x, y):
+        N, P, Cn = self._npc(x)
+        self.launches += 1
+        _lib.check(self.lib.eg_globalmean_fwd(_p(x), _p(y), N, P, Cn, self._st), "globalmean_fwd")
+
+    def globalmean_bwd(self, gy, gx):
+        N, P, Cn = self._npc(gx)
+        self.launches += 1
+        _lib.check(self.lib.eg_globalmean_bwd(_p(gy), _p(gx), N, P, Cn, self._st), "globalmean_bwd")
+
+    def sn_ws_floats(self, K, Cn):
+        return int(self.lib.eg_spectral_norm_ws_floats(K, Cn))
+
+    def spectral_norm_fwd(self, W, u, Wbar, ws):
+        Cn = W.shape[-1]
+        self.launches += 4
+        _lib.check(self.lib.eg_spectral_norm_fwd(_p(W), _p(u), _p(Wbar), _p(ws), W.numel() // Cn, Cn, self._st), "spectral_norm_fwd")
+
+    def spectral_norm_bwd(self, W, u, ws, Gbar, gW):
+        Cn = W.shape[-1]
+        self.launches += 4
+        _lib.check(self.lib.eg_spectral_norm_bwd(_p(W), _p(u), _p(ws), _p(Gbar), _p(gW), W.numel() // Cn, Cn, self._st), "spectral_norm_bwd")
+
+    def softmax_ce_bwd(self, logits, z, label_col, focal, weight, inv_global_batch, glogits, loss):
+        B, Cn = logits.shape
+        self.launches += 1
+        _lib.check(self.lib.eg_softmax_ce_bwd(_p(logits), _p(z), z.shape[1], label_col, B, Cn, int(focal), float(weight),
+                                              float(inv_global_batch), _p(glogits), _p(loss), self._st), "softmax_ce_bwd")
+
+    def copy_cslice(self, src, src_c0, dst, dst_c0, width):
+        """dst[..., dst_c0:dst_c0+width] = src[..., src_c0:src_c0+width]  (channel slices / tf.concat on channels)"""
+        Cs, Cd = src.shape[-1], dst.shape[-1]
+        rows = src.numel() // Cs
+        self.launches += 1
+        _lib.check(self.lib.eg_copy2d(src.data_ptr() + 4 * src_c0, Cs, dst.data_ptr() + 4 * dst_c0, Cd, rows, width, self._st), "copy2d")
 
     # ---- optimizer ----------------------------------------------------------------------------------
     def rmsprop(self, var, grad, ms, lr, decay=0.9, eps=1e-10):

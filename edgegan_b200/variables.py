@@ -37,6 +37,8 @@ class VarSpec:
             return np.full(self.shape, self.value, np.float32)
         if self.init == "normal":              # tf.random_normal_initializer(stddev)
             return rs.normal(0.0, self.std, size=self.shape).astype(np.float32)
+        if self.init == "uniform":             # xavier-style uniform(-std, std) (linear.py:36)
+            return rs.uniform(-self.std, self.std, size=self.shape).astype(np.float32)
         if self.init == "trunc_normal":        # tf.truncated_normal_initializer: redraw beyond 2 sigma
             x = rs.normal(0.0, self.std, size=self.shape)
             bad = np.abs(x) > 2 * self.std

@@ -26,6 +26,7 @@ extern "C" {
 #define EG_ACT_LRELU_BLOCK 2 /* tf.maximum(x, 0.2x): slope 1 at x == 0 (activation.py:9) */
 #define EG_ACT_TANH 3
 #define EG_ACT_SIGMOID 4     /* discriminator.py:81 (the `prob` output) */
+#define EG_ACT_LRELU 5       /* nn.lrelu = tf.maximum(0.2x, x): slope 0.2 at x == 0 (activation.py:30-32) */
 
 /* conv algorithm selector */
 #define EG_ALGO_AUTO 0
@@ -151,6 +152,38 @@ int eg_reparam_fwd(const float* mu, const float* ls, float eps, float* z, long l
  * target has row stride `target_stride` (z carries a trailing class-id column in multi-class mode) */
 int eg_zl1_loss_bwd(const float* mu, const float* ls, float eps, const float* target, int target_stride, int B,
                     int Z, float weight, float inv_global_count, float* gmu, float* gls, float* loss, void* stream);
+
+/* ---- multi-class classifier D2 (models/classifier.py:12-119, nn/modules/conv.py:133-357) ---------------- */
+/* prelu: tf.maximum(leak*x, x) with a learned scalar leak held in device memory (activation.py:23-27).
+ * bwd: gx = gy * (leak*x >= x ? leak : 1) (gx may be NULL); gleak[0] (= or +=) sum gy*x*[leak*x >= x] (may be NULL) */
+int eg_prelu_fwd(const float* x, const float* leak, float* y, long long n, void* stream);
+int eg_prelu_bwd(const float* x, const float* leak, const float* gy, float* gx, float* gleak, long long n,
+                 int accumulate_leak, void* stream);
+/* update-gate normalisation (conv.py:197-198): y = (x - min)/(max - min) over H,W per (n,c); stats[N,C,2] =
+ * (min, max); bwd sends the min / max terms to the arg-extrema, split evenly between ties */
+int eg_minmax_fwd(const float* x, float* y, float* stats, int N, int P, int C, void* stream);
+int eg_minmax_bwd(const float* x, const float* stats, const float* gy, float* gx, int N, int P, int C, void* stream);
+/* out = a + b*c  (ht + rg*img_new, conv.py:209) ; out = a*b */
+int eg_fma3(const float* a, const float* b, const float* c, float* out, long long n, void* stream);
+int eg_mul(const float* a, const float* b, float* out, long long n, void* stream);
+/* y = mean_pool2x2(a + b) (b may be NULL; pooling.py:4-8 after conv.py:236); gx (= or +=) pooled-gradient ;
+ * y[n,c] = mean_p x[n,p,c] (classifier.py:111) and its gradient */
+int eg_add_pool2_fwd(const float* a, const float* b, float* y, int N, int H, int W, int C, void* stream);
+int eg_pool2_bwd(const float* gy, float* gx, int N, int H, int W, int C, int accumulate, void* stream);
+int eg_globalmean_fwd(const float* x, float* y, int N, int P, int C, void* stream);
+int eg_globalmean_bwd(const float* gy, float* gx, int N, int P, int C, void* stream);
+/* spectral normalisation with ONE power iteration from a frozen u (normalization.py:38-76):
+ * W viewed as [K, C]; v = l2n(u W^T), u' = l2n(v W), sigma = v W u'^T, Wbar = W / sigma.  `ws` holds
+ * eg_spectral_norm_ws_floats(K, C) floats and carries the forward's intermediates to the backward, which maps
+ * Gbar = dL/dWbar to gW = dL/dW THROUGH sigma, v and u' (no stop_gradient in the reference). */
+int eg_spectral_norm_ws_floats(int K, int C);
+int eg_spectral_norm_fwd(const float* W, const float* u, float* Wbar, float* ws, int K, int C, void* stream);
+int eg_spectral_norm_bwd(const float* W, const float* u, float* ws, const float* Gbar, float* gW, int K, int C,
+                         void* stream);
+/* softmax cross-entropy heads (functional.py:5-16): labels = (int) z[b, label_col];
+ * focal = 0: loss += weight * mean CE ; focal = 1: loss += weight * mean (1-p_y)^2 CE ; glogits = dloss/dlogits */
+int eg_softmax_ce_bwd(const float* logits, const float* z, int z_stride, int label_col, int B, int C, int focal,
+                      float weight, float inv_global_batch, float* glogits, float* loss, void* stream);
 
 /* generator input of the multi-class model (edgegan.py:188-197): out[n, zdim+classes] =
  * z[:, :zdim] ++ one_hot(int(z[:, zdim]), classes);  z has zdim+1 columns */

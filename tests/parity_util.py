@@ -39,6 +39,7 @@ def oracle_sensitivity(ocfg, v, u, inp, col64, rel=1e-6, seed=0, runs=None):
     out = {}
     for run, rec in col64.items():
         out[run] = {n: maxabs(col[run]["grads"][n] - g) / (maxabs(g) + 1e-30) for n, g in rec["grads"].items()}
+        out[run] = dict(out[run])
     return out
 
 

@@ -36,6 +36,8 @@ def act_fwd(act, x):
         return torch.tanh(x)
     if act == "sigmoid":
         return torch.sigmoid(x)
+    if act == "lrelu2":
+        return torch.where(x > 0, x, 0.2 * x)
     raise ValueError(act)
 
 
@@ -51,6 +53,8 @@ def act_grad(act, x):
     if act == "sigmoid":
         s = torch.sigmoid(x)
         return s * (1 - s)
+    if act == "lrelu2":
+        return torch.where(x > 0, torch.ones_like(x), torch.full_like(x, 0.2))
     raise ValueError(act)
 
 
@@ -326,6 +330,100 @@ class RefOps:
     def onehot_concat(self, z, zdim, classes, out):
         lab = z[:, zdim].to(torch.int64)
         out.copy_(torch.cat([z[:, :zdim], TF.one_hot(lab, classes).to(self.dtype)], dim=1))
+
+    # ---- classifier pieces -------------------------------------------------------------------------------------
+    def prelu_fwd(self, x, leak, y):
+        a = leak.reshape(()) * x
+        y.copy_(torch.where(a >= x, a, x))
+
+    def prelu_bwd(self, x, leak, gy, gx, gleak, accumulate_leak=False):
+        first = (leak.reshape(()) * x >= x)
+        if gx is not None:
+            gx.copy_(torch.where(first, gy * leak.reshape(()), gy))
+        if gleak is not None:
+            v = (gy * x * first.to(self.dtype)).sum().reshape(gleak.shape)
+            gleak.add_(v) if accumulate_leak else gleak.copy_(v)
+
+    @staticmethod
+    def _mm(x):
+        N, C = x.shape[0], x.shape[-1]
+        x3 = x.reshape(N, -1, C)
+        return x3, x3.amin(1, keepdim=True), x3.amax(1, keepdim=True)
+
+    def minmax_fwd(self, x, y, stats):
+        x3, mn, mx = self._mm(x)
+        y.copy_(((x3 - mn) / (mx - mn)).reshape(x.shape))
+        stats.copy_(torch.stack([mn[:, 0, :], mx[:, 0, :]], dim=-1))
+
+    def minmax_bwd(self, x, stats, gy, gx):
+        xr = x.detach().clone().requires_grad_(True)
+        x3 = xr.reshape(x.shape[0], -1, x.shape[-1])
+        mn, mx = x3.amin(1, keepdim=True), x3.amax(1, keepdim=True)      # amin/amax split the gradient between ties
+        yv = ((x3 - mn) / (mx - mn)).reshape(x.shape)
+        (g,) = torch.autograd.grad(yv, xr, gy)
+        gx.copy_(g)
+
+    def fma3(self, a, b, c, out):
+        out.copy_(a + b * c)
+
+    def mul(self, a, b, out):
+        out.copy_(a * b)
+
+    def add_pool2_fwd(self, a, b, y):
+        v = a + b if b is not None else a
+        y.copy_(_nhwc(TF.avg_pool2d(_nchw(v), 2, 2)))
+
+    def pool2_bwd(self, gy, gx, accumulate=False):
+        up = gy.repeat_interleave(2, dim=1).repeat_interleave(2, dim=2) * 0.25
+        gx.add_(up) if accumulate else gx.copy_(up)
+
+    def globalmean_fwd(self, x, y):
+        N, C = x.shape[0], x.shape[-1]
+        y.copy_(x.reshape(N, -1, C).mean(1))
+
+    def globalmean_bwd(self, gy, gx):
+        N, C = gx.shape[0], gx.shape[-1]
+        P = gx.numel() // (N * C)
+        gx.copy_((gy.reshape(N, 1, C) / P).expand(N, P, C).reshape(gx.shape))
+
+    def sn_ws_floats(self, K, C):
+        return 2 * K + C + 8
+
+    @staticmethod
+    def _sn(W, u):
+        Wm = W.reshape(-1, W.shape[-1])
+
+        def l2n(t):
+            return t / (torch.sum(t ** 2) ** 0.5 + 1e-12)
+        v1 = l2n(u.reshape(1, -1) @ Wm.t())
+        u1 = l2n(v1 @ Wm)
+        sigma = (v1 @ Wm @ u1.t())[0, 0]
+        return (Wm / sigma).reshape(W.shape)
+
+    def spectral_norm_fwd(self, W, u, Wbar, ws):
+        Wbar.copy_(self._sn(W, u))
+
+    def spectral_norm_bwd(self, W, u, ws, Gbar, gW):
+        Wr = W.detach().clone().requires_grad_(True)
+        (g,) = torch.autograd.grad(self._sn(Wr, u), Wr, Gbar)
+        gW.copy_(g)
+
+    def softmax_ce_bwd(self, logits, z, label_col, focal, weight, inv_global_batch, glogits, loss):
+        lr_ = logits.detach().clone().requires_grad_(True)
+        lab = z[:, label_col].to(torch.int64)
+        ce = TF.cross_entropy(lr_, lab, reduction="none")
+        if focal:
+            py = torch.softmax(lr_, dim=1).gather(1, lab.view(-1, 1)).squeeze(1)
+            per = (1 - py) ** 2 * ce
+        else:
+            per = ce
+        total = weight * inv_global_batch * per.sum()
+        (g,) = torch.autograd.grad(total, lr_)
+        glogits.copy_(g)
+        loss.add_(total.detach())
+
+    def copy_cslice(self, src, src_c0, dst, dst_c0, width):
+        dst[..., dst_c0:dst_c0 + width] = src[..., src_c0:src_c0 + width]
 
     def rmsprop(self, var, grad, ms, lr, decay=0.9, eps=1e-10):
         ms.copy_(decay * ms + (1 - decay) * grad * grad)

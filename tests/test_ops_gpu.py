@@ -230,3 +230,88 @@ def test_onehot_rmsprop_biasgrad(dev, ref):
         res.append([o.to_numpy(t) for t in (out, var, ms, db, db2)])
     for g_, w_ in zip(*res):
         close(g_, w_, 2e-5)
+
+
+# ---- classifier kernels -------------------------------------------------------------------------------------
+def test_prelu_lrelu2(dev, ref):
+    rs = np.random.RandomState(20)
+    x, gy = rnd(rs, 3, 8, 8, 16), rnd(rs, 3, 8, 8, 16)
+    x.reshape(-1)[:5] = 0.0                                    # ties at zero
+    leak = np.array(0.2, np.float32).reshape(1)
+    res = []
+    for o in (dev, ref):
+        X, L, GY = o.from_numpy(x), o.from_numpy(leak), o.from_numpy(gy)
+        y, gx, gl, gl2 = o.zeros(x.shape), o.zeros(x.shape), o.zeros((1,)), o.from_numpy(np.array([1.5], np.float32))
+        o.prelu_fwd(X, L, y)
+        o.prelu_bwd(X, L, GY, gx, gl, False)
+        o.prelu_bwd(X, L, GY, None, gl2, True)
+        a, ga = o.zeros(x.shape), o.zeros(x.shape)
+        o.act_fwd(X, a, "lrelu2")
+        o.act_bwd(X, GY, ga, "lrelu2")
+        res.append([o.to_numpy(t) for t in (y, gx, gl, gl2, a, ga)])
+    for g_, w_ in zip(*res):
+        close(g_, w_, 2e-5)
+
+
+@pytest.mark.parametrize("shape", [(2, 8, 8, 40), (3, 16, 16, 8)])
+def test_minmax(dev, ref, shape):
+    rs = np.random.RandomState(21)
+    x, gy = rnd(rs, *shape), rnd(rs, *shape)
+    x[0, 0, 0, :] = x[0, 1, 1, :] = x.reshape(shape[0], -1, shape[-1]).max(1)[0] + 0.5     # tied maxima in sample 0
+    N, C = shape[0], shape[-1]
+    y, st = both(dev, ref, "minmax_fwd", [x], [shape, (N, C, 2)])
+    both(dev, ref, "minmax_bwd", [x, st, gy], [shape], tol=5e-5)
+
+
+def test_fma_mul_pool_mean_cslice(dev, ref):
+    rs = np.random.RandomState(22)
+    shape = (2, 6, 8, 5)
+    a, b, c = rnd(rs, *shape), rnd(rs, *shape), rnd(rs, *shape)
+    both(dev, ref, "fma3", [a, b, c], [shape])
+    both(dev, ref, "mul", [a, b], [shape])
+    both(dev, ref, "add_pool2_fwd", [a, b], [(2, 3, 4, 5)])
+    both(dev, ref, "add_pool2_fwd", [a, None], [(2, 3, 4, 5)])
+    gy = rnd(rs, 2, 3, 4, 5)
+    both(dev, ref, "pool2_bwd", [gy], [shape], False)
+    both(dev, ref, "pool2_bwd", [gy], [rnd(rs, *shape)], True)
+    both(dev, ref, "globalmean_fwd", [a], [(2, 5)])
+    both(dev, ref, "globalmean_bwd", [rnd(rs, 2, 5)], [shape])
+    res = []
+    for o in (dev, ref):
+        S, D = o.from_numpy(a), o.from_numpy(rnd(np.random.RandomState(1), 2, 6, 8, 9))
+        o.copy_cslice(S, 1, D, 4, 3)
+        res.append(o.to_numpy(D))
+    close(res[0], res[1], 1e-6)
+
+
+@pytest.mark.parametrize("shape", [(3, 3, 11, 8), (3, 3, 128, 256), (1, 1, 768, 14), (7, 7, 3, 8)])
+def test_spectral_norm(dev, ref, shape):
+    rs = np.random.RandomState(23)
+    W, u, G = rnd(rs, *shape, scale=0.02), rnd(rs, 1, shape[-1]), rnd(rs, *shape)
+    Cn = shape[-1]
+    K = int(np.prod(shape)) // Cn
+    res = []
+    for o in (dev, ref):
+        Wt, ut, Gt = o.from_numpy(W), o.from_numpy(u), o.from_numpy(G)
+        wb, ws, gw = o.zeros(shape), o.zeros((o.sn_ws_floats(K, Cn),)), o.zeros(shape)
+        o.spectral_norm_fwd(Wt, ut, wb, ws)
+        o.spectral_norm_bwd(Wt, ut, ws, Gt, gw)
+        res.append([o.to_numpy(wb), o.to_numpy(gw)])
+    close(res[0][0], res[1][0], 2e-5, "wbar")
+    close(res[0][1], res[1][1], 1e-4, "gW")
+
+
+@pytest.mark.parametrize("focal", [False, True])
+def test_softmax_ce(dev, ref, focal):
+    rs = np.random.RandomState(24)
+    B, Cn = 9, 14
+    logits = rnd(rs, B, Cn, scale=2.0)
+    z = rnd(rs, B, 101)
+    z[:, 100] = rs.randint(0, Cn, B)
+    res = []
+    for o in (dev, ref):
+        gl, loss = o.zeros((B, Cn)), o.from_numpy(np.array([0.25], np.float32))
+        o.softmax_ce_bwd(o.from_numpy(logits), o.from_numpy(z), 100, focal, 0.5, 1.0 / 11, gl, loss)
+        res.append([o.to_numpy(gl), o.to_numpy(loss)])
+    for g_, w_ in zip(*res):
+        close(g_, w_, 2e-5)

@@ -84,6 +84,33 @@ def test_single_class_step_matches_oracle(algo, tol):
         assert np.isfinite(a).all(), k
 
 
+@pytest.mark.parametrize("run,algo", [("d_optim2", "tc3x"), ("g_optim_u", "tc3x"), ("d_optim2", "simt")])
+def test_multi_class_runs_from_identical_weights(run, algo):
+    """14-class model (BASELINE configs[2]): the classifier run (focal loss on real images, spectral-norm backward)
+    and the generator run with the classifier's CE term, each from the oracle's initial weights, batch 4."""
+    from parity_util import check_grads, oracle_pair, oracle_sensitivity
+    B = 4
+    ocfg, v, u, m, ops = make(B, True, algo, seed=7)
+    inp = O.make_inputs(ocfg, seed=21)
+    (st64, col64), (st32, col32) = oracle_pair(ocfg, v, u, inp, runs=[run])
+    sens = oracle_sensitivity(ocfg, v, u, inp, col64, runs=[run])
+    grads = {}
+    m.run_hook = lambda r, model: grads.__setitem__(r, model.export_variables("grad"))
+    m.update_model(ops.from_numpy(inp.images), ops.from_numpy(inp.z), ops.from_numpy(inp.alpha), inp.eps, runs=[run])
+    torch.cuda.synchronize()
+    for name in list(col64[run]["grads"]):                 # mathematically-zero gradients (see test_host_step_cpu)
+        if np.abs(col64[run]["grads"][name]).max() < 1e-9:
+            for c in (col64, col32):
+                c[run]["grads"].pop(name)
+    report, fails = check_grads(grads, col64, col32, 2e-3, sens=sens)
+    print(run, algo, report)
+    assert not fails, fails[:5]
+    losses = m.read_losses()
+    key = "loss_d_ac" if run == "d_optim2" else "image_gloss"
+    ref = st64.losses["d_optim2"] if run == "d_optim2" else st64.losses["g_optim_u/image_gloss"]
+    assert abs(losses[key] - ref) < 2e-3 * max(1.0, abs(ref)), (losses[key], ref)
+
+
 @pytest.mark.parametrize("run,algo", [("d_optim", "tc3x"), ("d_optim_patch2", "tc3x"), ("g_optim_u", "tc3x"), ("e_optim", "tc3x"),
                                       ("d_optim", "simt"), ("g_optim_u", "simt")])
 def test_single_runs_from_identical_weights(run, algo):
