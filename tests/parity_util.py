@@ -26,7 +26,22 @@ def oracle_pair(ocfg, v, u, inp, runs=None):
     return out[torch.float64], out[torch.float32]
 
 
-def oracle_sensitivity(ocfg, v, u, inp, col64, rel=1e-6, seed=0, runs=None):
+def oracle_sensitivity(ocfg, v, u, inp, col64, rel=1e-5, seed=0, runs=None, samples=2):
+    """max over `samples` random perturbations of _oracle_sensitivity_once (the response is heavy-tailed: a
+    single lrelu-mask or arg-max flip moves a whole filter gradient by a finite amount)."""
+    out = None
+    for k in range(samples):
+        cur = _oracle_sensitivity_once(ocfg, v, u, inp, col64, rel, seed + k, runs)
+        if out is None:
+            out = cur
+        else:
+            for run in out:
+                for n in out[run]:
+                    out[run][n] = max(out[run][n], cur[run][n])
+    return out
+
+
+def _oracle_sensitivity_once(ocfg, v, u, inp, col64, rel, seed, runs):
     """How far the fp64 oracle's own gradients move when the images are perturbed by `rel` (relative): the
     critics' penalty gradient is discontinuous in the lrelu masks of low-variance instance-norm channels, so
     near such a point ANY two fp32 implementations disagree by a finite amount.  run -> name -> rel. change."""
