@@ -73,16 +73,27 @@ __device__ __forceinline__ void sts128(uint32_t a, uint4 v) {
 __device__ __forceinline__ uint32_t tf32_rna(uint32_t x) { return (x + 0x1000u) & 0xFFFFE000u; }
 // lo is rounded to nearest too: its own truncation would otherwise leave a biased 2^-20 relative residual
 __device__ __forceinline__ uint32_t tf32_lo(uint32_t x) { return tf32_rna(__float_as_uint(__uint_as_float(x) - __uint_as_float(x & 0xFFFFE000u))); }
-// elementwise pass over `bytes` of shared memory by 128 threads (the swizzle is irrelevant: same offset in/out)
+// elementwise pass over `bytes` of shared memory by 128 threads (the swizzle is irrelevant: same offset in/out).
+// Loads are issued in batches of 8 x 16 B per thread before any use, so the LDS latency is paid once per batch.
 __device__ __forceinline__ void condition_tile(uint32_t src, uint32_t dst_lo, uint32_t bytes, int tid, int mode) {
-    for (uint32_t off = (uint32_t)tid * 16u; off < bytes; off += 128u * 16u) {
-        uint4 v = lds128(src + off);
-        if (mode == 3) {
-            v.x = tf32_lo(v.x); v.y = tf32_lo(v.y); v.z = tf32_lo(v.z); v.w = tf32_lo(v.w);
-            sts128(dst_lo + off, v);
-        } else {
-            v.x = tf32_rna(v.x); v.y = tf32_rna(v.y); v.z = tf32_rna(v.z); v.w = tf32_rna(v.w);
-            sts128(src + off, v);
+    constexpr uint32_t kStep = 128u * 16u;                   // bytes covered by one pass of the 128 threads
+    for (uint32_t base = (uint32_t)tid * 16u; base < bytes; base += 8u * kStep) {
+        uint4 v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            if (base + j * kStep < bytes) v[j] = lds128(src + base + j * kStep);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            if (base + j * kStep < bytes) {
+                uint4 o;
+                if (mode == 3) {
+                    o.x = tf32_lo(v[j].x); o.y = tf32_lo(v[j].y); o.z = tf32_lo(v[j].z); o.w = tf32_lo(v[j].w);
+                    sts128(dst_lo + base + j * kStep, o);
+                } else {
+                    o.x = tf32_rna(v[j].x); o.y = tf32_rna(v[j].y); o.z = tf32_rna(v[j].z); o.w = tf32_rna(v[j].w);
+                    sts128(src + base + j * kStep, o);
+                }
+            }
         }
     }
 }
@@ -122,6 +133,13 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint6
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n"
         ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// same with the A operand read from tensor memory (128 lanes x K 32-bit columns) instead of shared memory
+__device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}\n"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
 // arrive on an mbarrier when all previously issued MMAs have completed (implies fence::before_thread_sync)
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -138,6 +156,19 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
           "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
         : "r"(taddr));
 }
+// 32 registers per thread -> 32 lanes x 32 consecutive columns (thread = TMEM lane)
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+          "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]),
+          "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]),
+          "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ---------------------------------------------------------------------------------------------------
@@ -194,6 +225,7 @@ struct TcParams {
     int ldn;              // number of output channels (columns)
     int mode;             // 1 = TF32 (operands rounded to nearest), 3 = 3xTF32 split
     int b_lo_tap_off;     // 3x: tap offset of the filter's lo copy inside the filter map
+    int dbg;              // timing experiments only: bit0 skip the B_lo load, bit1 skip the conditioning pass
     const float* bias;
     float* out;
 };
@@ -214,10 +246,12 @@ conv_tc_kmajor(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const int BN = P.BN, mode = P.mode;
     const uint32_t a_bytes = 128 * 128, b_bytes = (uint32_t)BN * 128;
-    // stage: [A][A_lo (3x)][B][B_lo (3x)]
-    const uint32_t a_lo_off = a_bytes, b_off = (mode == 3 ? 2 : 1) * a_bytes, b_lo_off = b_off + b_bytes;
-    const uint32_t stage_bytes = (mode == 3 ? 2 : 1) * (a_bytes + b_bytes);
-    const uint32_t tx_bytes = a_bytes + (mode == 3 ? 2 : 1) * b_bytes;
+    // stage: [A landing tile][B][B_lo (3x)].  In the 3x kernel the A operand never goes back to shared memory: warps 2-5
+    // read the landed tile once and write hi / lo straight into tensor memory (TS-mode MMA), which removes the A
+    // operand fetch -- half of the SS-mode shared-memory traffic, the measured limiter -- and the lo store.
+    const uint32_t a_lo_off = 0, b_off = a_bytes, b_lo_off = b_off + b_bytes;
+    const uint32_t stage_bytes = a_bytes + (mode == 3 ? 2 : 1) * b_bytes;
+    const uint32_t tx_bytes = a_bytes + ((mode == 3 && !(P.dbg & 1)) ? 2 : 1) * b_bytes;
 
     __shared__ __align__(8) uint64_t full_bar[kStages];      // TMA bytes landed
     __shared__ __align__(8) uint64_t ready_bar[kStages];     // operands conditioned (4 warp arrivals)
@@ -236,8 +270,11 @@ conv_tc_kmajor(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
     const int w0 = tw * P.bw, h0 = th * P.bh, n0 = tn * P.bn;
     const int col0 = blockIdx.y * BN;
     const int niter = ph.ntaps * ph.kchunks;
+    // TMEM columns: [0, acc_cols) accumulators (two in the chunked kernel), then kStages x (32 hi + 32 lo) A columns
     const int acc_cols = kChunked ? 2 * BN : BN;
-    const uint32_t tmem_cols = acc_cols <= 32 ? 32 : (acc_cols <= 64 ? 64 : (acc_cols <= 128 ? 128 : 256));
+    const uint32_t a_col0 = (uint32_t)acc_cols;
+    const int need_cols = kChunked ? acc_cols + kStages * 64 : acc_cols;
+    const uint32_t tmem_cols = need_cols <= 32 ? 32 : (need_cols <= 64 ? 64 : (need_cols <= 128 ? 128 : (need_cols <= 256 ? 256 : 512)));
 
     if (warp == 0 && lane == 0) {
         for (int i = 0; i < 4; ++i) prefetch_tmap(&maps.a[i]);
@@ -268,7 +305,7 @@ conv_tc_kmajor(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
                 mbar_expect_tx(fb, tx_bytes);
                 tma_load_4d(sa, &maps.a[tp.amap], fb, kc * 32, w0 + tp.ax, h0 + tp.ay, n0);
                 tma_load_3d(sa + b_off, &maps.b[0], fb, kc * 32, col0, tp.bsel);
-                if (mode == 3) tma_load_3d(sa + b_lo_off, &maps.b[0], fb, kc * 32, col0, tp.bsel + P.b_lo_tap_off);
+                if (mode == 3 && !(P.dbg & 1)) tma_load_3d(sa + b_lo_off, &maps.b[0], fb, kc * 32, col0, tp.bsel + P.b_lo_tap_off);
                 if (++stage == kStages) { stage = 0; phase ^= 1; }
             }
         }
@@ -289,16 +326,21 @@ conv_tc_kmajor(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
                 mbar_wait(smem_u32(&ready_bar[stage]), phase);
                 tc_fence_after();
                 const uint32_t sa = smem_base + stage * stage_bytes;
-                const uint64_t ad = make_smem_desc(sa, 16, 1024), bd = make_smem_desc(sa + b_off, 16, 1024);
+                const uint64_t bd = make_smem_desc(sa + b_off, 16, 1024);
+                if (!kChunked) {
+                    const uint64_t ad = make_smem_desc(sa, 16, 1024);
 #pragma unroll
-                for (int k = 0; k < 4; ++k)       // 4 x (K = 8 tf32 = 32 B) inside the 128-byte swizzle span
-                    umma_tf32(dst, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, !(first && k == 0));
-                if (mode == 3) {
-                    const uint64_t ald = make_smem_desc(sa + a_lo_off, 16, 1024), bld = make_smem_desc(sa + b_lo_off, 16, 1024);
+                    for (int k = 0; k < 4; ++k)   // 4 x (K = 8 tf32 = 32 B) inside the 128-byte swizzle span
+                        umma_tf32(dst, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, !(first && k == 0));
+                } else {
+                    const uint64_t bld = make_smem_desc(sa + b_lo_off, 16, 1024);
+                    const uint32_t a_hi = tmem_base + a_col0 + (uint32_t)(stage * 64), a_lo = a_hi + 32;
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) umma_tf32(dst, ald + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, 1);
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) umma_tf32(dst, ad + (uint64_t)(k * 2), bld + (uint64_t)(k * 2), idesc, 1);
+                    for (int k = 0; k < 4; ++k) {
+                        umma_tf32_ts(dst, a_hi + k * 8, bd + (uint64_t)(k * 2), idesc, !(first && k == 0));
+                        umma_tf32_ts(dst, a_lo + k * 8, bd + (uint64_t)(k * 2), idesc, 1);
+                        umma_tf32_ts(dst, a_hi + k * 8, bld + (uint64_t)(k * 2), idesc, 1);
+                    }
                 }
                 umma_commit(smem_u32(&empty_bar[stage]));
                 if (kChunked && (it % kChunkStages == kChunkStages - 1 || it == niter - 1))
@@ -339,8 +381,26 @@ conv_tc_kmajor(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
             for (int it = 0; it < niter; ++it) {
                 mbar_wait(smem_u32(&full_bar[stage]), phase);
                 const uint32_t sa = smem_base + stage * stage_bytes;
-                condition_tile(sa, sa + a_lo_off, a_bytes, ctid, mode);     // the filter operand was prepared in global
-                fence_proxy_async();
+                if (!kChunked) {
+                    if (!(P.dbg & 2)) condition_tile(sa, sa + a_lo_off, a_bytes, ctid, mode);   // the filter was prepared in global
+                    fence_proxy_async();
+                } else {
+                    // this thread's accumulator row = TMEM lane = row of the A tile: 8 x 16 B at the swizzled positions
+                    const int arow = (warp & 3) * 32 + lane;
+                    uint32_t hi[32], lo[32];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const uint4 v = lds128(sa + (uint32_t)arow * 128u + (uint32_t)((j ^ (arow & 7)) << 4));
+                        hi[4 * j] = v.x; hi[4 * j + 1] = v.y; hi[4 * j + 2] = v.z; hi[4 * j + 3] = v.w;
+                    }
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) { lo[j] = tf32_lo(hi[j]); hi[j] &= 0xFFFFE000u; }
+                    const uint32_t ta = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + a_col0 + (uint32_t)(stage * 64);
+                    tmem_st32(ta, hi);
+                    tmem_st32(ta + 32, lo);
+                    tmem_st_wait();
+                    tc_fence_before();
+                }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(smem_u32(&ready_bar[stage]));
                 if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -633,7 +693,8 @@ int get_scratch(cudaStream_t st, size_t bytes, float** out) {
     return 0;
 }
 
-constexpr int kStagesK = 3;
+constexpr int kStagesK = 3;      // SS-mode (TF32) kernel
+constexpr int kStagesK3 = 4;     // TS-mode (3xTF32) kernel: 4 x (16 KB A landing + 2 x BN*128 B filter hi/lo)
 constexpr int kStagesW = 3;
 
 bool g_attr_set = false;
@@ -641,7 +702,7 @@ int set_attrs() {
     if (g_attr_set) return 0;
     cudaError_t e = cudaFuncSetAttribute(conv_tc_kmajor<kStagesK, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return eg_fail(e, __FILE__, __LINE__);
-    e = cudaFuncSetAttribute(conv_tc_kmajor<kStagesK, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    e = cudaFuncSetAttribute(conv_tc_kmajor<kStagesK3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return eg_fail(e, __FILE__, __LINE__);
     e = cudaFuncSetAttribute(conv_tc_wgrad<kStagesW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return eg_fail(e, __FILE__, __LINE__);
@@ -724,7 +785,9 @@ static TcTap x_tap(const eg_conv_shape* s, int r, int q, int bsel) {
     return t;
 }
 
-static size_t kmajor_smem(int BN, int mode) { return (size_t)kStagesK * (mode == 3 ? 2 : 1) * (128 * 128 + BN * 128) + 1024; }
+static size_t kmajor_smem(int BN, int mode) {
+    return mode == 3 ? (size_t)kStagesK3 * (128 * 128 + 2 * BN * 128) + 1024 : (size_t)kStagesK * (128 * 128 + BN * 128) + 1024;
+}
 
 int eg_tc_conv2d_fwd(const eg_conv_shape* s, const float* x, const float* w, const float* bias, float* y, int three_x,
                      cudaStream_t st) {
@@ -737,7 +800,7 @@ int eg_tc_conv2d_fwd(const eg_conv_shape* s, const float* x, const float* w, con
     TcParams P{};
     pick_box(s->OW, s->OH, 128, P.bw, P.bh, P.bn);
     P.BN = pick_bn(s->Co);
-    P.mode = mode; P.b_lo_tap_off = taps;
+    P.mode = mode; P.b_lo_tap_off = taps; P.dbg = g_dbg[3];
     if (int r = make_x_maps(maps.a, s, x, P.bw, P.bh, P.bn)) return r;
     for (int i = s->stride * s->stride; i < 4; ++i) maps.a[i] = maps.a[0];
     if (int r = make_filter_map(&maps.b[0], wt, s->Ci, s->Co, 2 * taps, P.BN)) return r;
@@ -751,7 +814,7 @@ int eg_tc_conv2d_fwd(const eg_conv_shape* s, const float* x, const float* w, con
     ph.tiles_w = s->OW / P.bw; ph.tiles_h = s->OH / P.bh; ph.tiles_n = eg_ceil_div(s->N, P.bn);
     ph.out_off = 0; ph.sw = s->Co; ph.sh = (long long)s->OW * s->Co; ph.sn = (long long)s->OH * s->OW * s->Co;
     dim3 grid(ph.tiles_w * ph.tiles_h * ph.tiles_n, s->Co / P.BN, 1);
-    if (mode == 3) conv_tc_kmajor<kStagesK, true><<<grid, kThreads, kmajor_smem(P.BN, mode), st>>>(maps, P);
+    if (mode == 3) conv_tc_kmajor<kStagesK3, true><<<grid, kThreads, kmajor_smem(P.BN, mode), st>>>(maps, P);
     else           conv_tc_kmajor<kStagesK, false><<<grid, kThreads, kmajor_smem(P.BN, mode), st>>>(maps, P);
     EG_CHECK_LAUNCH();
     return 0;
@@ -769,7 +832,7 @@ int eg_tc_conv2d_bwd_data(const eg_conv_shape* s, const float* dy, const float* 
     const int Hp = s->H / S, Wp = s->W / S;
     pick_box(Wp, Hp, 128, P.bw, P.bh, P.bn);
     P.BN = pick_bn(s->Ci);
-    P.mode = mode; P.b_lo_tap_off = taps;
+    P.mode = mode; P.b_lo_tap_off = taps; P.dbg = g_dbg[3];
     // A = dy, dense stride-1 window
     if (int r = make_act_map(&maps.a[0], dy, s->Co, s->OW, s->OH, s->N, s->Co, (long long)s->OW * s->Co,
                              (long long)s->OH * s->OW * s->Co, P.bw, P.bh, P.bn)) return r;
@@ -802,7 +865,7 @@ int eg_tc_conv2d_bwd_data(const eg_conv_shape* s, const float* dy, const float* 
             if (ph.ntaps == 0) return eg_fail_arg("dgrad phase without taps", __FILE__, __LINE__);
         }
     dim3 grid(max_tiles, s->Ci / P.BN, S * S);
-    if (mode == 3) conv_tc_kmajor<kStagesK, true><<<grid, kThreads, kmajor_smem(P.BN, mode), st>>>(maps, P);
+    if (mode == 3) conv_tc_kmajor<kStagesK3, true><<<grid, kThreads, kmajor_smem(P.BN, mode), st>>>(maps, P);
     else           conv_tc_kmajor<kStagesK, false><<<grid, kThreads, kmajor_smem(P.BN, mode), st>>>(maps, P);
     EG_CHECK_LAUNCH();
     return 0;
