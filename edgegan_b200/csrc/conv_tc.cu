@@ -62,6 +62,11 @@ __device__ __forceinline__ uint4 lds128(uint32_t a) {
     asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
     return v;
 }
+__device__ __forceinline__ uint32_t lds32(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}
 __device__ __forceinline__ void sts128(uint32_t a, uint4 v) {
     asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
@@ -469,7 +474,11 @@ struct WgParams {
     float* out;
 };
 
-template <int kStages>
+// kTS (3xTF32 mode): the row operand goes through tensor memory like in the K-major kernel.  Thread r of warps 2-5
+// owns channel row r of the 128-row tile: for each of the 32 pixels of a stage it reads its channel from the
+// MN-major slab (one 128-B line per pixel, 32-B-atom swizzle -> conflict-free across the warp) and stores hi / lo as
+// 32 TMEM columns; the column operand stays in shared memory and gets its lo copy written next to it.
+template <int kStages, bool kTS>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_wgrad(const __grid_constant__ TcMaps maps, const __grid_constant__ WgParams P) {
     extern __shared__ uint8_t smem_raw[];
@@ -477,8 +486,10 @@ conv_tc_wgrad(const __grid_constant__ TcMaps maps, const __grid_constant__ WgPar
     const int BN = P.BN, PIX = P.pix, mode = P.mode;
     const uint32_t sub_bytes = (uint32_t)PIX * 128;          // one 32-channel slab: PIX rows x 128 B
     const uint32_t a_bytes = 4 * sub_bytes, b_bytes = (uint32_t)(BN / 32) * sub_bytes;
-    const uint32_t ab_bytes = a_bytes + b_bytes;             // stage: [A slabs][B slabs][A_lo][B_lo] (lo: 3x only)
-    const uint32_t stage_bytes = (mode == 3 ? 2 : 1) * ab_bytes;
+    const uint32_t ab_bytes = a_bytes + b_bytes;
+    // stage: SS: [A slabs][B slabs][A_lo][B_lo] (lo: 3x only) ; TS: [A slabs][B slabs][B_lo]
+    const uint32_t stage_bytes = kTS ? ab_bytes + b_bytes : (mode == 3 ? 2 : 1) * ab_bytes;
+    const uint32_t b_lo_off = kTS ? ab_bytes : ab_bytes + a_bytes;
 
     __shared__ __align__(8) uint64_t full_bar[kStages];
     __shared__ __align__(8) uint64_t ready_bar[kStages];
@@ -494,7 +505,9 @@ conv_tc_wgrad(const __grid_constant__ TcMaps maps, const __grid_constant__ WgPar
     const int t_beg = split * P.chunks_per_split;
     const int t_end = min(ntiles, t_beg + P.chunks_per_split);
     const int niter = t_end - t_beg;
-    const uint32_t tmem_cols = BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256));
+    const uint32_t a_col0 = (uint32_t)BN;
+    const int need_cols = kTS ? BN + kStages * 64 : BN;
+    const uint32_t tmem_cols = need_cols <= 32 ? 32 : (need_cols <= 64 ? 64 : (need_cols <= 128 ? 128 : (need_cols <= 256 ? 256 : 512)));
     if (niter <= 0) return;
 
     if (warp == 0 && lane == 0) {
@@ -538,7 +551,7 @@ conv_tc_wgrad(const __grid_constant__ TcMaps maps, const __grid_constant__ WgPar
         }
     } else if (warp == 1) {
         if (elect_one()) {
-            const uint32_t idesc = make_idesc(128, BN, 1, 1);
+            const uint32_t idesc = make_idesc(128, BN, kTS ? 0 : 1, 1);
             int stage = 0; uint32_t phase = 0;
             for (int it = 0; it < niter; ++it) {
                 mbar_wait(smem_u32(&ready_bar[stage]), phase);
@@ -546,15 +559,25 @@ conv_tc_wgrad(const __grid_constant__ TcMaps maps, const __grid_constant__ WgPar
                 const uint32_t sa = smem_base + stage * stage_bytes, sb = sa + a_bytes;
                 // MN-major tf32 operands must use the "128B swizzle with 32B atoms" layout (Swizzle<2,5,2>): an atom is
                 // 32 channels (128 B) x 4 pixels; LBO = next 32-channel slab, SBO = next 4 pixels (512 B)
-                const uint64_t ad = make_smem_desc(sa, sub_bytes, P.sbo, P.layout_type);
                 const uint64_t bd = make_smem_desc(sb, sub_bytes, P.sbo, P.layout_type);
-                for (int k = 0; k < PIX / 8; ++k)
-                    umma_tf32(tmem_base, ad + (uint64_t)(k * 64), bd + (uint64_t)(k * 64), idesc, (it | k) != 0);
-                if (mode == 3) {
-                    const uint64_t ald = make_smem_desc(sa + ab_bytes, sub_bytes, P.sbo, P.layout_type);
-                    const uint64_t bld = make_smem_desc(sb + ab_bytes, sub_bytes, P.sbo, P.layout_type);
-                    for (int k = 0; k < PIX / 8; ++k) umma_tf32(tmem_base, ald + (uint64_t)(k * 64), bd + (uint64_t)(k * 64), idesc, 1);
-                    for (int k = 0; k < PIX / 8; ++k) umma_tf32(tmem_base, ad + (uint64_t)(k * 64), bld + (uint64_t)(k * 64), idesc, 1);
+                if (kTS) {
+                    const uint64_t bld = make_smem_desc(sa + b_lo_off, sub_bytes, P.sbo, P.layout_type);
+                    const uint32_t a_hi = tmem_base + a_col0 + (uint32_t)(stage * 64), a_lo = a_hi + 32;
+                    for (int k = 0; k < PIX / 8; ++k) {
+                        umma_tf32_ts(tmem_base, a_hi + k * 8, bd + (uint64_t)(k * 64), idesc, (it | k) != 0);
+                        umma_tf32_ts(tmem_base, a_lo + k * 8, bd + (uint64_t)(k * 64), idesc, 1);
+                        umma_tf32_ts(tmem_base, a_hi + k * 8, bld + (uint64_t)(k * 64), idesc, 1);
+                    }
+                } else {
+                    const uint64_t ad = make_smem_desc(sa, sub_bytes, P.sbo, P.layout_type);
+                    for (int k = 0; k < PIX / 8; ++k)
+                        umma_tf32(tmem_base, ad + (uint64_t)(k * 64), bd + (uint64_t)(k * 64), idesc, (it | k) != 0);
+                    if (mode == 3) {
+                        const uint64_t ald = make_smem_desc(sa + ab_bytes, sub_bytes, P.sbo, P.layout_type);
+                        const uint64_t bld = make_smem_desc(sb + ab_bytes, sub_bytes, P.sbo, P.layout_type);
+                        for (int k = 0; k < PIX / 8; ++k) umma_tf32(tmem_base, ald + (uint64_t)(k * 64), bd + (uint64_t)(k * 64), idesc, 1);
+                        for (int k = 0; k < PIX / 8; ++k) umma_tf32(tmem_base, ad + (uint64_t)(k * 64), bld + (uint64_t)(k * 64), idesc, 1);
+                    }
                 }
                 umma_commit(smem_u32(&empty_bar[stage]));
                 if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -563,19 +586,38 @@ conv_tc_wgrad(const __grid_constant__ TcMaps maps, const __grid_constant__ WgPar
         }
     } else {
         const int ctid = threadIdx.x - 64;
+        const int q = warp & 3;
         {
             int stage = 0; uint32_t phase = 0;
             for (int it = 0; it < niter; ++it) {
                 mbar_wait(smem_u32(&full_bar[stage]), phase);
                 const uint32_t sa = smem_base + stage * stage_bytes;
-                condition_tile(sa, sa + ab_bytes, ab_bytes, ctid, mode);       // both operands are activations
-                fence_proxy_async();
+                if (kTS) {
+                    // row operand: channel (q*32 + lane) of slab q, pixels 0..31 -> 32 hi + 32 lo TMEM columns
+                    uint32_t hi[32], lo[32];
+                    const uint32_t slab = sa + (uint32_t)q * sub_bytes + (uint32_t)((lane & 7) << 2);
+#pragma unroll
+                    for (int p = 0; p < 32; ++p)
+                        hi[p] = lds32(slab + (uint32_t)p * 128u + (uint32_t)((((lane >> 3) ^ (p & 3)) << 5)));
+#pragma unroll
+                    for (int p = 0; p < 32; ++p) { lo[p] = tf32_lo(hi[p]); hi[p] &= 0xFFFFE000u; }
+                    const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + a_col0 + (uint32_t)(stage * 64);
+                    tmem_st32(ta, hi);
+                    tmem_st32(ta + 32, lo);
+                    // column operand: lo copy next to it in shared memory
+                    condition_tile(sa + a_bytes, sa + b_lo_off, b_bytes, ctid, 3);
+                    fence_proxy_async();
+                    tmem_st_wait();
+                    tc_fence_before();
+                } else {
+                    condition_tile(sa, sa + ab_bytes, ab_bytes, ctid, mode);       // both operands are activations
+                    fence_proxy_async();
+                }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(smem_u32(&ready_bar[stage]));
                 if (++stage == kStages) { stage = 0; phase ^= 1; }
             }
         }
-        const int q = warp & 3;
         const int row = row0 + q * 32 + lane;
         const bool valid = row < P.rows_total;
         float* obase = P.out + (long long)tap * P.tap_stride + (long long)row * P.sm;
@@ -696,6 +738,7 @@ int get_scratch(cudaStream_t st, size_t bytes, float** out) {
 constexpr int kStagesK = 3;      // SS-mode (TF32) kernel
 constexpr int kStagesK3 = 4;     // TS-mode (3xTF32) kernel: 4 x (16 KB A landing + 2 x BN*128 B filter hi/lo)
 constexpr int kStagesW = 3;
+constexpr int kStagesW3 = 4;     // TS-mode wgrad: 4 x (16 KB rows + 2 x BN/32*4 KB columns hi/lo)
 
 bool g_attr_set = false;
 int set_attrs() {
@@ -704,7 +747,9 @@ int set_attrs() {
     if (e != cudaSuccess) return eg_fail(e, __FILE__, __LINE__);
     e = cudaFuncSetAttribute(conv_tc_kmajor<kStagesK3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return eg_fail(e, __FILE__, __LINE__);
-    e = cudaFuncSetAttribute(conv_tc_wgrad<kStagesW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    e = cudaFuncSetAttribute(conv_tc_wgrad<kStagesW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return eg_fail(e, __FILE__, __LINE__);
+    e = cudaFuncSetAttribute(conv_tc_wgrad<kStagesW3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return eg_fail(e, __FILE__, __LINE__);
     g_attr_set = true;
     return 0;
@@ -912,8 +957,13 @@ int eg_tc_conv2d_bwd_weight(const eg_conv_shape* s, const float* x, const float*
         if (e != cudaSuccess) return eg_fail(e, __FILE__, __LINE__);
     }
     dim3 grid(rows / 128, cols / P.BN, P.ntaps * splits);
-    const size_t smem = (size_t)kStagesW * (P.mode == 3 ? 2 : 1) * ((4 + P.BN / 32) * P.pix * 128) + 1024;
-    conv_tc_wgrad<kStagesW><<<grid, kThreads, smem, st>>>(maps, P);
+    if (P.mode == 3) {
+        const size_t smem = (size_t)kStagesW3 * ((4 + 2 * (P.BN / 32)) * P.pix * 128) + 1024;
+        conv_tc_wgrad<kStagesW3, true><<<grid, kThreads, smem, st>>>(maps, P);
+    } else {
+        const size_t smem = (size_t)kStagesW * ((4 + P.BN / 32) * P.pix * 128) + 1024;
+        conv_tc_wgrad<kStagesW, false><<<grid, kThreads, smem, st>>>(maps, P);
+    }
     EG_CHECK_LAUNCH();
     return 0;
 }
