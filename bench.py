@@ -356,9 +356,15 @@ def conv_roofline(model, ops, step_fn, algo):
               for k, v in agg.items()}
     if tc_ms > 0:
         ach = tc_fl / tc_ms / 1e9
+        mult = 3.0 if algo == "tc3x" else 1.0
         return {"bound": "tensor", "kernel": "tcgen05 implicit-GEMM conv (fwd/dgrad/wgrad), kind::tf32",
                 "achieved": ach, "peak": peak_kind, "unit": "TFLOP/s", "frac": ach / peak_kind, "traffic": None,
-                "peak_source": f"{src} bf16 sustained / 2 (tf32 rate)", "conv_ms_per_step": all_ms, "detail": detail}
+                "peak_source": f"{src} bf16 sustained / 2 (tf32 rate)", "conv_ms_per_step": all_ms,
+                "mma_per_algorithmic_flop": mult,
+                "tensor_pipe_work_frac": mult * ach / peak_kind,
+                "note": ("achieved counts ALGORITHMIC conv FLOPs; the 3xTF32 mode issues 3 tensor-core MMAs per algorithmic "
+                         "MMA (hi*hi + lo*hi + hi*lo), so the tensor pipe is busy tensor_pipe_work_frac of its tf32 peak"),
+                "detail": detail}
     simt_fl = sum(v[0] for v in agg.values())
     ach = simt_fl / all_ms / 1e9 if all_ms > 0 else 0.0
     return {"bound": "tensor", "kernel": "fp32 FFMA implicit-GEMM conv (SIMT path; tensor cores not used)",

@@ -270,7 +270,8 @@ int launch_cfg(const float* a, const float* b, const float* bias, float* dst, co
 template <int MODE>
 int launch_mode(const float* a, const float* b, const float* bias, float* dst, const ConvP& p, const Phase& f,
                 int gz, bool va, bool vb, int atomic_out, cudaStream_t st) {
-    if (f.N <= 4)  return launch_cfg<MODE, 256, 4, 4, 1>(a, b, bias, dst, p, f, gz, va, vb, atomic_out, st);
+    // N <= 4 (3-channel images): one output pixel per thread, all of its channels in registers
+    if (f.N <= 4)  return launch_cfg<MODE, 256, 4, 1, 4>(a, b, bias, dst, p, f, gz, va, vb, atomic_out, st);
     if (f.N <= 16) return launch_cfg<MODE, 128, 16, 4, 2>(a, b, bias, dst, p, f, gz, va, vb, atomic_out, st);
     return launch_cfg<MODE, 64, 64, 4, 4>(a, b, bias, dst, p, f, gz, va, vb, atomic_out, st);
 }

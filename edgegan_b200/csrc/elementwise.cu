@@ -159,14 +159,23 @@ sum_scaled_k(const float* __restrict__ x, long long n, float scale, float* __res
 }
 
 // ---- discriminator head ----------------------------------------------------------------------------
-__global__ void __launch_bounds__(TB)
+__global__ void __launch_bounds__(512)
 rowdot_fwd_k(const float* __restrict__ h, const float* __restrict__ w, const float* __restrict__ bias,
              float* __restrict__ d, int F) {
     __shared__ float red[33];
     const int b = blockIdx.x;
     const float* hp = h + (size_t)b * F;
     float s = 0.f;
-    for (int i = threadIdx.x; i < F; i += blockDim.x) s = fmaf(hp[i], w[i], s);
+    if ((F & 3) == 0 && ((reinterpret_cast<uintptr_t>(hp) | reinterpret_cast<uintptr_t>(w)) & 15) == 0) {
+        const float4* h4 = reinterpret_cast<const float4*>(hp);
+        const float4* w4 = reinterpret_cast<const float4*>(w);
+        for (int i = threadIdx.x; i < F / 4; i += blockDim.x) {
+            const float4 a = __ldg(h4 + i), c = __ldg(w4 + i);
+            s = fmaf(a.x, c.x, s); s = fmaf(a.y, c.y, s); s = fmaf(a.z, c.z, s); s = fmaf(a.w, c.w, s);
+        }
+    } else {
+        for (int i = threadIdx.x; i < F; i += blockDim.x) s = fmaf(hp[i], w[i], s);
+    }
     s = block_sum(s, red);
     if (threadIdx.x == 0) d[b] = s + (bias ? bias[0] : 0.f);
 }
@@ -408,7 +417,7 @@ int eg_sum_scaled(const float* x, long long n, float scale, float* out, int accu
 }
 int eg_rowdot_fwd(const float* h, const float* w, const float* bias, float* d, int B, int F, void* stream) {
     EG_REQUIRE(h && w && d && B > 0 && F > 0);
-    rowdot_fwd_k<<<B, TB, 0, ST>>>(h, w, bias, d, F);
+    rowdot_fwd_k<<<B, 512, 0, ST>>>(h, w, bias, d, F);
     EG_CHECK_LAUNCH(); return 0;
 }
 int eg_rowdot_bwd_input(const float* gd, const float* w, float* gh, int B, int F, void* stream) {
