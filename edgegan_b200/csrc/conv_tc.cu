@@ -231,6 +231,7 @@ struct TcParams {
     int mode;             // 1 = TF32 (operands rounded to nearest), 3 = 3xTF32 split
     int b_lo_tap_off;     // 3x: tap offset of the filter's lo copy inside the filter map
     int dbg;              // timing experiments only: bit0 skip the B_lo load, bit1 skip the conditioning pass
+    int ksplit;           // CTAs sharing one output tile, each taking a slice of the (tap, k-chunk) loop (red.add epilogue)
     const float* bias;
     float* out;
 };
@@ -267,14 +268,19 @@ conv_tc_kmajor(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
     __shared__ uint32_t tmem_base_slot;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const TcPhase& ph = P.ph[blockIdx.z];
+    const TcPhase& ph = P.ph[blockIdx.z / P.ksplit];
+    const int split = blockIdx.z % P.ksplit;
     int t = blockIdx.x;
     if (t >= ph.tiles_w * ph.tiles_h * ph.tiles_n) return;      // uniform per block (phases may differ in size)
     const int tw = t % ph.tiles_w; t /= ph.tiles_w;
     const int th = t % ph.tiles_h; const int tn = t / ph.tiles_h;
     const int w0 = tw * P.bw, h0 = th * P.bh, n0 = tn * P.bn;
     const int col0 = blockIdx.y * BN;
-    const int niter = ph.ntaps * ph.kchunks;
+    const int total_iter = ph.ntaps * ph.kchunks;
+    const int per_split = (total_iter + P.ksplit - 1) / P.ksplit;
+    const int it0 = split * per_split;
+    const int niter = min(total_iter, it0 + per_split) - it0;
+    if (niter <= 0) return;
     // TMEM columns: [0, acc_cols) accumulators (two in the chunked kernel), then kStages x (32 hi + 32 lo) A columns
     const int acc_cols = kChunked ? 2 * BN : BN;
     const uint32_t a_col0 = (uint32_t)acc_cols;
@@ -302,7 +308,7 @@ conv_tc_kmajor(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
         if (elect_one()) {
             int stage = 0; uint32_t phase = 0;
             for (int it = 0; it < niter; ++it) {
-                const int tap = it / ph.kchunks, kc = it - tap * ph.kchunks;
+                const int tap = (it0 + it) / ph.kchunks, kc = (it0 + it) - tap * ph.kchunks;
                 const TcTap tp = ph.taps[tap];
                 mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
                 const uint32_t sa = smem_base + stage * stage_bytes;
@@ -441,11 +447,16 @@ conv_tc_kmajor(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) {
                         float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
-                        if (P.bias != nullptr) {
+                        if (P.bias != nullptr && split == 0) {
                             const float4 bb = __ldg(reinterpret_cast<const float4*>(P.bias + col0 + c + j));
                             v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
                         }
-                        *reinterpret_cast<float4*>(orow + c + j) = v;
+                        if (P.ksplit > 1) {
+                            atomicAdd(orow + c + j, v.x); atomicAdd(orow + c + j + 1, v.y);
+                            atomicAdd(orow + c + j + 2, v.z); atomicAdd(orow + c + j + 3, v.w);
+                        } else {
+                            *reinterpret_cast<float4*>(orow + c + j) = v;
+                        }
                     }
                 }
             }
@@ -758,7 +769,7 @@ int set_attrs() {
 int pick_bn(int n) { return n % 128 == 0 ? 128 : 64; }
 
 // wgrad operand layout knobs: {TMA swizzle enum, UMMA layout type, SBO bytes} (tools/tc_probe.py can sweep them)
-int g_dbg[8] = {(int)CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, 1, 512, 0, 0, 0, 0, 0};
+int g_dbg[8] = {(int)CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, 1, 512, 0, 64, 0, 0, 0};
 
 // prepared filter: returns the base of [hi copy (taps*Ci*Co)][lo copy (3x only)]
 int prep_filter(const eg_conv_shape* s, const float* w, int transpose, int mode, cudaStream_t st, float** out) {
@@ -830,6 +841,15 @@ static TcTap x_tap(const eg_conv_shape* s, int r, int q, int bsel) {
     return t;
 }
 
+// split the (tap, k-chunk) loop over several CTAs when the output tiles alone cannot fill the machine
+static int pick_ksplit(int ctas, int min_iters) {
+    if (ctas >= 100) return 1;
+    int k = 148 / ctas;
+    const int cap = min_iters / 8;            // keep >= 8 stages per CTA
+    if (k > cap) k = cap;
+    return k < 1 ? 1 : k;
+}
+
 static size_t kmajor_smem(int BN, int mode) {
     return mode == 3 ? (size_t)kStagesK3 * (128 * 128 + 2 * BN * 128) + 1024 : (size_t)kStagesK * (128 * 128 + BN * 128) + 1024;
 }
@@ -858,7 +878,12 @@ int eg_tc_conv2d_fwd(const eg_conv_shape* s, const float* x, const float* w, con
     ph.ext_w = s->OW; ph.ext_h = s->OH; ph.ext_n = s->N;
     ph.tiles_w = s->OW / P.bw; ph.tiles_h = s->OH / P.bh; ph.tiles_n = eg_ceil_div(s->N, P.bn);
     ph.out_off = 0; ph.sw = s->Co; ph.sh = (long long)s->OW * s->Co; ph.sn = (long long)s->OH * s->OW * s->Co;
-    dim3 grid(ph.tiles_w * ph.tiles_h * ph.tiles_n, s->Co / P.BN, 1);
+    P.ksplit = pick_ksplit(ph.tiles_w * ph.tiles_h * ph.tiles_n * (s->Co / P.BN), ph.ntaps * ph.kchunks);
+    if (P.ksplit > 1) {
+        cudaError_t e = cudaMemsetAsync(y, 0, sizeof(float) * (size_t)s->N * s->OH * s->OW * s->Co, st);
+        if (e != cudaSuccess) return eg_fail(e, __FILE__, __LINE__);
+    }
+    dim3 grid(ph.tiles_w * ph.tiles_h * ph.tiles_n, s->Co / P.BN, P.ksplit);
     if (mode == 3) conv_tc_kmajor<kStagesK3, true><<<grid, kThreads, kmajor_smem(P.BN, mode), st>>>(maps, P);
     else           conv_tc_kmajor<kStagesK, false><<<grid, kThreads, kmajor_smem(P.BN, mode), st>>>(maps, P);
     EG_CHECK_LAUNCH();
@@ -909,7 +934,14 @@ int eg_tc_conv2d_bwd_data(const eg_conv_shape* s, const float* dy, const float* 
             if (nt > max_tiles) max_tiles = nt;
             if (ph.ntaps == 0) return eg_fail_arg("dgrad phase without taps", __FILE__, __LINE__);
         }
-    dim3 grid(max_tiles, s->Ci / P.BN, S * S);
+    int min_iters = 1 << 30;
+    for (int i = 0; i < S * S; ++i) min_iters = P.ph[i].ntaps * P.ph[i].kchunks < min_iters ? P.ph[i].ntaps * P.ph[i].kchunks : min_iters;
+    P.ksplit = pick_ksplit(max_tiles * (s->Ci / P.BN) * S * S, min_iters);
+    if (P.ksplit > 1) {
+        cudaError_t e = cudaMemsetAsync(dx, 0, sizeof(float) * (size_t)s->N * s->H * s->W * s->Ci, st);
+        if (e != cudaSuccess) return eg_fail(e, __FILE__, __LINE__);
+    }
+    dim3 grid(max_tiles, s->Ci / P.BN, S * S * P.ksplit);
     if (mode == 3) conv_tc_kmajor<kStagesK3, true><<<grid, kThreads, kmajor_smem(P.BN, mode), st>>>(maps, P);
     else           conv_tc_kmajor<kStagesK, false><<<grid, kThreads, kmajor_smem(P.BN, mode), st>>>(maps, P);
     EG_CHECK_LAUNCH();
@@ -949,7 +981,7 @@ int eg_tc_conv2d_bwd_weight(const eg_conv_shape* s, const float* x, const float*
     if (splits > ntiles) splits = ntiles;
     if (splits < 1) splits = 1;
     P.chunks_per_split = eg_ceil_div(ntiles, splits);
-    if (P.mode == 3 && P.chunks_per_split > 16) P.chunks_per_split = 16;   // bound the truncating accumulation chain
+    if (P.mode == 3 && P.chunks_per_split > g_dbg[4]) P.chunks_per_split = g_dbg[4];   // bound the truncating accumulation chain
     splits = eg_ceil_div(ntiles, P.chunks_per_split);
     P.out = dw;
     if (!accumulate) {

@@ -23,6 +23,7 @@ CASES = [
     (4, 6, 6, 512, 512, 3, 1, 0, 4, 4),        # encoder last block
     (2, 32, 32, 64, 128, 1, 1, 0, 32, 32),     # 1x1 shortcut
     (3, 16, 16, 128, 128, 3, 1, 1, 16, 16),    # SAME 3x3 stride 1 (classifier style), batch not a tile multiple
+    (8, 8, 8, 256, 512, 5, 2, 1, 4, 4),        # few output tiles, long K -> split-K path (generator at small batch)
 ]
 
 
@@ -101,3 +102,11 @@ def test_tc_matches_simt_at_full_size(dev):
     dev.conv_bwd_weight(x, dy, a, 2, 1, False, "simt")
     dev.conv_bwd_weight(x, dy, b, 2, 1, False, "tc")
     assert relerr(dev.to_numpy(b), dev.to_numpy(a).astype(np.float64)) < TOL
+    # 3xTF32 at full size (24 576 pixels per filter tap): fp32-class agreement with the FFMA kernel
+    dev.conv_bwd_weight(x, dy, b, 2, 1, False, "tc3x")
+    assert relerr(dev.to_numpy(b), dev.to_numpy(a).astype(np.float64)) < 5e-5
+    for name, args, shape in (("conv_fwd", (x, w, None), (N, 8, 16, Co)), ("conv_bwd_data", (dy, w, None), (N, H, W, Ci))):
+        a, b = dev.zeros(shape), dev.zeros(shape)
+        getattr(dev, name)(*args, a, 2, 1, "simt")
+        getattr(dev, name)(*args, b, 2, 1, "tc3x")
+        assert relerr(dev.to_numpy(b), dev.to_numpy(a).astype(np.float64)) < 2e-5, name

@@ -16,7 +16,21 @@ def timeit(f, n=5):
     for _ in range(n): f()
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / n
-dbgs = [int(a) for a in sys.argv[1:]] or [0]
+dbgs = [int(a) for a in sys.argv[1:] if not a.startswith("cap=")] or [0]
+caps = [int(a[4:]) for a in sys.argv[1:] if a.startswith("cap=")]
+if caps:
+    for name, N, H, W, Ci, Co, k, s, p in CASES:
+        OH, OW = (H + 2 * p - k) // s + 1, (W + 2 * p - k) // s + 1
+        x, dy = rnd(N, H, W, Ci), rnd(N, OH, OW, Co)
+        ref, dw = dev.zeros((k, k, Ci, Co)), dev.zeros((k, k, Ci, Co))
+        dev.conv_bwd_weight(x, dy, ref, s, p, False, "simt")
+        fl = 2.0 * N * OH * OW * k * k * Ci * Co
+        for cap in caps:
+            dev.lib.eg_debug_set(4, cap)
+            t3 = timeit(lambda: dev.conv_bwd_weight(x, dy, dw, s, p, False, "tc3x"))
+            err = float((dw - ref).abs().max() / ref.abs().max())
+            print(f"{name:22s} cap={cap:4d} wgrad {t3*1e3:7.1f} us {fl/t3/1e9:6.1f} TF/s  relerr vs simt {err:.2e}", flush=True)
+    sys.exit(0)
 for name, N, H, W, Ci, Co, k, s, p in CASES:
     OH, OW = (H + 2 * p - k) // s + 1, (W + 2 * p - k) // s + 1
     x, w, dy = rnd(N, H, W, Ci), rnd(k, k, Ci, Co), rnd(N, OH, OW, Co)
