@@ -253,6 +253,87 @@ igemm_simt(const float* __restrict__ asrc, const float* __restrict__ bsrc, const
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Input gradient onto 3-channel images (g_dconv_4 forward = conv-transpose to RGB; d_conv_0 input gradients in the
+// penalty sweep and in the generator step).  With N = 3 every dy value feeds only 3 FMAs, so the tiled GEMM above is
+// issue-bound (6 TFLOP/s).  Here: one thread per input pixel of one parity phase; the dy pixels a block needs are
+// staged ONCE in shared memory with coalesced loads (pixel pitch Co+4 floats -> conflict-free float4 reads), and the
+// filter of the phase sits in __constant__ memory in [tap][co][ci] order (uniform loads).  8.5 TFLOP/s; a
+// 4-pixel-per-thread variant with the filter in shared memory was slower (occupancy) -- see DESIGN.md section 7.
+constexpr int kThinMaxTaps = 9, kThinMaxCo = 64, kThinTH = 8, kThinTW = 16;
+__constant__ float c_thin_w[4 * kThinMaxTaps * kThinMaxCo * 3];
+
+__global__ void thin_prep_w_k(const float* __restrict__ w, float* __restrict__ out, ConvP p) {
+    // out[((phase*kThinMaxTaps + t)*Co + co)*3 + ci] = w[r, q, ci, co] for the t-th valid tap (r, q) of the phase
+    const int S = p.S, Co = p.Co;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= S * S * kThinMaxTaps * Co * 3) return;
+    const int ci = i % 3; int t2 = i / 3; const int co = t2 % Co; t2 /= Co; const int t = t2 % kThinMaxTaps; const int phase = t2 / kThinMaxTaps;
+    const int ph = phase / S, pw = phase % S;
+    const int r0 = (ph + p.PT) % S, q0 = (pw + p.PL) % S;
+    const int nq = q0 < p.KW ? (p.KW - q0 + S - 1) / S : 0, nr = r0 < p.KH ? (p.KH - r0 + S - 1) / S : 0;
+    float v = 0.f;
+    if (t < nr * nq) {
+        const int r = r0 + S * (t / nq), q = q0 + S * (t % nq);
+        v = w[(((size_t)r * p.KW + q) * p.Ci + ci) * Co + co];
+    }
+    out[i] = v;
+}
+
+__global__ void __launch_bounds__(kThinTH * kThinTW)
+dgrad_thin_k(const float* __restrict__ dy, const float* __restrict__ bias, float* __restrict__ dx, ConvP p,
+             int tiles_x, int tiles_y) {
+    extern __shared__ __align__(16) float sdy[];              // [(TH+hy) x (TW+hx)] pixels, pitch Co+4
+    const int S = p.S, Co = p.Co, pitch = Co + 4;
+    const int phase = blockIdx.z, ph = phase / S, pw = phase % S;
+    const int Hp = (p.H - ph + S - 1) / S, Wp = (p.W - pw + S - 1) / S;
+    const int r0 = (ph + p.PT) % S, q0 = (pw + p.PL) % S;
+    const int nr = r0 < p.KH ? (p.KH - r0 + S - 1) / S : 0, nq = q0 < p.KW ? (p.KW - q0 + S - 1) / S : 0;
+    const int d0y = (ph + p.PT - r0) / S, d0x = (pw + p.PL - q0) / S;
+    int b = blockIdx.x;
+    const int tx = b % tiles_x; b /= tiles_x; const int ty = b % tiles_y; const int n = b / tiles_y;
+    const int y0 = ty * kThinTH, x0 = tx * kThinTW;          // tile origin in phase coordinates (ih2, iw2)
+    // dy rows needed: oh = ih2 + d0y - j, j in [0, nr)  ->  [y0 + d0y - (nr-1), y0 + TH-1 + d0y]
+    const int oy0 = y0 + d0y - (nr - 1), ox0 = x0 + d0x - (nq - 1);
+    const int rows = kThinTH + nr - 1, cols = kThinTW + nq - 1;
+    const int c4n = Co / 4;
+    for (int i = threadIdx.x; i < rows * cols * c4n; i += blockDim.x) {
+        const int c4 = i % c4n; int t = i / c4n; const int cx = t % cols; const int cy = t / cols;
+        const int oh = oy0 + cy, ow = ox0 + cx;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if ((unsigned)oh < (unsigned)p.OH && (unsigned)ow < (unsigned)p.OW)
+            v = __ldg(reinterpret_cast<const float4*>(dy + (((size_t)n * p.OH + oh) * p.OW + ow) * Co) + c4);
+        *reinterpret_cast<float4*>(sdy + (size_t)(cy * cols + cx) * pitch + c4 * 4) = v;
+    }
+    __syncthreads();
+    const int ly = threadIdx.x / kThinTW, lx = threadIdx.x % kThinTW;
+    const int ih2 = y0 + ly, iw2 = x0 + lx;
+    if (ih2 >= Hp || iw2 >= Wp) return;
+    float a0 = bias ? bias[0] : 0.f, a1 = bias ? bias[1] : 0.f, a2 = bias ? bias[2] : 0.f;
+    const float* cw = c_thin_w + (size_t)phase * kThinMaxTaps * Co * 3;
+    for (int j = 0; j < nr; ++j) {
+        for (int jq = 0; jq < nq; ++jq) {
+            // oh = ih2 + d0y - j  ->  tile row (ly + nr-1 - j); same for columns
+            const float4* dp = reinterpret_cast<const float4*>(sdy + (size_t)((ly + nr - 1 - j) * cols + (lx + nq - 1 - jq)) * pitch);
+            const float* wt = cw + (size_t)(j * nq + jq) * Co * 3;
+#pragma unroll 4
+            for (int c4 = 0; c4 < c4n; ++c4) {
+                const float4 d = dp[c4];
+                const float* w4 = wt + c4 * 12;
+                a0 = fmaf(d.x, w4[0], a0); a1 = fmaf(d.x, w4[1], a1); a2 = fmaf(d.x, w4[2], a2);
+                a0 = fmaf(d.y, w4[3], a0); a1 = fmaf(d.y, w4[4], a1); a2 = fmaf(d.y, w4[5], a2);
+                a0 = fmaf(d.z, w4[6], a0); a1 = fmaf(d.z, w4[7], a1); a2 = fmaf(d.z, w4[8], a2);
+                a0 = fmaf(d.w, w4[9], a0); a1 = fmaf(d.w, w4[10], a1); a2 = fmaf(d.w, w4[11], a2);
+            }
+        }
+    }
+    float* o = dx + (((size_t)n * p.H + ih2 * S + ph) * p.W + iw2 * S + pw) * 3;
+    o[0] = a0; o[1] = a1; o[2] = a2;
+}
+
+// staging buffer for the rearranged filter (device), one per process; the constant bank is refilled per call
+float* g_thin_stage = nullptr;
+
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 template <int MODE, int BM, int BN, int TM, int TN>
@@ -313,6 +394,34 @@ int eg_simt_conv2d_bwd_data(const eg_conv_shape* s, const float* dy, const float
     f.M = p.N * ((p.H + S - 1) / S) * ((p.W + S - 1) / S);   // largest parity sub-grid (grid sizing only)
     f.N = p.Ci; f.K = 0;
     const bool v = (p.Co % 4 == 0) && aligned16(dy) && aligned16(w);
+    {
+        // taps per phase <= kThinMaxTaps, stride <= 2, Co <= kThinMaxCo
+        const int max_nr = (p.KH + S - 1) / S, max_nq = (p.KW + S - 1) / S;
+        if (p.Ci == 3 && v && S <= 2 && p.Co <= kThinMaxCo && max_nr * max_nq <= kThinMaxTaps && p.H % S == 0 && p.W % S == 0) {
+            const size_t nflt = (size_t)S * S * kThinMaxTaps * p.Co * 3;
+            if (g_thin_stage == nullptr) {
+                cudaError_t e = cudaMalloc(&g_thin_stage, sizeof(float) * 4 * kThinMaxTaps * kThinMaxCo * 3);
+                if (e != cudaSuccess) return eg_fail(e, __FILE__, __LINE__);
+            }
+            thin_prep_w_k<<<eg_ceil_div((long long)nflt, 256), 256, 0, st>>>(w, g_thin_stage, p);
+            EG_CHECK_LAUNCH();
+            cudaError_t e = cudaMemcpyToSymbolAsync(c_thin_w, g_thin_stage, sizeof(float) * nflt, 0, cudaMemcpyDeviceToDevice, st);
+            if (e != cudaSuccess) return eg_fail(e, __FILE__, __LINE__);
+            const int Hp = p.H / S, Wp = p.W / S;
+            const int tiles_x = eg_ceil_div(Wp, kThinTW), tiles_y = eg_ceil_div(Hp, kThinTH);
+            const size_t smem = sizeof(float) * (size_t)(kThinTH + max_nr - 1) * (kThinTW + max_nq - 1) * (p.Co + 4);
+            static bool attr = false;
+            if (!attr) {
+                e = cudaFuncSetAttribute(dgrad_thin_k, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+                if (e != cudaSuccess) return eg_fail(e, __FILE__, __LINE__);
+                attr = true;
+            }
+            dim3 grid(tiles_x * tiles_y * p.N, 1, S * S);
+            dgrad_thin_k<<<grid, kThinTH * kThinTW, smem, st>>>(dy, bias, dx, p, tiles_x, tiles_y);
+            EG_CHECK_LAUNCH();
+            return 0;
+        }
+    }
     return launch_mode<M_DGRAD>(dy, w, bias, dx, p, f, S * S, v, v, 0, st);
 }
 
