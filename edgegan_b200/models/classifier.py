@@ -110,6 +110,15 @@ class Classifier(object):
             ws = ops.buf(scope + "/sn_ws", (ops.sn_ws_floats(K, Cn),))
             ops.spectral_norm_fwd(W, self.aux.var[scope + "/u"], wb, ws)
             self.wbar[scope], self.ws[scope] = wb, ws
+            if scope.endswith("/update_gate"):
+                # conv(concat(a, inp)) = conv(a, W[:, :, :hd]) + conv(inp, W[:, :, hd:]): two contiguous filter copies, so
+                # the hd-channel part runs on the tensor cores (hd + 3 input channels would not) and no concat is built
+                k, _, cin, co = W.shape
+                hd = cin - self.c_dim
+                wa, wi = ops.buf(scope + "/wbar_a", (k, k, hd, co)), ops.buf(scope + "/wbar_i", (k, k, self.c_dim, co))
+                ops.copy2d(wb, 0, cin * co, wa, 0, hd * co, k * k, hd * co)
+                ops.copy2d(wb, hd * co, cin * co, wi, 0, self.c_dim * co, k * k, self.c_dim * co)
+                self.wbar[scope + "#a"], self.wbar[scope + "#i"] = wa, wi
         self._wbar_valid = True
 
     # ---- forward -------------------------------------------------------------------------------------
@@ -140,11 +149,11 @@ class Classifier(object):
             U = lambda key, c: B(f"u{t}/{key}", (n, H, H, c))
             a_in = U("a_in", hd)
             ops.prelu_fwd(ht, self._v(f"{p}/norm_activation_in/prelu/param"), a_in)
-            full = U("full", hd + self.c_dim)
-            ops.copy_cslice(a_in, 0, full, 0, hd)
-            ops.copy_cslice(inp, 0, full, hd, self.c_dim)
-            cg, rgl, rg = U("cg", hd), U("rgl", hd), U("rg", hd)
-            self._conv(f"{p}/update_gate", full, cg, 3)
+            cg, cg_i, rgl, rg = U("cg", hd), U("cg_i", hd), U("rgl", hd), U("rg", hd)
+            gate = f"{nm}/{p}/update_gate"
+            ops.conv_fwd(a_in, self.wbar[gate + "#a"], self.store.var[gate + "/biases"].view(-1), cg, 1, 1)
+            ops.conv_fwd(inp, self.wbar[gate + "#i"], None, cg_i, 1, 1)
+            ops.axpby(cg_i, cg, 1.0, 1.0)
             ops.act_fwd(cg, rgl, "lrelu2")
             mm = B(f"u{t}/mm", (n, hd, 2))
             ops.minmax_fwd(rgl, rg, mm)
@@ -160,7 +169,7 @@ class Classifier(object):
             self._conv(f"{p}/Conv_3", ht, ho, 1)
             out = B(f"u{t}/out", (n, H // 2, H // 2, fd))
             ops.add_pool2_fwd(ho, hn2, out)
-            units.append(dict(p=p, hd=hd, fd=fd, ht=ht, inp=inp, a_in=a_in, full=full, cg=cg, rgl=rgl, rg=rg, mm=mm,
+            units.append(dict(p=p, hd=hd, fd=fd, ht=ht, inp=inp, a_in=a_in, cg=cg, rgl=rgl, rg=rg, mm=mm,
                               img=img, plus=plus, hin=hin, c1=c1, hn1=hn1))
             ht = out
         hl = B("hlast", ht.shape)
@@ -251,12 +260,21 @@ class Classifier(object):
             g_rgl, g_cg = U("g_rgl", hd), U("g_cg", hd)
             ops.minmax_bwd(u["rgl"], u["mm"], g_rg, g_rgl)
             ops.act_bwd(u["cg"], g_rgl, g_cg, "lrelu2")
+            gate = f"{nm}/{p}/update_gate"
             if param_grads:
-                self._wgrad(f"{p}/update_gate", u["full"], g_cg, 3, tag)
-            g_full = U("g_full", hd + self.c_dim)
-            ops.conv_bwd_data(g_cg, wb("update_gate"), None, g_full, 1, 1)
+                # dL/dWbar of the two filter parts, assembled into the [k, k, hd+3, hd] layout for the spectral-norm backward
+                Wg = self.store.var[gate + "/weights"]
+                cin, co = hd + self.c_dim, hd
+                gbar = self._gbar[:Wg.numel()].view(Wg.shape)
+                ga, gi_w = B(f"u{t}/gbar_a", (3, 3, hd, co)), B(f"u{t}/gbar_i", (3, 3, self.c_dim, co))
+                ops.conv_bwd_weight(u["a_in"], g_cg, ga, 1, 1, False)
+                ops.conv_bwd_weight(inp, g_cg, gi_w, 1, 1, False)
+                ops.copy2d(ga, 0, hd * co, gbar, 0, cin * co, 9, hd * co)
+                ops.copy2d(gi_w, 0, self.c_dim * co, gbar, hd * co, cin * co, 9, self.c_dim * co)
+                ops.spectral_norm_bwd(Wg, self.aux.var[gate + "/u"], self.ws[gate], gbar, self.store.g[gate + "/weights"])
+                ops.bias_grad(g_cg, self.store.g[gate + "/biases"].view(-1), False)
             g_ain, g_ht2 = U("g_ain", hd), U("g_ht2", hd)
-            ops.copy_cslice(g_full, 0, g_ain, 0, hd)
+            ops.conv_bwd_data(g_cg, self.wbar[gate + "#a"], None, g_ain, 1, 1)
             ops.prelu_bwd(htu, self._v(f"{p}/norm_activation_in/prelu/param"), g_ain, g_ht2,
                           self._g(f"{p}/norm_activation_in/prelu/param") if param_grads else None)
             ops.axpby(g_ht2, g_ht, 1.0, 1.0)
@@ -264,7 +282,7 @@ class Classifier(object):
                 gi = B(f"g_pyr{t - 1}", inp.shape)
                 ops.conv_bwd_data(g_img, wb("Conv"), None, gi, 1, 1)
                 gi2 = U("g_inp2", self.c_dim)
-                ops.copy_cslice(g_full, hd, gi2, 0, self.c_dim)
+                ops.conv_bwd_data(g_cg, self.wbar[gate + "#i"], None, gi2, 1, 1)
                 ops.axpby(gi2, gi, 1.0, 1.0)
                 g_pyr[t - 1] = gi
             g_out = g_ht

@@ -204,6 +204,12 @@ class DeviceOps:
         _lib.check(self.lib.eg_copy2d(src.data_ptr() + 4 * src_w0 * Cn, Ws * Cn, dst.data_ptr() + 4 * dst_w0 * Cn,
                                       Wd * Cn, N * H, width * Cn, self._st), "copy2d")
 
+    def copy2d(self, src, src_off, src_stride, dst, dst_off, dst_stride, rows, cols):
+        """dst.flat[dst_off + r*dst_stride + c] = src.flat[src_off + r*src_stride + c]  (element units)"""
+        self.launches += 1
+        _lib.check(self.lib.eg_copy2d(src.data_ptr() + 4 * src_off, src_stride, dst.data_ptr() + 4 * dst_off, dst_stride,
+                                      rows, cols, self._st), "copy2d")
+
     def copy(self, src, dst):
         self.launches += 1
         _lib.check(self.lib.eg_copy2d(_p(src), src.numel(), _p(dst), dst.numel(), 1, src.numel(), self._st), "copy2d")

@@ -253,6 +253,11 @@ class RefOps:
     def copy_wslice(self, src, src_w0, dst, dst_w0, width):
         dst[:, :, dst_w0:dst_w0 + width, :] = src[:, :, src_w0:src_w0 + width, :]
 
+    def copy2d(self, src, src_off, src_stride, dst, dst_off, dst_stride, rows, cols):
+        sf, df = src.reshape(-1), dst.reshape(-1)
+        for r in range(rows):
+            df[dst_off + r * dst_stride: dst_off + r * dst_stride + cols] = sf[src_off + r * src_stride: src_off + r * src_stride + cols]
+
     def copy(self, src, dst):
         dst.copy_(src.reshape(dst.shape))
 

@@ -8,11 +8,18 @@ from edgegan_b200.ops import DeviceOps
 
 B = int(os.environ.get("B", "64"))
 ops = DeviceOps()
-flags = Flags(batch_size=B, multiclasses=False); flags.num_classes = None
+MULTI = os.environ.get("MULTI", "0") == "1"
+flags = Flags(batch_size=B, multiclasses=MULTI)
+if not MULTI:
+    flags.num_classes = None
 m = EdgeGAN(None, flags, None, ops=ops, seed=1)
 m.build_train_model()
 rs = np.random.RandomState(0)
-img = ops.from_numpy(rs.uniform(-1, 1, (B, 64, 128, 3))); z = ops.from_numpy(rs.normal(size=(B, 100)))
+img = ops.from_numpy(rs.uniform(-1, 1, (B, 64, 128, 3)))
+zn = rs.normal(size=(B, 100))
+if MULTI:
+    zn = np.concatenate([zn, rs.randint(0, 14, (B, 1))], 1)
+z = ops.from_numpy(zn)
 al = ops.from_numpy(rs.uniform(0, 1, (3, B)))
 for _ in range(2):
     m.update_model(img, z, al, 0.3)
@@ -32,6 +39,10 @@ def wrap(name):
 for n in orig: setattr(ops, n, wrap(n))
 m.update_model(img, z, al, 0.3)
 torch.cuda.synchronize()
+ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+for n, f in orig.items(): setattr(ops, n, f)
+ev0.record(); m.update_model(img, z, al, 0.3); ev1.record(); torch.cuda.synchronize()
+print(f"step ms {ev0.elapsed_time(ev1):.2f}")
 agg = collections.OrderedDict()
 for key, fl, e0, e1 in recs:
     a = agg.setdefault(key, [0, 0.0, 0.0]); a[0] += 1; a[1] += e0.elapsed_time(e1); a[2] += fl
