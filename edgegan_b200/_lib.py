@@ -61,8 +61,8 @@ SIGNATURES = {
     "eg_addrelu_pool2_bwd": [vp, vp, vp, vp, i32, i32, i32, i32, vp],
     "eg_relu_globalmean_fwd": [vp, vp, i32, i32, i32, vp],
     "eg_relu_globalmean_bwd": [vp, vp, vp, i32, i32, i32, vp],
-    "eg_reparam_fwd": [vp, vp, f32, vp, i64, vp],
-    "eg_zl1_loss_bwd": [vp, vp, f32, vp, i32, i32, i32, f32, f32, vp, vp, vp, vp],
+    "eg_reparam_fwd": [vp, vp, f32, vp, vp, i64, vp],
+    "eg_zl1_loss_bwd": [vp, vp, f32, vp, vp, i32, i32, i32, f32, f32, vp, vp, vp, vp],
     "eg_prelu_fwd": [vp, vp, vp, i64, vp],
     "eg_prelu_bwd": [vp, vp, vp, vp, vp, i64, i32, vp],
     "eg_minmax_fwd": [vp, vp, vp, i32, i32, i32, vp],

@@ -301,17 +301,20 @@ __global__ void relu_globalmean_bwd_k(const float* __restrict__ x, const float* 
     const int c = (int)(i % C); const long long n = i / ((long long)P * C);
     gx[i] = x[i] > 0.f ? gy[n * C + c] / P : 0.f;
 }
-__global__ void reparam_fwd_k(const float* __restrict__ mu, const float* __restrict__ ls, float eps, float* __restrict__ z, long long n) {
+__global__ void reparam_fwd_k(const float* __restrict__ mu, const float* __restrict__ ls, float eps, const float* __restrict__ eps_dev,
+                              float* __restrict__ z, long long n) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (eps_dev != nullptr) eps = eps_dev[0];
     if (i < n) z[i] = mu[i] + eps * expf(ls[i]);
 }
 __global__ void __launch_bounds__(TB)
-zl1_loss_bwd_k(const float* __restrict__ mu, const float* __restrict__ ls, float eps, const float* __restrict__ target,
+zl1_loss_bwd_k(const float* __restrict__ mu, const float* __restrict__ ls, float eps, const float* __restrict__ eps_dev, const float* __restrict__ target,
                int tstride, int B, int Z, float weight, float inv_count, float* __restrict__ gmu,
                float* __restrict__ gls, float* __restrict__ loss) {
     __shared__ float red[33];
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     float l = 0.f;
+    if (eps_dev != nullptr) eps = eps_dev[0];
     if (i < B * Z) {
         const int b = i / Z, j = i % Z;
         const float e = expf(ls[i]);
@@ -473,15 +476,15 @@ int eg_relu_globalmean_bwd(const float* x, const float* gy, float* gx, int N, in
     relu_globalmean_bwd_k<<<grid1d((long long)N * P * C), TB, 0, ST>>>(x, gy, gx, (long long)N * P * C, P, C);
     EG_CHECK_LAUNCH(); return 0;
 }
-int eg_reparam_fwd(const float* mu, const float* ls, float eps, float* z, long long n, void* stream) {
+int eg_reparam_fwd(const float* mu, const float* ls, float eps, const float* eps_dev, float* z, long long n, void* stream) {
     EG_REQUIRE(mu && ls && z && n > 0);
-    reparam_fwd_k<<<grid1d(n), TB, 0, ST>>>(mu, ls, eps, z, n);
+    reparam_fwd_k<<<grid1d(n), TB, 0, ST>>>(mu, ls, eps, eps_dev, z, n);
     EG_CHECK_LAUNCH(); return 0;
 }
-int eg_zl1_loss_bwd(const float* mu, const float* ls, float eps, const float* target, int target_stride, int B,
-                    int Z, float weight, float inv_global_count, float* gmu, float* gls, float* loss, void* stream) {
+int eg_zl1_loss_bwd(const float* mu, const float* ls, float eps, const float* eps_dev, const float* target, int target_stride,
+                    int B, int Z, float weight, float inv_global_count, float* gmu, float* gls, float* loss, void* stream) {
     EG_REQUIRE(mu && ls && target && gmu && gls && loss && B > 0 && Z > 0 && target_stride >= Z);
-    zl1_loss_bwd_k<<<grid1d((long long)B * Z), TB, 0, ST>>>(mu, ls, eps, target, target_stride, B, Z, weight,
+    zl1_loss_bwd_k<<<grid1d((long long)B * Z), TB, 0, ST>>>(mu, ls, eps, eps_dev, target, target_stride, B, Z, weight,
                                                            inv_global_count, gmu, gls, loss);
     EG_CHECK_LAUNCH(); return 0;
 }

@@ -269,7 +269,10 @@ class EdgeGAN(object):
             self._rs = rs
             alpha = ops.from_numpy(rs.uniform(0, 1, (3, n)).astype(np.float32))
             eps = float(rs.normal()) if eps is None else eps
-        eps = 0.0 if eps is None else float(eps)
+        if eps is None:
+            eps = 0.0
+        elif not hasattr(eps, "data_ptr"):
+            eps = float(eps)          # python scalar; a 1-element device tensor keeps a captured graph re-playable
         todo = runs or [r for r in RUN_NAMES if r != "d_optim2" or self.multiclass]
         zin = self._g_input(z)
         G1, G2 = self.edge_generator, self.image_generator
@@ -327,6 +330,24 @@ class EdgeGAN(object):
             elif run == "g_optim_b":
                 self._generator_run(run, zin, z, fresh_forward=True)
                 fakes_fresh = False
+
+    def capture_step(self, images, z, alpha, eps, warmup=2):
+        """Capture one update_model into a CUDA graph over STATIC device buffers (images, z, alpha and a 1-element
+        device tensor eps): refill the buffers, then `graph.replay()`.  The step allocates nothing after its first
+        call and takes every scalar input from device memory, so the ~650 launches replay without host work.
+        Runs `warmup` real steps first (they update the weights like any other step)."""
+        import torch
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(warmup):
+                self.update_model(images, z, alpha, eps)
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=s):
+            self.update_model(images, z, alpha, eps)
+        return g
 
     def read_losses(self):
         """host copy of the loss scalars of the last step (one device->host read)."""

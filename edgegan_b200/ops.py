@@ -279,12 +279,14 @@ class DeviceOps:
 
     def reparam_fwd(self, mu, ls, eps, z):
         self.launches += 1
-        _lib.check(self.lib.eg_reparam_fwd(_p(mu), _p(ls), float(eps), _p(z), mu.numel(), self._st), "reparam_fwd")
+        ed = eps if isinstance(eps, torch.Tensor) else None       # device scalar (graph replay) or python float
+        _lib.check(self.lib.eg_reparam_fwd(_p(mu), _p(ls), 0.0 if ed is not None else float(eps), _p(ed), _p(z), mu.numel(), self._st), "reparam_fwd")
 
     def zl1_loss_bwd(self, mu, ls, eps, target, weight, inv_global_count, gmu, gls, loss):
         B, Z = mu.shape
         self.launches += 1
-        _lib.check(self.lib.eg_zl1_loss_bwd(_p(mu), _p(ls), float(eps), _p(target), target.shape[1], B, Z, float(weight),
+        ed = eps if isinstance(eps, torch.Tensor) else None
+        _lib.check(self.lib.eg_zl1_loss_bwd(_p(mu), _p(ls), 0.0 if ed is not None else float(eps), _p(ed), _p(target), target.shape[1], B, Z, float(weight),
                                             float(inv_global_count), _p(gmu), _p(gls), _p(loss), self._st), "zl1_loss_bwd")
 
     def onehot_concat(self, z, zdim, classes, out):

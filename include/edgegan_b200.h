@@ -146,12 +146,15 @@ int eg_addrelu_pool2_bwd(const float* a, const float* b, const float* gy, float*
 /* y[n,c] = mean_p relu(x[n,p,c])   (encoder.py:69-71: relu, 8x8 SAME avg pool over a <=8x8 map, flatten) */
 int eg_relu_globalmean_fwd(const float* x, float* y, int N, int P, int C, void* stream);
 int eg_relu_globalmean_bwd(const float* x, const float* gy, float* gx, int N, int P, int C, void* stream);
-/* z = mu + eps * exp(log_sigma)   (encoder.py:78-82; eps is ONE scalar for the whole batch) */
-int eg_reparam_fwd(const float* mu, const float* ls, float eps, float* z, long long n, void* stream);
+/* z = mu + eps * exp(log_sigma)   (encoder.py:78-82; eps is ONE scalar for the whole batch).
+ * eps_dev, when not NULL, is a device scalar that overrides `eps` (keeps a captured CUDA graph re-playable) */
+int eg_reparam_fwd(const float* mu, const float* ls, float eps, const float* eps_dev, float* z, long long n,
+                   void* stream);
 /* loss[0] += weight * mean|target - z| ; gmu = dloss/dmu ; gls = dloss/dls   (functional.py:40-41, edgegan.py:337-342)
  * target has row stride `target_stride` (z carries a trailing class-id column in multi-class mode) */
-int eg_zl1_loss_bwd(const float* mu, const float* ls, float eps, const float* target, int target_stride, int B,
-                    int Z, float weight, float inv_global_count, float* gmu, float* gls, float* loss, void* stream);
+int eg_zl1_loss_bwd(const float* mu, const float* ls, float eps, const float* eps_dev, const float* target,
+                    int target_stride, int B, int Z, float weight, float inv_global_count, float* gmu, float* gls,
+                    float* loss, void* stream);
 
 /* ---- multi-class classifier D2 (models/classifier.py:12-119, nn/modules/conv.py:133-357) ---------------- */
 /* prelu: tf.maximum(leak*x, x) with a learned scalar leak held in device memory (activation.py:23-27).

@@ -321,11 +321,13 @@ class RefOps:
         gx.copy_(g.reshape(gx.shape))
 
     def reparam_fwd(self, mu, ls, eps, z):
+        eps = eps.reshape(()) if isinstance(eps, torch.Tensor) else eps
         z.copy_(mu + eps * torch.exp(ls))
 
     def zl1_loss_bwd(self, mu, ls, eps, target, weight, inv_global_count, gmu, gls, loss):
         Z = mu.shape[1]
         e = torch.exp(ls)
+        eps = eps.reshape(()) if isinstance(eps, torch.Tensor) else eps
         diff = target[:, :Z] - (mu + eps * e)
         loss.add_(weight * inv_global_count * diff.abs().sum())
         gz = -weight * inv_global_count * torch.sign(diff)
