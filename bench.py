@@ -211,7 +211,9 @@ def main():
     s_eps = torch.zeros(1, dtype=torch.float32, device=ops.device)
     eps_host = [torch.tensor([e], dtype=torch.float32).pin_memory() for _, _, _, e in host]
     eps_dev = [t.cuda() for t in eps_host]
-    if not args.no_graph and not args.ncu:
+    if world > 1:
+        graph_note = "eager launches (NCCL all-reduces between the runs are not captured)"
+    elif not args.no_graph and not args.ncu:
         try:
             s_img.copy_(dev_sets[0][0]); s_z.copy_(dev_sets[0][1]); s_al.copy_(dev_sets[0][2])
             graph = model.capture_step(s_img, s_z, s_al, s_eps)
