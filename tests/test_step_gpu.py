@@ -160,3 +160,26 @@ def test_step_is_deterministic_enough_and_finite():
     for k in outs[0]:
         assert np.isfinite(outs[0][k]).all(), k
         assert np.abs(outs[0][k] - outs[1][k]).max() < 2e-5, k      # split-K atomics reorder fp32 sums
+
+
+def test_nn_functional_mirror_on_device():
+    """edgegan_b200.nn (reference op signatures) on the GPU: the critic assembled like discriminator.py:61-76."""
+    from edgegan_b200 import nn
+    from edgegan_b200.ops import DeviceOps
+    cfg = O.Config(batch_size=4, multiclasses=False)
+    rs = np.random.RandomState(0)
+    v = O.discriminator_variables(cfg, "D", 64, 128, rs)
+    x = rs.uniform(-1, 1, (4, 64, 128, 3)).astype(np.float32)
+    ops = DeviceOps()
+    ops.set_default_algo("tc3x")
+    with nn.variable_context(ops, variables=v):
+        with nn.variable_scope("D"):
+            D = nn.conv_block(ops.from_numpy(x), 64, "d_conv_0", 4, 2, True, False, None, "lrelu")
+            D = nn.conv_block(D, 128, "d_conv_1", 4, 2, True, False, "instance", "lrelu")
+            D = nn.conv_block(D, 256, "d_conv_3", 4, 2, True, False, "instance", "lrelu")
+            D = nn.conv_block(D, 512, "d_conv_4", 4, 2, True, False, "instance", "lrelu")
+            d = nn.linear(D.reshape(4, -1), 1, name="d_linear_5")
+    vt = {k: torch.tensor(a, dtype=torch.float64) for k, a in v.items()}
+    _, want = O.discriminator(vt, "D", torch.tensor(x, dtype=torch.float64))
+    got = ops.to_numpy(d).astype(np.float64)
+    assert np.abs(got - want.numpy()).max() < 1e-4 * max(1.0, np.abs(want.numpy()).max())
