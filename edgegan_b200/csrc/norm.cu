@@ -126,6 +126,112 @@ instnorm_bwd2_k(const float* __restrict__ x, const float* __restrict__ stats, co
 }
 
 // ---------------------------------------------------------------------------------------------------
+// float4 variants (C % 4 == 0, 16-byte aligned): a thread owns 4 consecutive channels, 8 threads cover the 32-channel
+// slab, 32 rows of the slab are in flight per block iteration -> 4x fewer load instructions, 4x the bytes in flight.
+constexpr int VQ = 8, VR = 32;     // channel quads per block, row-threads
+
+template <int K>
+__device__ __forceinline__ void reduce_cols4(float4 (&v)[K], float4 (*sm)[VR][VQ]) {
+    const int cx = threadIdx.x, ry = threadIdx.y;
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < K; ++k) sm[k][ry][cx] = v[k];
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 8
+        for (int r = 0; r < VR; ++r) { const float4 t = sm[k][r][cx]; s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w; }
+        v[k] = s;
+    }
+}
+#define F4OP(dst, expr) { dst.x = expr(x); dst.y = expr(y); dst.z = expr(z); dst.w = expr(w); }
+
+__global__ void __launch_bounds__(VQ * VR)
+instnorm_fwd_v4(const float* __restrict__ x, float* __restrict__ y, float* __restrict__ stats, int P, int C, float eps, int act) {
+    __shared__ float4 sm[1][VR][VQ];
+    const int n = blockIdx.y, c = (blockIdx.x * VQ + threadIdx.x) * 4;
+    const bool ok = c < C;
+    const float4* xp = reinterpret_cast<const float4*>(x + (size_t)n * P * C + c);
+    const size_t pitch = C / 4;
+    float4 v[1] = {make_float4(0.f, 0.f, 0.f, 0.f)};
+    if (ok) for (int p = threadIdx.y; p < P; p += VR) { const float4 t = __ldg(xp + p * pitch); v[0].x += t.x; v[0].y += t.y; v[0].z += t.z; v[0].w += t.w; }
+    reduce_cols4<1>(v, sm);
+    const float4 mean = make_float4(v[0].x / P, v[0].y / P, v[0].z / P, v[0].w / P);
+    v[0] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (ok) for (int p = threadIdx.y; p < P; p += VR) {
+        const float4 t = __ldg(xp + p * pitch);
+        float d;
+        d = t.x - mean.x; v[0].x = fmaf(d, d, v[0].x); d = t.y - mean.y; v[0].y = fmaf(d, d, v[0].y);
+        d = t.z - mean.z; v[0].z = fmaf(d, d, v[0].z); d = t.w - mean.w; v[0].w = fmaf(d, d, v[0].w);
+    }
+    reduce_cols4<1>(v, sm);
+    if (!ok) return;
+    const float4 sd = make_float4(sqrtf(v[0].x / P), sqrtf(v[0].y / P), sqrtf(v[0].z / P), sqrtf(v[0].w / P));
+    const float4 r = make_float4(1.f / (sd.x + eps), 1.f / (sd.y + eps), 1.f / (sd.z + eps), 1.f / (sd.w + eps));
+    if (threadIdx.y == 0) {
+        float* st = stats + ((size_t)n * C + c) * 2;
+        st[0] = mean.x; st[1] = sd.x; st[2] = mean.y; st[3] = sd.y; st[4] = mean.z; st[5] = sd.z; st[6] = mean.w; st[7] = sd.w;
+    }
+    float4* yp = reinterpret_cast<float4*>(y + (size_t)n * P * C + c);
+    for (int p = threadIdx.y; p < P; p += VR) {
+        const float4 t = __ldg(xp + p * pitch);
+        float4 o;
+        o.x = act_fwd(act, (t.x - mean.x) * r.x); o.y = act_fwd(act, (t.y - mean.y) * r.y);
+        o.z = act_fwd(act, (t.z - mean.z) * r.z); o.w = act_fwd(act, (t.w - mean.w) * r.w);
+        yp[p * pitch] = o;
+    }
+}
+
+struct Stat4 { float4 mean, sd, r; };
+__device__ __forceinline__ Stat4 load_stats4(const float* stats, size_t idx, float eps) {
+    const float4 a = *reinterpret_cast<const float4*>(stats + idx * 2), b = *reinterpret_cast<const float4*>(stats + idx * 2 + 4);
+    Stat4 s;
+    s.mean = make_float4(a.x, a.z, b.x, b.z); s.sd = make_float4(a.y, a.w, b.y, b.w);
+    s.r = make_float4(1.f / (s.sd.x + eps), 1.f / (s.sd.y + eps), 1.f / (s.sd.z + eps), 1.f / (s.sd.w + eps));
+    return s;
+}
+
+__global__ void __launch_bounds__(VQ * VR)
+instnorm_bwd_v4(const float* __restrict__ x, const float* __restrict__ stats, const float* __restrict__ gy,
+                const float* __restrict__ addend, float* __restrict__ gx, int P, int C, float eps, int act) {
+    __shared__ float4 sm[2][VR][VQ];
+    const int n = blockIdx.y, c = (blockIdx.x * VQ + threadIdx.x) * 4;
+    const bool ok = c < C;
+    const size_t base = (size_t)n * P * C + c, pitch = C / 4;
+    const float4* xp = reinterpret_cast<const float4*>(x + base);
+    const float4* gp = reinterpret_cast<const float4*>(gy + base);
+    Stat4 s{};
+    if (ok) s = load_stats4(stats, (size_t)n * C + c, eps);
+    float4 v[2] = {make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f)};
+    if (ok) for (int p = threadIdx.y; p < P; p += VR) {
+        const float4 t = __ldg(xp + p * pitch), g = __ldg(gp + p * pitch);
+        float cc, gn;
+        cc = t.x - s.mean.x; gn = g.x * act_grad(act, cc * s.r.x); v[0].x += gn; v[1].x = fmaf(gn, cc, v[1].x);
+        cc = t.y - s.mean.y; gn = g.y * act_grad(act, cc * s.r.y); v[0].y += gn; v[1].y = fmaf(gn, cc, v[1].y);
+        cc = t.z - s.mean.z; gn = g.z * act_grad(act, cc * s.r.z); v[0].z += gn; v[1].z = fmaf(gn, cc, v[1].z);
+        cc = t.w - s.mean.w; gn = g.w * act_grad(act, cc * s.r.w); v[0].w += gn; v[1].w = fmaf(gn, cc, v[1].w);
+    }
+    reduce_cols4<2>(v, sm);
+    if (!ok) return;
+    const float4 mg = make_float4(v[0].x / P, v[0].y / P, v[0].z / P, v[0].w / P);
+    const float4 kq = make_float4(s.r.x * s.r.x / s.sd.x * (v[1].x / P), s.r.y * s.r.y / s.sd.y * (v[1].y / P),
+                                  s.r.z * s.r.z / s.sd.z * (v[1].z / P), s.r.w * s.r.w / s.sd.w * (v[1].w / P));
+    const float4* ap = addend ? reinterpret_cast<const float4*>(addend + base) : nullptr;
+    float4* op = reinterpret_cast<float4*>(gx + base);
+    for (int p = threadIdx.y; p < P; p += VR) {
+        const float4 t = __ldg(xp + p * pitch), g = __ldg(gp + p * pitch);
+        float4 o; float cc, gn;
+        cc = t.x - s.mean.x; gn = g.x * act_grad(act, cc * s.r.x); o.x = s.r.x * (gn - mg.x) - kq.x * cc;
+        cc = t.y - s.mean.y; gn = g.y * act_grad(act, cc * s.r.y); o.y = s.r.y * (gn - mg.y) - kq.y * cc;
+        cc = t.z - s.mean.z; gn = g.z * act_grad(act, cc * s.r.z); o.z = s.r.z * (gn - mg.z) - kq.z * cc;
+        cc = t.w - s.mean.w; gn = g.w * act_grad(act, cc * s.r.w); o.w = s.r.w * (gn - mg.w) - kq.w * cc;
+        if (ap) { const float4 a = __ldg(ap + p * pitch); o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w; }
+        op[p * pitch] = o;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // batch norm over rows of x[R, C]
 
 __global__ void __launch_bounds__(CG * RY)
@@ -195,6 +301,12 @@ extern "C" {
 
 int eg_instnorm_fwd(const float* x, float* y, float* stats, int N, int P, int C, float eps, int act, void* stream) {
     EG_REQUIRE(x && y && stats && N > 0 && P > 0 && C > 0 && N <= 65535);
+    if (C % 4 == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(stats)) & 15) == 0) {
+        dim3 grid(eg_ceil_div(C, VQ * 4), N), block(VQ, VR);
+        instnorm_fwd_v4<<<grid, block, 0, (cudaStream_t)stream>>>(x, y, stats, P, C, eps, act);
+        EG_CHECK_LAUNCH();
+        return 0;
+    }
     dim3 grid(eg_ceil_div(C, CG), N), block(CG, RY);
     instnorm_fwd_k<<<grid, block, 0, (cudaStream_t)stream>>>(x, y, stats, P, C, eps, act);
     EG_CHECK_LAUNCH();
@@ -204,6 +316,13 @@ int eg_instnorm_fwd(const float* x, float* y, float* stats, int N, int P, int C,
 int eg_instnorm_bwd(const float* x, const float* stats, const float* gy, const float* addend, float* gx, int N,
                     int P, int C, float eps, int act, void* stream) {
     EG_REQUIRE(x && stats && gy && gx && N > 0 && P > 0 && C > 0 && N <= 65535);
+    if (C % 4 == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(gy) | reinterpret_cast<uintptr_t>(gx) |
+                        reinterpret_cast<uintptr_t>(stats) | reinterpret_cast<uintptr_t>(addend)) & 15) == 0) {
+        dim3 grid(eg_ceil_div(C, VQ * 4), N), block(VQ, VR);
+        instnorm_bwd_v4<<<grid, block, 0, (cudaStream_t)stream>>>(x, stats, gy, addend, gx, P, C, eps, act);
+        EG_CHECK_LAUNCH();
+        return 0;
+    }
     dim3 grid(eg_ceil_div(C, CG), N), block(CG, RY);
     instnorm_bwd_k<<<grid, block, 0, (cudaStream_t)stream>>>(x, stats, gy, addend, gx, P, C, eps, act);
     EG_CHECK_LAUNCH();
