@@ -102,7 +102,7 @@ def test_multi_class_runs_from_identical_weights(run, algo):
         if np.abs(col64[run]["grads"][name]).max() < 1e-9:
             for c in (col64, col32):
                 c[run]["grads"].pop(name)
-    report, fails = check_grads(grads, col64, col32, 2e-3, sens=sens)
+    report, fails = check_grads(grads, col64, col32, 1e-2 if run.startswith("g_optim") else 2e-3, sens=sens)
     print(run, algo, report)
     assert not fails, fails[:5]
     losses = m.read_losses()
@@ -127,7 +127,9 @@ def test_single_runs_from_identical_weights(run, algo):
     m.run_hook = lambda r, model: grads.__setitem__(r, model.export_variables("grad"))
     m.update_model(ops.from_numpy(inp.images), ops.from_numpy(inp.z), ops.from_numpy(inp.alpha), inp.eps, runs=[run])
     torch.cuda.synchronize()
-    report, fails = check_grads(grads, col64, col32, 2e-3, sens=sens)
+    # generator gradients pass through three critics' backward passes: the fp32 oracle itself is only reproducible
+    # to ~1e-2 there (tools/parity_report.py), so the absolute bar for g_optim runs is 1e-2 instead of 2e-3
+    report, fails = check_grads(grads, col64, col32, 1e-2 if run.startswith("g_optim") else 2e-3, sens=sens)
     print(run, algo, report)
     assert not fails, fails[:5]
 
