@@ -185,3 +185,33 @@ def test_nn_functional_mirror_on_device():
     _, want = O.discriminator(vt, "D", torch.tensor(x, dtype=torch.float64))
     got = ops.to_numpy(d).astype(np.float64)
     assert np.abs(got - want.numpy()).max() < 1e-4 * max(1.0, np.abs(want.numpy()).max())
+
+
+def test_config5_shapes_128x128_multiclass_runs_and_matches():
+    """BASELINE configs[4] geometry (14-class, 128x256 pairs; patch critics see the native 128x128 so the bicubic
+    resize is the identity, generator linear -> 32768, joint critic flat 65536) at batch 2: the critic run and the
+    classifier run from the oracle's weights, plus the inference path."""
+    from parity_util import check_grads, oracle_pair, oracle_sensitivity
+    B = 2
+    ocfg, v, u, m, ops = make(B, True, "tc3x", h=128, w=256, dis=128, seed=9)
+    inp = O.make_inputs(ocfg, seed=31)
+    runs = ["d_optim_patch2", "d_optim2"]
+    (st64, col64), (st32, col32) = oracle_pair(ocfg, v, u, inp, runs=runs)
+    sens = oracle_sensitivity(ocfg, v, u, inp, col64, runs=runs, samples=1)
+    grads = {}
+    m.run_hook = lambda r, model: grads.__setitem__(r, model.export_variables("grad"))
+    m.update_model(ops.from_numpy(inp.images), ops.from_numpy(inp.z), ops.from_numpy(inp.alpha), inp.eps, runs=runs)
+    torch.cuda.synchronize()
+    for run in runs:
+        for name in list(col64[run]["grads"]):
+            if np.abs(col64[run]["grads"][name]).max() < 1e-9:
+                for c in (col64, col32):
+                    c[run]["grads"].pop(name)
+    report, fails = check_grads(grads, col64, col32, 2e-3, sens=sens)
+    print(report)
+    assert not fails, fails[:5]
+    st = O.OracleState(ocfg, v, u)
+    e_ref, i_ref = O.test_forward(st, inp.images[:1], classes=[5], eps=0.3)
+    cls = ops.from_numpy(np.array([5.0], np.float32))
+    e, i = m.test_forward(ops.from_numpy(inp.images[:1]), classes=cls, eps=0.3)
+    assert np.abs(ops.to_numpy(e) - e_ref).max() <= 1e-4 and np.abs(ops.to_numpy(i) - i_ref).max() <= 1e-4
