@@ -173,6 +173,9 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32
           "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
         : "memory");
 }
+__device__ __forceinline__ void red_add_v4(float* p, const float4 v) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
@@ -232,6 +235,7 @@ struct TcParams {
     int b_lo_tap_off;     // 3x: tap offset of the filter's lo copy inside the filter map
     int dbg;              // timing experiments only: bit0 skip the B_lo load, bit1 skip the conditioning pass
     int ksplit;           // CTAs sharing one output tile, each taking a slice of the (tap, k-chunk) loop (red.add epilogue)
+    int grid_x, grid_y;   // work items: grid_x pixel tiles x grid_y channel tiles x (nphases * ksplit)
     const float* bias;
     float* out;
 };
@@ -239,232 +243,279 @@ struct TcParams {
 // ---------------------------------------------------------------------------------------------------
 // forward / input-gradient kernel (both operands K-major)
 // ---------------------------------------------------------------------------------------------------
-// kChunked (3xTF32 mode): the tensor core accumulates with truncation (measured: tools/tc_probe.py, the error of a
-// length-K chain grows ~K * 2^-24 with a sign bias), so the accumulation is cut into chunks of kChunkStages smem
-// stages that ping-pong between two TMEM accumulators; warps 2-5 drain each finished chunk into fp32 registers
-// with round-to-nearest adds while the next chunk is being multiplied.
+// One persistent kernel, one CTA per SM, looping over (pixel tile, channel tile, phase x k-split) work items.
+//
+//  * A operand through tensor memory (TS-mode MMA): an SS-mode 128x128x8 tf32 MMA streams 8 KB of operands per 64
+//    cycles = the whole 128 B/clk shared-memory port, so TMA fills and any smem-side conditioning starve it.  Warps
+//    2-5 read the landed A tile once (ld.shared.v4 at the swizzled positions of their accumulator row) and write it
+//    to TMEM (tcgen05.st): mode 3 writes hi = trunc(x) and lo = rna(x - hi), mode 1 writes rna(x).
+//  * chunked accumulation: the tensor core accumulates with truncation (tools/tc_probe.py: the error of a length-K
+//    chain grows ~K * 2^-24 with a sign bias), so every kChunkStages stages the MMA warp switches between two TMEM
+//    accumulators and warps 2-5 drain the finished one into fp32 registers with round-to-nearest adds, one chunk
+//    behind the MMAs.  The same lag carries across work items: the output tile of item i is stored while the tensor
+//    core is already multiplying item i+1 (no per-tile prologue / epilogue bubble).
 constexpr int kChunkStages = 4;
 
-template <int kStages, bool kChunked>
-__global__ void __launch_bounds__(kThreads, 1)
+struct WorkItem {
+    int w0, h0, n0, col0, split, it0, niter, pz;
+};
+
+__device__ __forceinline__ bool get_item(const TcParams& P, int id, WorkItem& t) {
+    const int x = id % P.grid_x, y = (id / P.grid_x) % P.grid_y, z = id / (P.grid_x * P.grid_y);
+    t.pz = z / P.ksplit; t.split = z % P.ksplit;
+    const TcPhase& ph = P.ph[t.pz];
+    if (x >= ph.tiles_w * ph.tiles_h * ph.tiles_n) return false;
+    const int total_iter = ph.ntaps * ph.kchunks;
+    const int per_split = (total_iter + P.ksplit - 1) / P.ksplit;
+    t.it0 = t.split * per_split;
+    t.niter = min(total_iter, t.it0 + per_split) - t.it0;
+    if (t.niter <= 0) return false;
+    int r = x;
+    const int tw = r % ph.tiles_w; r /= ph.tiles_w;
+    const int th = r % ph.tiles_h; const int tn = r / ph.tiles_h;
+    t.w0 = tw * P.bw; t.h0 = th * P.bh; t.n0 = tn * P.bn; t.col0 = y * P.BN;
+    return true;
+}
+
+// warpgroups 0 and 1 (warps 0-7): A -> TMEM, alternating stages (one group alone cannot condition a stage in the
+// time the tensor core needs to consume it); warpgroup 2 (warps 8-11): drain + store; warp 12: TMA, warp 13: MMA.
+// Roles are warpgroup-aligned so that setmaxnreg can move registers to the epilogue warps (128 accumulators each).
+constexpr int kThreadsK = 512;
+
+template <int kStages>
+__global__ void __launch_bounds__(kThreadsK, 1)
 conv_tc_kmajor(const __grid_constant__ TcMaps maps, const __grid_constant__ TcParams P) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const int BN = P.BN, mode = P.mode;
     const uint32_t a_bytes = 128 * 128, b_bytes = (uint32_t)BN * 128;
-    // stage: [A landing tile][B][B_lo (3x)].  In the 3x kernel the A operand never goes back to shared memory: warps 2-5
-    // read the landed tile once and write hi / lo straight into tensor memory (TS-mode MMA), which removes the A
-    // operand fetch -- half of the SS-mode shared-memory traffic, the measured limiter -- and the lo store.
-    const uint32_t a_lo_off = 0, b_off = a_bytes, b_lo_off = b_off + b_bytes;
+    // stage: [A landing tile][B][B_lo (3x)]
+    const uint32_t b_off = a_bytes, b_lo_off = b_off + b_bytes;
     const uint32_t stage_bytes = a_bytes + (mode == 3 ? 2 : 1) * b_bytes;
-    const uint32_t tx_bytes = a_bytes + ((mode == 3 && !(P.dbg & 1)) ? 2 : 1) * b_bytes;
+    const uint32_t tx_bytes = stage_bytes;
+    const uint32_t stg_base = smem_base + kStages * stage_bytes;   // 4 x 4 KB output staging tiles (one per epilogue warp)
 
     __shared__ __align__(8) uint64_t full_bar[kStages];      // TMA bytes landed
-    __shared__ __align__(8) uint64_t ready_bar[kStages];     // operands conditioned (4 warp arrivals)
+    __shared__ __align__(8) uint64_t ready_bar[kStages];     // A operand written to tensor memory (4 warp arrivals)
     __shared__ __align__(8) uint64_t empty_bar[kStages];     // MMAs that read the stage have completed
-    __shared__ __align__(8) uint64_t tmem_full_bar;
     __shared__ __align__(8) uint64_t acc_full_bar[2];        // chunk accumulator complete (tcgen05.commit)
     __shared__ __align__(8) uint64_t acc_empty_bar[2];       // chunk accumulator drained (4 warp arrivals)
     __shared__ uint32_t tmem_base_slot;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const TcPhase& ph = P.ph[blockIdx.z / P.ksplit];
-    const int split = blockIdx.z % P.ksplit;
-    int t = blockIdx.x;
-    if (t >= ph.tiles_w * ph.tiles_h * ph.tiles_n) return;      // uniform per block (phases may differ in size)
-    const int tw = t % ph.tiles_w; t /= ph.tiles_w;
-    const int th = t % ph.tiles_h; const int tn = t / ph.tiles_h;
-    const int w0 = tw * P.bw, h0 = th * P.bh, n0 = tn * P.bn;
-    const int col0 = blockIdx.y * BN;
-    const int total_iter = ph.ntaps * ph.kchunks;
-    const int per_split = (total_iter + P.ksplit - 1) / P.ksplit;
-    const int it0 = split * per_split;
-    const int niter = min(total_iter, it0 + per_split) - it0;
-    if (niter <= 0) return;
-    // TMEM columns: [0, acc_cols) accumulators (two in the chunked kernel), then kStages x (32 hi + 32 lo) A columns
-    const int acc_cols = kChunked ? 2 * BN : BN;
-    const uint32_t a_col0 = (uint32_t)acc_cols;
-    const int need_cols = kChunked ? acc_cols + kStages * 64 : acc_cols;
-    const uint32_t tmem_cols = need_cols <= 32 ? 32 : (need_cols <= 64 ? 64 : (need_cols <= 128 ? 128 : (need_cols <= 256 ? 256 : 512)));
+    // TMEM columns: [0, 2*BN) two chunk accumulators, then kStages x (32 hi + 32 lo) A columns
+    const uint32_t a_col0 = (uint32_t)(2 * BN);
+    const int need_cols = 2 * BN + kStages * 64;
+    const uint32_t tmem_cols = need_cols <= 128 ? 128 : (need_cols <= 256 ? 256 : 512);
+    const int total_ids = P.grid_x * P.grid_y * P.nphases * P.ksplit;
 
-    if (warp == 0 && lane == 0) {
+    if (warp == 12 && lane == 0) {
         for (int i = 0; i < 4; ++i) prefetch_tmap(&maps.a[i]);
         prefetch_tmap(&maps.b[0]);
         for (int s = 0; s < kStages; ++s) {
             mbar_init(smem_u32(&full_bar[s]), 1); mbar_init(smem_u32(&ready_bar[s]), 4); mbar_init(smem_u32(&empty_bar[s]), 1);
         }
-        mbar_init(smem_u32(&tmem_full_bar), 1);
         for (int b = 0; b < 2; ++b) { mbar_init(smem_u32(&acc_full_bar[b]), 1); mbar_init(smem_u32(&acc_empty_bar[b]), 4); }
         fence_barrier_init();
     }
-    if (warp == 1) { tmem_alloc(smem_u32(&tmem_base_slot), tmem_cols); tmem_relinquish(); }
+    if (warp == 13) { tmem_alloc(smem_u32(&tmem_base_slot), tmem_cols); tmem_relinquish(); }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_slot;
 
-    if (warp == 0) {
+    if (warp >= 12) {
+      asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
+      if (warp == 12) {
         // ===== TMA producer =====
         if (elect_one()) {
             int stage = 0; uint32_t phase = 0;
-            for (int it = 0; it < niter; ++it) {
-                const int tap = (it0 + it) / ph.kchunks, kc = (it0 + it) - tap * ph.kchunks;
-                const TcTap tp = ph.taps[tap];
-                mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
-                const uint32_t sa = smem_base + stage * stage_bytes;
-                const uint32_t fb = smem_u32(&full_bar[stage]);
-                mbar_expect_tx(fb, tx_bytes);
-                tma_load_4d(sa, &maps.a[tp.amap], fb, kc * 32, w0 + tp.ax, h0 + tp.ay, n0);
-                tma_load_3d(sa + b_off, &maps.b[0], fb, kc * 32, col0, tp.bsel);
-                if (mode == 3 && !(P.dbg & 1)) tma_load_3d(sa + b_lo_off, &maps.b[0], fb, kc * 32, col0, tp.bsel + P.b_lo_tap_off);
-                if (++stage == kStages) { stage = 0; phase ^= 1; }
+            WorkItem t;
+            if (P.dbg & 8) __nanosleep((blockIdx.x & 15) * 500);
+            for (int id = blockIdx.x; id < total_ids; id += gridDim.x) {
+                if (!get_item(P, id, t)) continue;
+                const TcPhase& ph = P.ph[t.pz];
+                for (int it = 0; it < t.niter; ++it) {
+                    const int tap = (t.it0 + it) / ph.kchunks, kc = (t.it0 + it) - tap * ph.kchunks;
+                    const TcTap tp = ph.taps[tap];
+                    mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+                    const uint32_t sa = smem_base + stage * stage_bytes;
+                    const uint32_t fb = smem_u32(&full_bar[stage]);
+                    mbar_expect_tx(fb, tx_bytes);
+                    tma_load_4d(sa, &maps.a[tp.amap], fb, kc * 32, t.w0 + tp.ax, t.h0 + tp.ay, t.n0);
+                    tma_load_3d(sa + b_off, &maps.b[0], fb, kc * 32, t.col0, tp.bsel);
+                    if (mode == 3) tma_load_3d(sa + b_lo_off, &maps.b[0], fb, kc * 32, t.col0, tp.bsel + P.b_lo_tap_off);
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                }
             }
         }
-    } else if (warp == 1) {
+      } else if (warp == 13) {
         // ===== MMA issuer =====
         if (elect_one()) {
             const uint32_t idesc = make_idesc(128, BN, 0, 0);
             int stage = 0; uint32_t phase = 0;
-            for (int it = 0; it < niter; ++it) {
-                uint32_t dst = tmem_base;
-                bool first = (it == 0);
-                if (kChunked) {
-                    const int c = it / kChunkStages, buf = c & 1;
-                    first = (it % kChunkStages == 0);
-                    dst = tmem_base + (uint32_t)(buf * BN);
-                    if (first && c >= 2) { mbar_wait(smem_u32(&acc_empty_bar[buf]), (uint32_t)(((c >> 1) - 1) & 1)); tc_fence_after(); }
-                }
-                mbar_wait(smem_u32(&ready_bar[stage]), phase);
-                tc_fence_after();
-                const uint32_t sa = smem_base + stage * stage_bytes;
-                const uint64_t bd = make_smem_desc(sa + b_off, 16, 1024);
-                if (!kChunked) {
-                    const uint64_t ad = make_smem_desc(sa, 16, 1024);
-#pragma unroll
-                    for (int k = 0; k < 4; ++k)   // 4 x (K = 8 tf32 = 32 B) inside the 128-byte swizzle span
-                        umma_tf32(dst, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, !(first && k == 0));
-                } else {
-                    const uint64_t bld = make_smem_desc(sa + b_lo_off, 16, 1024);
+            int cg = 0;                                          // chunks issued so far (over all work items)
+            WorkItem t;
+            for (int id = blockIdx.x; id < total_ids; id += gridDim.x) {
+                if (!get_item(P, id, t)) continue;
+                for (int it = 0; it < t.niter; ++it) {
+                    const bool first = (it % kChunkStages == 0);
+                    const int buf = cg & 1;
+                    if (first && cg >= 2) { mbar_wait(smem_u32(&acc_empty_bar[buf]), (uint32_t)(((cg >> 1) - 1) & 1)); tc_fence_after(); }
+                    const uint32_t dst = tmem_base + (uint32_t)(buf * BN);
+                    mbar_wait(smem_u32(&ready_bar[stage]), phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_base + stage * stage_bytes;
+                    const uint64_t bd = make_smem_desc(sa + b_off, 16, 1024);
                     const uint32_t a_hi = tmem_base + a_col0 + (uint32_t)(stage * 64), a_lo = a_hi + 32;
+                    if (mode == 3) {
+                        const uint64_t bld = make_smem_desc(sa + b_lo_off, 16, 1024);
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        umma_tf32_ts(dst, a_hi + k * 8, bd + (uint64_t)(k * 2), idesc, !(first && k == 0));
-                        umma_tf32_ts(dst, a_lo + k * 8, bd + (uint64_t)(k * 2), idesc, 1);
-                        umma_tf32_ts(dst, a_hi + k * 8, bld + (uint64_t)(k * 2), idesc, 1);
+                        for (int k = 0; k < 4; ++k) {            // 4 x (K = 8 tf32 = 32 B) inside the 128-byte swizzle span
+                            umma_tf32_ts(dst, a_hi + k * 8, bd + (uint64_t)(k * 2), idesc, !(first && k == 0));
+                            umma_tf32_ts(dst, a_lo + k * 8, bd + (uint64_t)(k * 2), idesc, 1);
+                            umma_tf32_ts(dst, a_hi + k * 8, bld + (uint64_t)(k * 2), idesc, 1);
+                        }
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            umma_tf32_ts(dst, a_hi + k * 8, bd + (uint64_t)(k * 2), idesc, !(first && k == 0));
                     }
+                    umma_commit(smem_u32(&empty_bar[stage]));
+                    if (it % kChunkStages == kChunkStages - 1 || it == t.niter - 1) {
+                        umma_commit(smem_u32(&acc_full_bar[buf]));
+                        ++cg;
+                    }
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
-                umma_commit(smem_u32(&empty_bar[stage]));
-                if (kChunked && (it % kChunkStages == kChunkStages - 1 || it == niter - 1))
-                    umma_commit(smem_u32(&acc_full_bar[(it / kChunkStages) & 1]));
-                if (++stage == kStages) { stage = 0; phase ^= 1; }
             }
-            if (!kChunked) umma_commit(smem_u32(&tmem_full_bar));
         }
-    } else {
-        // ===== warps 2..5: operand conditioning during the main loop (+ chunk draining), then the epilogue =====
-        const int ctid = threadIdx.x - 64;
+      }
+    } else if (warp < 8) {
+        // ===== warps 0..7: A operand -> tensor memory (warps 0-3 take the even stages, warps 4-7 the odd ones) =====
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 104;");
+        static_assert(kStages % 2 == 0, "stage parity selects the conditioning warpgroup");
         const int q = warp & 3;                                  // TMEM lane quarter this warp may access
-        float acc[kChunked ? 128 : 1];
-        if (kChunked) {
-#pragma unroll
-            for (int j = 0; j < (kChunked ? 128 : 1); ++j) acc[j] = 0.f;
-        }
-        auto drain = [&](int c) {                                // add chunk c's TMEM accumulator into registers
-            const int buf = c & 1;
-            mbar_wait(smem_u32(&acc_full_bar[buf]), (uint32_t)((c >> 1) & 1));
-            tc_fence_after();
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-                if (g * 32 < BN) {
-                    uint32_t r[32];
-                    tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + g * 32), r);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) acc[kChunked ? g * 32 + j : 0] += __uint_as_float(r[j]);
-                }
-            }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(smem_u32(&acc_empty_bar[buf]));
-        };
-        {
-            int stage = 0; uint32_t phase = 0;
+        const int grp = warp >> 2;
+        const int arow = q * 32 + lane;                          // A tile row of this thread = TMEM lane
+        int stage = 0; uint32_t phase = 0;
+        WorkItem t;
+        for (int id = blockIdx.x; id < total_ids; id += gridDim.x) {
+            if (!get_item(P, id, t)) continue;
+            const int niter = t.niter;
             for (int it = 0; it < niter; ++it) {
+                if ((stage & 1) != grp) { if (++stage == kStages) { stage = 0; phase ^= 1; } continue; }
                 mbar_wait(smem_u32(&full_bar[stage]), phase);
                 const uint32_t sa = smem_base + stage * stage_bytes;
-                if (!kChunked) {
-                    if (!(P.dbg & 2)) condition_tile(sa, sa + a_lo_off, a_bytes, ctid, mode);   // the filter was prepared in global
-                    fence_proxy_async();
-                } else {
-                    // this thread's accumulator row = TMEM lane = row of the A tile: 8 x 16 B at the swizzled positions
-                    const int arow = (warp & 3) * 32 + lane;
-                    uint32_t hi[32], lo[32];
+                const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + a_col0 + (uint32_t)(stage * 64);
+                uint32_t hi[32];
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const uint4 v = lds128(sa + (uint32_t)arow * 128u + (uint32_t)((j ^ (arow & 7)) << 4));
-                        hi[4 * j] = v.x; hi[4 * j + 1] = v.y; hi[4 * j + 2] = v.z; hi[4 * j + 3] = v.w;
-                    }
+                for (int j = 0; j < 8; ++j) {                    // 8 x 16 B at the swizzled positions of row arow
+                    const uint4 v = lds128(sa + (uint32_t)arow * 128u + (uint32_t)((j ^ (arow & 7)) << 4));
+                    hi[4 * j] = v.x; hi[4 * j + 1] = v.y; hi[4 * j + 2] = v.z; hi[4 * j + 3] = v.w;
+                }
+                if (P.dbg & 2) {
+                    // timing experiment: operands left unwritten
+                } else if (mode == 3) {
+                    uint32_t lo[32];
 #pragma unroll
                     for (int j = 0; j < 32; ++j) { lo[j] = tf32_lo(hi[j]); hi[j] &= 0xFFFFE000u; }
-                    const uint32_t ta = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + a_col0 + (uint32_t)(stage * 64);
                     tmem_st32(ta, hi);
                     tmem_st32(ta + 32, lo);
-                    tmem_st_wait();
-                    tc_fence_before();
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) hi[j] = tf32_rna(hi[j]);
+                    tmem_st32(ta, hi);
                 }
+                tmem_st_wait();
+                tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(smem_u32(&ready_bar[stage]));
                 if (++stage == kStages) { stage = 0; phase ^= 1; }
-                if (kChunked && (it % kChunkStages == kChunkStages - 1 || it == niter - 1)) {
-                    const int c = it / kChunkStages;
-                    if (c >= 1) drain(c - 1);                    // lag by one chunk: never wait on MMAs still in flight
-                }
             }
-            if (kChunked) drain((niter - 1) / kChunkStages);
         }
-        const int row = q * 32 + lane;
-        const int wl = row % P.bw, hl = (row / P.bw) % P.bh, nl = row / (P.bw * P.bh);
-        const int ow = w0 + wl, oh = h0 + hl, on = n0 + nl;
-        const bool valid = ow < ph.ext_w && oh < ph.ext_h && on < ph.ext_n;
-        float* orow = P.out + ph.out_off + (long long)on * ph.sn + (long long)oh * ph.sh + (long long)ow * ph.sw + col0;
-        if (!kChunked) {
-            mbar_wait(smem_u32(&tmem_full_bar), 0);
-            tc_fence_after();
-        }
+    } else {
+        // ===== warps 8..11: drain the chunk accumulators into fp32 registers, store the finished tiles =====
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+        const int q = warp & 3;                                  // this thread's accumulator row = TMEM lane q * 32 + lane
+        float acc[128];
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-            const int c = g * 32;
-            if (c < BN) {
-                uint32_t r[32];
-                if (!kChunked) {
-                    tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, r);
-                    tmem_ld_wait();
-                } else {
+        for (int j = 0; j < 128; ++j) acc[j] = 0.f;
+        int cg = 0;                                              // chunks drained so far (over all work items)
+        WorkItem t;
+        for (int id = blockIdx.x; id < total_ids; id += gridDim.x) {
+            if (!get_item(P, id, t)) continue;
+            const int nchunks = (t.niter + kChunkStages - 1) / kChunkStages;
+#pragma unroll 1
+            for (int c = 0; c < nchunks; ++c, ++cg) {
+                const int buf = cg & 1;
+                mbar_wait(smem_u32(&acc_full_bar[buf]), (uint32_t)((cg >> 1) & 1));
+                tc_fence_after();
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(acc[kChunked ? g * 32 + j : 0]);
+                for (int g = 0; g < 4; ++g) {
+                    if (g * 32 < BN) {
+                        uint32_t r[32];
+                        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + g * 32), r);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) acc[g * 32 + j] += __uint_as_float(r[j]);
+                    }
                 }
-                if (valid) {
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(&acc_empty_bar[buf]));
+            }
+            // Store through a per-warp staging tile (32 rows x 32 columns, 16-byte chunks XOR-swizzled by row): a thread
+            // owns one accumulator row, so direct stores would touch 32 different 128-byte lines per instruction; after
+            // the transpose each instruction writes 4 rows x 128 contiguous bytes.
+            const TcPhase& ph = P.ph[t.pz];
+            const int sub = lane >> 3, cj = lane & 7;            // row within a group of 4, 16-byte chunk within the row
+            long long roff[8];
+            uint32_t vmask = 0;
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
-                        if (P.bias != nullptr && split == 0) {
-                            const float4 bb = __ldg(reinterpret_cast<const float4*>(P.bias + col0 + c + j));
-                            v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
-                        }
-                        if (P.ksplit > 1) {
-                            atomicAdd(orow + c + j, v.x); atomicAdd(orow + c + j + 1, v.y);
-                            atomicAdd(orow + c + j + 2, v.z); atomicAdd(orow + c + j + 3, v.w);
-                        } else {
-                            *reinterpret_cast<float4*>(orow + c + j) = v;
+            for (int i = 0; i < 8; ++i) {
+                const int r = q * 32 + i * 4 + sub;
+                const int ow = t.w0 + r % P.bw, oh = t.h0 + (r / P.bw) % P.bh, on = t.n0 + r / (P.bw * P.bh);
+                if (ow < ph.ext_w && oh < ph.ext_h && on < ph.ext_n) vmask |= 1u << i;
+                roff[i] = ph.out_off + (long long)on * ph.sn + (long long)oh * ph.sh + (long long)ow * ph.sw + t.col0 + cj * 4;
+            }
+            if (P.dbg & 4) vmask = 0;
+            const float* brow = (P.bias != nullptr && t.split == 0) ? P.bias + t.col0 + cj * 4 : nullptr;
+            const uint32_t stg = stg_base + (uint32_t)q * 4096u;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                const int c = g * 32;
+                if (c < BN) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        sts128(stg + (uint32_t)lane * 128u + (uint32_t)((j ^ (lane & 7)) << 4),
+                               make_uint4(__float_as_uint(acc[c + 4 * j]), __float_as_uint(acc[c + 4 * j + 1]),
+                                          __float_as_uint(acc[c + 4 * j + 2]), __float_as_uint(acc[c + 4 * j + 3])));
+                        acc[c + 4 * j] = 0.f; acc[c + 4 * j + 1] = 0.f; acc[c + 4 * j + 2] = 0.f; acc[c + 4 * j + 3] = 0.f;
+                    }
+                    __syncwarp();
+                    float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (brow != nullptr) bb = __ldg(reinterpret_cast<const float4*>(brow + c));
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int rr = i * 4 + sub;
+                        const uint4 u = lds128(stg + (uint32_t)rr * 128u + (uint32_t)((cj ^ (rr & 7)) << 4));
+                        if (vmask & (1u << i)) {
+                            float* dst = P.out + roff[i] + c;
+                            const float4 v = make_float4(__uint_as_float(u.x) + bb.x, __uint_as_float(u.y) + bb.y,
+                                                         __uint_as_float(u.z) + bb.z, __uint_as_float(u.w) + bb.w);
+                            if (P.ksplit > 1) red_add_v4(dst, v);
+                            else *reinterpret_cast<float4*>(dst) = v;
                         }
                     }
+                    __syncwarp();
                 }
             }
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, tmem_cols); }
+    if (warp == 13) { tc_fence_after(); tmem_dealloc(tmem_base, tmem_cols); }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -746,7 +797,7 @@ int get_scratch(cudaStream_t st, size_t bytes, float** out) {
     return 0;
 }
 
-constexpr int kStagesK = 3;      // SS-mode (TF32) kernel
+int g_sms = 148;
 constexpr int kStagesK3 = 4;     // TS-mode (3xTF32) kernel: 4 x (16 KB A landing + 2 x BN*128 B filter hi/lo)
 constexpr int kStagesW = 3;
 constexpr int kStagesW3 = 4;     // TS-mode wgrad: 4 x (16 KB rows + 2 x BN/32*4 KB columns hi/lo)
@@ -754,10 +805,12 @@ constexpr int kStagesW3 = 4;     // TS-mode wgrad: 4 x (16 KB rows + 2 x BN/32*4
 bool g_attr_set = false;
 int set_attrs() {
     if (g_attr_set) return 0;
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_kmajor<kStagesK, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kmajor<kStagesK3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024);
     if (e != cudaSuccess) return eg_fail(e, __FILE__, __LINE__);
-    e = cudaFuncSetAttribute(conv_tc_kmajor<kStagesK3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    if (e != cudaSuccess) return eg_fail(e, __FILE__, __LINE__);
+    {
+        int dev = 0, n = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) g_sms = n;
+    }
     e = cudaFuncSetAttribute(conv_tc_wgrad<kStagesW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return eg_fail(e, __FILE__, __LINE__);
     e = cudaFuncSetAttribute(conv_tc_wgrad<kStagesW3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
@@ -851,7 +904,14 @@ static int pick_ksplit(int ctas, int min_iters) {
 }
 
 static size_t kmajor_smem(int BN, int mode) {
-    return mode == 3 ? (size_t)kStagesK3 * (128 * 128 + 2 * BN * 128) + 1024 : (size_t)kStagesK * (128 * 128 + BN * 128) + 1024;
+    return (size_t)kStagesK3 * (128 * 128 + (mode == 3 ? 2 : 1) * BN * 128) + 4 * 4096 + 1024;
+}
+static int launch_kmajor(const TcMaps& maps, TcParams& P, int gx, int gy, int mode, cudaStream_t st) {
+    P.grid_x = gx; P.grid_y = gy;
+    const int total = gx * gy * P.nphases * P.ksplit;
+    const int ctas = (total < g_sms || (P.dbg & 32)) ? total : g_sms;              // persistent: at most one CTA per SM
+    conv_tc_kmajor<kStagesK3><<<ctas, kThreadsK, kmajor_smem(P.BN, mode), st>>>(maps, P);
+    return 0;
 }
 
 int eg_tc_conv2d_fwd(const eg_conv_shape* s, const float* x, const float* w, const float* bias, float* y, int three_x,
@@ -883,9 +943,7 @@ int eg_tc_conv2d_fwd(const eg_conv_shape* s, const float* x, const float* w, con
         cudaError_t e = cudaMemsetAsync(y, 0, sizeof(float) * (size_t)s->N * s->OH * s->OW * s->Co, st);
         if (e != cudaSuccess) return eg_fail(e, __FILE__, __LINE__);
     }
-    dim3 grid(ph.tiles_w * ph.tiles_h * ph.tiles_n, s->Co / P.BN, P.ksplit);
-    if (mode == 3) conv_tc_kmajor<kStagesK3, true><<<grid, kThreads, kmajor_smem(P.BN, mode), st>>>(maps, P);
-    else           conv_tc_kmajor<kStagesK, false><<<grid, kThreads, kmajor_smem(P.BN, mode), st>>>(maps, P);
+    launch_kmajor(maps, P, ph.tiles_w * ph.tiles_h * ph.tiles_n, s->Co / P.BN, mode, st);
     EG_CHECK_LAUNCH();
     return 0;
 }
@@ -941,9 +999,7 @@ int eg_tc_conv2d_bwd_data(const eg_conv_shape* s, const float* dy, const float* 
         cudaError_t e = cudaMemsetAsync(dx, 0, sizeof(float) * (size_t)s->N * s->H * s->W * s->Ci, st);
         if (e != cudaSuccess) return eg_fail(e, __FILE__, __LINE__);
     }
-    dim3 grid(max_tiles, s->Ci / P.BN, S * S * P.ksplit);
-    if (mode == 3) conv_tc_kmajor<kStagesK3, true><<<grid, kThreads, kmajor_smem(P.BN, mode), st>>>(maps, P);
-    else           conv_tc_kmajor<kStagesK, false><<<grid, kThreads, kmajor_smem(P.BN, mode), st>>>(maps, P);
+    launch_kmajor(maps, P, max_tiles, s->Ci / P.BN, mode, st);
     EG_CHECK_LAUNCH();
     return 0;
 }
