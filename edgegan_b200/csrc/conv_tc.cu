@@ -217,12 +217,18 @@ struct __align__(64) TcMaps {
 
 struct TcTap { signed char amap, ax, ay, bsel; };   // bsel: filter tap index (K-major kernels) / b map (wgrad)
 
+// division by a runtime constant: q = umulhi(n, m), exact while n * d < 2^32 (checked on the host; m == 0 -> plain /)
+struct FastDiv { uint32_t d, m; };
+__device__ __forceinline__ uint32_t fd_div(uint32_t n, const FastDiv f) { return f.m ? __umulhi(n, f.m) : n / f.d; }
+
 struct TcPhase {          // one GEMM problem (a dgrad parity phase, or the whole forward)
     int ntaps, kchunks;   // k iterations = ntaps * kchunks (32 channels each)
     TcTap taps[kMaxTaps];
     int ext_w, ext_h, ext_n;          // extents of the pixel grid this phase covers
     int tiles_w, tiles_h, tiles_n;
+    FastDiv ftw, fth;                 // tiles_w, tiles_h
     long long out_off, sn, sh, sw;    // output element offset of pixel (n,h,w) = out_off + n*sn + h*sh + w*sw
+                                      // (sn, sh, sw are the same in every phase; only out_off differs)
 };
 
 struct TcParams {
@@ -236,6 +242,7 @@ struct TcParams {
     int dbg;              // timing experiments only: bit0 skip the B_lo load, bit1 skip the conditioning pass
     int ksplit;           // CTAs sharing one output tile, each taking a slice of the (tap, k-chunk) loop (red.add epilogue)
     int grid_x, grid_y;   // work items: grid_x pixel tiles x grid_y channel tiles x (nphases * ksplit)
+    FastDiv fgx, fgy, fks;
     const float* bias;
     float* out;
 };
@@ -261,18 +268,19 @@ struct WorkItem {
 };
 
 __device__ __forceinline__ bool get_item(const TcParams& P, int id, WorkItem& t) {
-    const int x = id % P.grid_x, y = (id / P.grid_x) % P.grid_y, z = id / (P.grid_x * P.grid_y);
-    t.pz = z / P.ksplit; t.split = z % P.ksplit;
+    const int yz = (int)fd_div((uint32_t)id, P.fgx), x = id - yz * P.grid_x;
+    const int z = (int)fd_div((uint32_t)yz, P.fgy), y = yz - z * P.grid_y;
+    t.pz = (int)fd_div((uint32_t)z, P.fks); t.split = z - t.pz * P.ksplit;
     const TcPhase& ph = P.ph[t.pz];
     if (x >= ph.tiles_w * ph.tiles_h * ph.tiles_n) return false;
     const int total_iter = ph.ntaps * ph.kchunks;
-    const int per_split = (total_iter + P.ksplit - 1) / P.ksplit;
+    int per_split = total_iter;
+    if (P.ksplit > 1) per_split = (total_iter + P.ksplit - 1) / P.ksplit;
     t.it0 = t.split * per_split;
     t.niter = min(total_iter, t.it0 + per_split) - t.it0;
     if (t.niter <= 0) return false;
-    int r = x;
-    const int tw = r % ph.tiles_w; r /= ph.tiles_w;
-    const int th = r % ph.tiles_h; const int tn = r / ph.tiles_h;
+    const int r = (int)fd_div((uint32_t)x, ph.ftw), tw = x - r * ph.tiles_w;
+    const int tn = (int)fd_div((uint32_t)r, ph.fth), th = r - tn * ph.tiles_h;
     t.w0 = tw * P.bw; t.h0 = th * P.bh; t.n0 = tn * P.bn; t.col0 = y * P.BN;
     return true;
 }
@@ -441,6 +449,18 @@ conv_tc_kmajor(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
         float acc[128];
 #pragma unroll
         for (int j = 0; j < 128; ++j) acc[j] = 0.f;
+        // the 8 tile rows this lane stores (pass i: row q*32 + i*4 + lane/8): local pixel coordinates and output offset
+        const int sub = lane >> 3, cj = lane & 7;                // row within a group of 4, 16-byte chunk within the row
+        uint32_t loc[8];
+        long long loff[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int r = q * 32 + i * 4 + sub;
+            const int wl = r % P.bw, hl = (r / P.bw) % P.bh, nl = r / (P.bw * P.bh);
+            loc[i] = (uint32_t)wl | ((uint32_t)hl << 8) | ((uint32_t)nl << 16);
+            loff[i] = (long long)nl * P.ph[0].sn + (long long)hl * P.ph[0].sh + (long long)wl * P.ph[0].sw + cj * 4;
+        }
+        const uint32_t stg = stg_base + (uint32_t)q * 4096u;
         int cg = 0;                                              // chunks drained so far (over all work items)
         WorkItem t;
         for (int id = blockIdx.x; id < total_ids; id += gridDim.x) {
@@ -469,19 +489,18 @@ conv_tc_kmajor(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
             // owns one accumulator row, so direct stores would touch 32 different 128-byte lines per instruction; after
             // the transpose each instruction writes 4 rows x 128 contiguous bytes.
             const TcPhase& ph = P.ph[t.pz];
-            const int sub = lane >> 3, cj = lane & 7;            // row within a group of 4, 16-byte chunk within the row
-            long long roff[8];
-            uint32_t vmask = 0;
+            uint32_t vmask = 0xffu;
+            if (t.w0 + P.bw > ph.ext_w || t.h0 + P.bh > ph.ext_h || t.n0 + P.bn > ph.ext_n) {   // ragged tile
+                vmask = 0;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int r = q * 32 + i * 4 + sub;
-                const int ow = t.w0 + r % P.bw, oh = t.h0 + (r / P.bw) % P.bh, on = t.n0 + r / (P.bw * P.bh);
-                if (ow < ph.ext_w && oh < ph.ext_h && on < ph.ext_n) vmask |= 1u << i;
-                roff[i] = ph.out_off + (long long)on * ph.sn + (long long)oh * ph.sh + (long long)ow * ph.sw + t.col0 + cj * 4;
+                for (int i = 0; i < 8; ++i) {
+                    const int ow = t.w0 + (int)(loc[i] & 255u), oh = t.h0 + (int)((loc[i] >> 8) & 255u), on = t.n0 + (int)(loc[i] >> 16);
+                    if (ow < ph.ext_w && oh < ph.ext_h && on < ph.ext_n) vmask |= 1u << i;
+                }
             }
             if (P.dbg & 4) vmask = 0;
+            float* obase = P.out + ph.out_off + (long long)t.n0 * ph.sn + (long long)t.h0 * ph.sh + (long long)t.w0 * ph.sw + t.col0;
             const float* brow = (P.bias != nullptr && t.split == 0) ? P.bias + t.col0 + cj * 4 : nullptr;
-            const uint32_t stg = stg_base + (uint32_t)q * 4096u;
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
                 const int c = g * 32;
@@ -501,7 +520,7 @@ conv_tc_kmajor(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
                         const int rr = i * 4 + sub;
                         const uint4 u = lds128(stg + (uint32_t)rr * 128u + (uint32_t)((cj ^ (rr & 7)) << 4));
                         if (vmask & (1u << i)) {
-                            float* dst = P.out + roff[i] + c;
+                            float* dst = obase + loff[i] + c;
                             const float4 v = make_float4(__uint_as_float(u.x) + bb.x, __uint_as_float(u.y) + bb.y,
                                                          __uint_as_float(u.z) + bb.z, __uint_as_float(u.w) + bb.w);
                             if (P.ksplit > 1) red_add_v4(dst, v);
@@ -540,8 +559,13 @@ struct WgParams {
 // owns channel row r of the 128-row tile: for each of the 32 pixels of a stage it reads its channel from the
 // MN-major slab (one 128-B line per pixel, 32-B-atom swizzle -> conflict-free across the warp) and stores hi / lo as
 // 32 TMEM columns; the column operand stays in shared memory and gets its lo copy written next to it.
+// In the kTS kernel the per-stage work of the helper warps is split: warps 2-5 move the row operand to tensor memory,
+// warps 6-9 write the lo copy of the column operand (a single warp per scheduler issues ~one dependent instruction
+// every 5 cycles).  A second row-operand warpgroup on alternate stages was measured and did not help.
+constexpr int kThreadsW3 = 320;
+
 template <int kStages, bool kTS>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kTS ? kThreadsW3 : kThreads, 1)
 conv_tc_wgrad(const __grid_constant__ TcMaps maps, const __grid_constant__ WgParams P) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -576,7 +600,7 @@ conv_tc_wgrad(const __grid_constant__ TcMaps maps, const __grid_constant__ WgPar
         for (int i = 0; i < 4; ++i) { prefetch_tmap(&maps.a[i]); }
         prefetch_tmap(&maps.b[0]);
         for (int s = 0; s < kStages; ++s) {
-            mbar_init(smem_u32(&full_bar[s]), 1); mbar_init(smem_u32(&ready_bar[s]), 4); mbar_init(smem_u32(&empty_bar[s]), 1);
+            mbar_init(smem_u32(&full_bar[s]), 1); mbar_init(smem_u32(&ready_bar[s]), kTS ? 8 : 4); mbar_init(smem_u32(&empty_bar[s]), 1);
         }
         mbar_init(smem_u32(&tmem_full_bar), 1);
         fence_barrier_init();
@@ -646,6 +670,19 @@ conv_tc_wgrad(const __grid_constant__ TcMaps maps, const __grid_constant__ WgPar
             }
             umma_commit(smem_u32(&tmem_full_bar));
         }
+    } else if (kTS && warp >= 6) {
+        // column operand: lo copy next to it in shared memory
+        const int ctid = threadIdx.x - 192;
+        int stage = 0; uint32_t phase = 0;
+        for (int it = 0; it < niter; ++it) {
+            mbar_wait(smem_u32(&full_bar[stage]), phase);
+            const uint32_t sa = smem_base + stage * stage_bytes;
+            condition_tile(sa + a_bytes, sa + b_lo_off, b_bytes, ctid, 3);
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&ready_bar[stage]));
+            if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
     } else {
         const int ctid = threadIdx.x - 64;
         const int q = warp & 3;
@@ -666,9 +703,6 @@ conv_tc_wgrad(const __grid_constant__ TcMaps maps, const __grid_constant__ WgPar
                     const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + a_col0 + (uint32_t)(stage * 64);
                     tmem_st32(ta, hi);
                     tmem_st32(ta + 32, lo);
-                    // column operand: lo copy next to it in shared memory
-                    condition_tile(sa + a_bytes, sa + b_lo_off, b_bytes, ctid, 3);
-                    fence_proxy_async();
                     tmem_st_wait();
                     tc_fence_before();
                 } else {
@@ -777,18 +811,19 @@ void pick_box(int W, int H, int pix, int& bw, int& bh, int& bn) {
     bw = gcd(W, pix); bh = gcd(H, pix / bw); bn = pix / (bw * bh);
 }
 
-// per-stream scratch for the prepared filter copies (the only memory the library owns; grown at first use,
-// i.e. during warm-up, never inside a captured region)
+// per-stream scratch (the only memory the library owns; grown at first use, i.e. during warm-up, never inside a
+// captured region).  slot 0: prepared filter copies; slots 1, 2: patch matrix / small operands of conv_thin.cu
 struct Scratch { float* p = nullptr; size_t bytes = 0; };
 std::mutex g_mu;
-std::map<cudaStream_t, Scratch> g_scratch;
+std::map<std::pair<cudaStream_t, int>, Scratch> g_scratch;
 
-int get_scratch(cudaStream_t st, size_t bytes, float** out) {
+int get_scratch(cudaStream_t st, size_t bytes, float** out, int slot = 0) {
     std::lock_guard<std::mutex> lk(g_mu);
-    Scratch& s = g_scratch[st];
+    Scratch& s = g_scratch[std::make_pair(st, slot)];
     if (s.bytes < bytes) {
         if (s.p) { cudaStreamSynchronize(st); cudaFree(s.p); s.p = nullptr; s.bytes = 0; }
-        size_t want = bytes < (32u << 20) ? (32u << 20) : bytes;
+        const size_t floor_bytes = slot == 1 ? (64u << 20) : (slot == 0 ? (32u << 20) : (1u << 20));
+        size_t want = bytes < floor_bytes ? floor_bytes : bytes;
         cudaError_t e = cudaMalloc(&s.p, want);
         if (e != cudaSuccess) return eg_fail(e, __FILE__, __LINE__);
         s.bytes = want;
@@ -822,7 +857,7 @@ int set_attrs() {
 int pick_bn(int n) { return n % 128 == 0 ? 128 : 64; }
 
 // wgrad operand layout knobs: {TMA swizzle enum, UMMA layout type, SBO bytes} (tools/tc_probe.py can sweep them)
-int g_dbg[8] = {(int)CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, 1, 512, 0, 64, 0, 0, 0};
+int g_dbg[8] = {(int)CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, 1, 512, 0, 64, 2, 0, 0};
 
 // prepared filter: returns the base of [hi copy (taps*Ci*Co)][lo copy (3x only)]
 int prep_filter(const eg_conv_shape* s, const float* w, int transpose, int mode, cudaStream_t st, float** out) {
@@ -845,14 +880,33 @@ extern "C" int eg_debug_set(int key, int value) {
     return 0;
 }
 
+int eg_tc_scratch(cudaStream_t st, int slot, size_t bytes, float** out) { return get_scratch(st, bytes, out, slot); }
+
+// conv_thin.cu
+int eg_thin_supported_fwd(const eg_conv_shape* s);
+int eg_thin_supported_bwd_data(const eg_conv_shape* s);
+int eg_thin_supported_bwd_weight(const eg_conv_shape* s);
+int eg_thin_conv2d_fwd(const eg_conv_shape* s, const float* x, const float* w, const float* bias, float* y, int three_x, cudaStream_t st);
+int eg_thin_conv2d_bwd_data(const eg_conv_shape* s, const float* dy, const float* w, const float* bias, float* dx, int three_x, cudaStream_t st);
+int eg_thin_conv2d_bwd_weight(const eg_conv_shape* s, const float* x, const float* dy, float* dw, int accumulate, int three_x, cudaStream_t st);
+
 // ---- capability queries ------------------------------------------------------------------------------
+// g_dbg[5]: which passes take the thin-channel route of conv_thin.cu (bit 0 fwd, bit 1 input grad, bit 2 filter grad).
+// Measured on B200 (tools/thin_time.py): the input gradient is 1.9x faster than the FFMA kernel, forward and filter
+// gradient are not (the patch matrix round trip costs what the dense product saves), so only bit 1 is on by default.
+static bool thin_fwd(const eg_conv_shape* s) { return (g_dbg[5] & 1) && eg_thin_supported_fwd(s); }
+static bool thin_bwd_data(const eg_conv_shape* s) { return (g_dbg[5] & 2) && eg_thin_supported_bwd_data(s); }
+static bool thin_bwd_weight(const eg_conv_shape* s) { return (g_dbg[5] & 4) && eg_thin_supported_bwd_weight(s); }
+
 int eg_tc_supported_fwd(const eg_conv_shape* s) {
+    if (thin_fwd(s)) return 1;
     if (s->Ci % 32 || s->Co % 64) return 0;
     if (s->stride != 1 && s->stride != 2) return 0;
     if (s->KH * s->KW > kMaxTaps) return 0;
     return 1;
 }
 int eg_tc_supported_bwd_data(const eg_conv_shape* s) {
+    if (thin_bwd_data(s)) return 1;
     if (s->Co % 32 || s->Ci % 64) return 0;
     if (s->stride != 1 && s->stride != 2) return 0;
     if (s->KH * s->KW > kMaxTaps) return 0;
@@ -860,8 +914,8 @@ int eg_tc_supported_bwd_data(const eg_conv_shape* s) {
     return 1;
 }
 int eg_tc_supported_bwd_weight(const eg_conv_shape* s) {
-    if (s->Ci % 32 || s->Co % 32) return 0;
-    if (s->Ci % 128 && s->Co % 128) return 0;      // one side must fill the 128 accumulator rows
+    if (thin_bwd_weight(s)) return 1;
+    if (s->Ci % 32 || s->Co % 32) return 0;        // (a row side below 128 channels is zero-filled by TMA)
     if (s->stride != 1 && s->stride != 2) return 0;
     if (s->KH * s->KW > kMaxTaps) return 0;
     return 1;
@@ -909,6 +963,13 @@ static size_t kmajor_smem(int BN, int mode) {
 static int launch_kmajor(const TcMaps& maps, TcParams& P, int gx, int gy, int mode, cudaStream_t st) {
     P.grid_x = gx; P.grid_y = gy;
     const int total = gx * gy * P.nphases * P.ksplit;
+    auto fd = [&](int d, long long nmax) {
+        FastDiv f; f.d = (uint32_t)d;
+        f.m = (d > 1 && nmax * d < (1ll << 32)) ? (uint32_t)(((1ull << 32) + (uint32_t)d - 1) / (uint32_t)d) : 0u;
+        return f;
+    };
+    P.fgx = fd(gx, total); P.fgy = fd(gy, total); P.fks = fd(P.ksplit, total);
+    for (int i = 0; i < P.nphases; ++i) { P.ph[i].ftw = fd(P.ph[i].tiles_w, gx); P.ph[i].fth = fd(P.ph[i].tiles_h, gx); }
     const int ctas = (total < g_sms || (P.dbg & 32)) ? total : g_sms;              // persistent: at most one CTA per SM
     conv_tc_kmajor<kStagesK3><<<ctas, kThreadsK, kmajor_smem(P.BN, mode), st>>>(maps, P);
     return 0;
@@ -916,6 +977,7 @@ static int launch_kmajor(const TcMaps& maps, TcParams& P, int gx, int gy, int mo
 
 int eg_tc_conv2d_fwd(const eg_conv_shape* s, const float* x, const float* w, const float* bias, float* y, int three_x,
                      cudaStream_t st) {
+    if (thin_fwd(s)) return eg_thin_conv2d_fwd(s, x, w, bias, y, three_x, st);
     if (int r = get_encode()) return r;
     if (int r = set_attrs()) return r;
     const int taps = s->KH * s->KW, mode = three_x ? 3 : 1;
@@ -950,6 +1012,7 @@ int eg_tc_conv2d_fwd(const eg_conv_shape* s, const float* x, const float* w, con
 
 int eg_tc_conv2d_bwd_data(const eg_conv_shape* s, const float* dy, const float* w, const float* bias, float* dx,
                           int three_x, cudaStream_t st) {
+    if (thin_bwd_data(s)) return eg_thin_conv2d_bwd_data(s, dy, w, bias, dx, three_x, st);
     if (int r = get_encode()) return r;
     if (int r = set_attrs()) return r;
     const int S = s->stride, taps = s->KH * s->KW, mode = three_x ? 3 : 1;
@@ -1006,6 +1069,7 @@ int eg_tc_conv2d_bwd_data(const eg_conv_shape* s, const float* dy, const float* 
 
 int eg_tc_conv2d_bwd_weight(const eg_conv_shape* s, const float* x, const float* dy, float* dw, int accumulate,
                             int three_x, cudaStream_t st) {
+    if (thin_bwd_weight(s)) return eg_thin_conv2d_bwd_weight(s, x, dy, dw, accumulate, three_x, st);
     if (int r = get_encode()) return r;
     if (int r = set_attrs()) return r;
     TcMaps maps;
@@ -1024,7 +1088,8 @@ int eg_tc_conv2d_bwd_weight(const eg_conv_shape* s, const float* x, const float*
     for (int r = 0; r < s->KH; ++r)
         for (int q = 0; q < s->KW; ++q) P.taps[r * s->KW + q] = x_tap(s, r, q, 0);
     // rows = whichever channel count fills 128 accumulator rows; prefer the wider one as rows
-    P.x_is_a = (s->Ci % 128 == 0 && (s->Co % 128 != 0 || s->Ci >= s->Co)) ? 1 : 0;
+    if (s->Ci % 128 && s->Co % 128) P.x_is_a = s->Ci >= s->Co ? 1 : 0;   // neither fills the rows: the rest is zero-filled
+    else P.x_is_a = (s->Ci % 128 == 0 && (s->Co % 128 != 0 || s->Ci >= s->Co)) ? 1 : 0;
     const int rows = P.x_is_a ? s->Ci : s->Co, cols = P.x_is_a ? s->Co : s->Ci;
     P.BN = cols % 128 == 0 ? 128 : (cols % 64 == 0 ? 64 : 32);
     P.rows_total = rows; P.cols_total = cols;
@@ -1032,7 +1097,8 @@ int eg_tc_conv2d_bwd_weight(const eg_conv_shape* s, const float* x, const float*
     P.sm = P.x_is_a ? s->Co : 1; P.sn = P.x_is_a ? 1 : s->Co;
     P.tiles_w = s->OW / P.bw; P.tiles_h = s->OH / P.bh; P.tiles_n = eg_ceil_div(s->N, P.bn);
     const int ntiles = P.tiles_w * P.tiles_h * P.tiles_n;
-    const int base_ctas = (rows / 128) * (cols / P.BN) * P.ntaps;
+    const int row_tiles = eg_ceil_div(rows, 128);
+    const int base_ctas = row_tiles * (cols / P.BN) * P.ntaps;
     int splits = eg_ceil_div(2 * 148, base_ctas);
     if (splits > ntiles) splits = ntiles;
     if (splits < 1) splits = 1;
@@ -1044,10 +1110,10 @@ int eg_tc_conv2d_bwd_weight(const eg_conv_shape* s, const float* x, const float*
         cudaError_t e = cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)P.ntaps * s->Ci * s->Co, st);
         if (e != cudaSuccess) return eg_fail(e, __FILE__, __LINE__);
     }
-    dim3 grid(rows / 128, cols / P.BN, P.ntaps * splits);
+    dim3 grid(row_tiles, cols / P.BN, P.ntaps * splits);
     if (P.mode == 3) {
         const size_t smem = (size_t)kStagesW3 * ((4 + 2 * (P.BN / 32)) * P.pix * 128) + 1024;
-        conv_tc_wgrad<kStagesW3, true><<<grid, kThreads, smem, st>>>(maps, P);
+        conv_tc_wgrad<kStagesW3, true><<<grid, kThreadsW3, smem, st>>>(maps, P);
     } else {
         const size_t smem = (size_t)kStagesW * ((4 + P.BN / 32) * P.pix * 128) + 1024;
         conv_tc_wgrad<kStagesW, false><<<grid, kThreads, smem, st>>>(maps, P);

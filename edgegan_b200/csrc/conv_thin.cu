@@ -1,0 +1,297 @@
+// Thin-channel convolutions (Ci <= 4: the image-side layers of the critics, the encoder and the generator) on the
+// tensor-core path.
+//
+// Replaces for those layers: tf.nn.conv2d / tf.nn.conv2d_transpose (edgegan/nn/modules/conv.py:29,49-53) and their
+// gradients.  With 3 input channels the implicit-GEMM K dimension of one filter tap is 12 bytes -- below TMA's
+// 16-byte granularity and far below a 32-channel K slab -- so the tcgen05 conv kernels cannot read the image
+// directly, and on the FFMA path these layers ran at ~10 % of their HBM roofline.  Here the K dimension is the
+// whole receptive field (KH*KW*Ci = 48 or 75 values, padded to a multiple of 32):
+//
+//   forward       y  = im2col(x)[P, Kpad] . w[Kpad, Co]                 (P = N*OH*OW output pixels)
+//   input grad    dx = col2im( dy[P, Co] . w^T[Co, Npad] ) + bias       (Npad = 64 or 128 >= KH*KW*Ci)
+//   filter grad   dw = im2col(x)^T[Kpad, P] . dy[P, Co]
+//
+// The dense products run on the kernels of conv_tc.cu as 1x1 convolutions over P "images" of one pixel; the
+// patch matrices live in a per-stream scratch buffer.  im2col / col2im are one pass over the patch matrix each.
+#include "common.cuh"
+
+int eg_tc_scratch(cudaStream_t st, int slot, size_t bytes, float** out);
+int eg_tc_conv2d_fwd(const eg_conv_shape* s, const float* x, const float* w, const float* bias, float* y, int three_x, cudaStream_t st);
+int eg_tc_conv2d_bwd_weight(const eg_conv_shape* s, const float* x, const float* dy, float* dw, int accumulate, int three_x, cudaStream_t st);
+
+namespace {
+
+constexpr int kThinMaxCi = 4;
+constexpr int kThinMaxK = 128;
+
+struct ThinP {
+    int N, H, W, Ci, OH, OW, KH, KW, stride, pad_t, pad_l;
+    int K, Kpad;
+};
+
+ThinP make_p(const eg_conv_shape* s) {
+    ThinP p;
+    p.N = s->N; p.H = s->H; p.W = s->W; p.Ci = s->Ci; p.OH = s->OH; p.OW = s->OW; p.KH = s->KH; p.KW = s->KW;
+    p.stride = s->stride; p.pad_t = s->pad_t; p.pad_l = s->pad_l;
+    p.K = s->KH * s->KW * s->Ci;
+    p.Kpad = (p.K + 31) / 32 * 32;
+    return p;
+}
+
+// A[q][j] = x[n, oh*s - pad_t + kh, ow*s - pad_l + kw, ci],  j = (kh*KW + kw)*Ci + ci ; zero outside the image and
+// for j >= K.  One thread writes 4 consecutive columns (16 B).
+__global__ void thin_im2col_k(const float* __restrict__ x, float* __restrict__ A, ThinP p, long long total4) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total4) return;
+    const int g4 = p.Kpad >> 2;
+    const long long q = i / g4;
+    const int j0 = (int)(i - q * g4) * 4;
+    const int ow = (int)(q % p.OW);
+    const long long t = q / p.OW;
+    const int oh = (int)(t % p.OH), n = (int)(t / p.OH);
+    float v[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const int j = j0 + e;
+        float val = 0.f;
+        if (j < p.K) {
+            const int tap = j / p.Ci, ci = j - tap * p.Ci;
+            const int kh = tap / p.KW, kw = tap - kh * p.KW;
+            const int h = oh * p.stride - p.pad_t + kh, w = ow * p.stride - p.pad_l + kw;
+            if (h >= 0 && h < p.H && w >= 0 && w < p.W) val = __ldg(x + (((long long)n * p.H + h) * p.W + w) * p.Ci + ci);
+        }
+        v[e] = val;
+    }
+    *reinterpret_cast<float4*>(A + i * 4) = make_float4(v[0], v[1], v[2], v[3]);
+}
+
+// dx[n, h, w, ci] = bias[ci] + sum over taps (kh, kw) with h = oh*s - pad_t + kh, w = ow*s - pad_l + kw of
+// C[(n, oh, ow)][(kh*KW + kw)*Ci + ci].  One thread per input pixel, all (<= 4) channels.
+__global__ void thin_col2im_k(const float* __restrict__ C, const float* __restrict__ bias, float* __restrict__ dx,
+                              ThinP p, int Npad, long long pixels) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= pixels) return;
+    const int w = (int)(i % p.W);
+    const long long t = i / p.W;
+    const int h = (int)(t % p.H), n = (int)(t / p.H);
+    float acc[kThinMaxCi];
+#pragma unroll
+    for (int c = 0; c < kThinMaxCi; ++c) acc[c] = (bias != nullptr && c < p.Ci) ? __ldg(bias + c) : 0.f;
+    for (int kh = 0; kh < p.KH; ++kh) {
+        const int hh = h + p.pad_t - kh;
+        if (hh < 0 || hh % p.stride) continue;
+        const int oh = hh / p.stride;
+        if (oh >= p.OH) continue;
+        for (int kw = 0; kw < p.KW; ++kw) {
+            const int ww = w + p.pad_l - kw;
+            if (ww < 0 || ww % p.stride) continue;
+            const int ow = ww / p.stride;
+            if (ow >= p.OW) continue;
+            const float* row = C + (((long long)n * p.OH + oh) * p.OW + ow) * Npad + (kh * p.KW + kw) * p.Ci;
+#pragma unroll
+            for (int c = 0; c < kThinMaxCi; ++c)
+                if (c < p.Ci) acc[c] += __ldg(row + c);
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < kThinMaxCi; ++c)
+        if (c < p.Ci) dx[i * p.Ci + c] = acc[c];
+}
+
+// Same patch matrix, one block per output row (n, oh): the KH input rows it reads are staged in shared memory and
+// the column -> (kh, kw, ci) decomposition comes from a table, so the inner loop has no integer division.
+template <int KPAD>
+__global__ void thin_im2col_row_k(const float* __restrict__ x, float* __restrict__ A, ThinP p) {
+    extern __shared__ float xs[];                            // [KH][W * Ci]
+    __shared__ int tab[KPAD];                                // j -> kh << 24 | kw << 16 | (kw * Ci + ci), -1 for j >= K
+    const int row = blockIdx.x, n = row / p.OH, oh = row - n * p.OH;
+    const int rowlen = p.W * p.Ci;
+    for (int kh = 0; kh < p.KH; ++kh) {
+        const int h = oh * p.stride - p.pad_t + kh;
+        const bool in = h >= 0 && h < p.H;
+        const float* src = x + ((long long)n * p.H + h) * rowlen;
+        for (int i = threadIdx.x; i < rowlen; i += blockDim.x) xs[kh * rowlen + i] = in ? __ldg(src + i) : 0.f;
+    }
+    for (int j = threadIdx.x; j < KPAD; j += blockDim.x) {
+        int t = -1;
+        if (j < p.K) {
+            const int tap = j / p.Ci, ci = j - tap * p.Ci, kh = tap / p.KW, kw = tap - kh * p.KW;
+            t = (kh << 24) | (kw << 16) | (kw * p.Ci + ci);
+        }
+        tab[j] = t;
+    }
+    __syncthreads();
+    constexpr int G4 = KPAD / 4;
+    float* Arow = A + (long long)row * p.OW * KPAD;
+    for (int idx = threadIdx.x; idx < p.OW * G4; idx += blockDim.x) {
+        const int ow = idx / G4, j0 = (idx - ow * G4) * 4;
+        const int wbase = ow * p.stride - p.pad_l;
+        float v[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int t = tab[j0 + e];
+            const int w = wbase + ((t >> 16) & 255);
+            v[e] = (t >= 0 && w >= 0 && w < p.W) ? xs[(t >> 24) * rowlen + wbase * p.Ci + (t & 0xffff)] : 0.f;
+        }
+        *reinterpret_cast<float4*>(Arow + (long long)idx * 4) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+}
+
+// col2im with the stride known at compile time: one block per input row (n, h).  The filter rows kh that reach
+// row h (at most ceil(KH / S)) each read one row of C pixels; their KW*Ci-column segments are staged in shared memory
+// with coalesced loads, then one thread per pixel w sums its taps from there.
+template <int S>
+__global__ void thin_col2im_row_k(const float* __restrict__ C, const float* __restrict__ bias, float* __restrict__ dx,
+                                  ThinP p, int Npad) {
+    extern __shared__ float cs[];                            // [valid kh][OW][KW * Ci]
+    const int row = blockIdx.x, n = row / p.H, h = row - n * p.H;
+    const int kwc = p.KW * p.Ci, seg = p.OW * kwc;
+    int nv = 0;
+    for (int kh = 0; kh < p.KH; ++kh) {
+        const int hh = h + p.pad_t - kh;
+        if (hh < 0 || hh % S) continue;
+        const int oh = hh / S;
+        if (oh >= p.OH) continue;
+        const float* src = C + ((long long)n * p.OH + oh) * p.OW * Npad + kh * kwc;
+        for (int i = threadIdx.x; i < seg; i += blockDim.x) {
+            const int ow = i / kwc, e = i - ow * kwc;
+            cs[nv * seg + i] = __ldg(src + (long long)ow * Npad + e);
+        }
+        ++nv;
+    }
+    __syncthreads();
+    for (int w = threadIdx.x; w < p.W; w += blockDim.x) {
+        float acc[kThinMaxCi];
+#pragma unroll
+        for (int c = 0; c < kThinMaxCi; ++c) acc[c] = (bias != nullptr && c < p.Ci) ? __ldg(bias + c) : 0.f;
+        for (int v = 0; v < nv; ++v) {
+            for (int kw = 0; kw < p.KW; ++kw) {
+                const int ww = w + p.pad_l - kw;
+                if (ww < 0 || ww % S) continue;
+                const int ow = ww / S;
+                if (ow >= p.OW) continue;
+                const float* r = cs + v * seg + ow * kwc + kw * p.Ci;
+#pragma unroll
+                for (int c = 0; c < kThinMaxCi; ++c)
+                    if (c < p.Ci) acc[c] += r[c];
+            }
+        }
+        float* o = dx + ((long long)row * p.W + w) * p.Ci;
+#pragma unroll
+        for (int c = 0; c < kThinMaxCi; ++c)
+            if (c < p.Ci) o[c] = acc[c];
+    }
+}
+
+// out[j][co] = j < K ? w[j][co] : 0   (the HWIO filter is already [K][Co])
+__global__ void thin_pad_rows_k(const float* __restrict__ w, float* __restrict__ out, int K, int Kpad, int Co) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= Kpad * Co) return;
+    out[i] = i < K * Co ? __ldg(w + i) : 0.f;
+}
+
+// out[co][j] = j < K ? w[j][co] : 0   (1x1 filter [Ci' = Co][Co' = Npad] of the input-gradient product)
+__global__ void thin_transpose_w_k(const float* __restrict__ w, float* __restrict__ out, int K, int Npad, int Co) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= Npad * Co) return;
+    const int co = i / Npad, j = i - co * Npad;
+    out[i] = j < K ? __ldg(w + (long long)j * Co + co) : 0.f;
+}
+
+__global__ void thin_dw_out_k(const float* __restrict__ dW, float* __restrict__ dw, int n, int accumulate) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    dw[i] = accumulate ? dw[i] + dW[i] : dW[i];
+}
+
+eg_conv_shape gemm_shape(long long P, int Ci, int Co) {
+    eg_conv_shape g{};
+    g.N = (int)P; g.H = 1; g.W = 1; g.Ci = Ci; g.OH = 1; g.OW = 1; g.Co = Co; g.KH = 1; g.KW = 1; g.stride = 1;
+    g.pad_t = 0; g.pad_l = 0;
+    return g;
+}
+
+int launch_im2col(const float* x, float* A, const ThinP& p, long long P, cudaStream_t st) {
+    const size_t smem = sizeof(float) * (size_t)p.KH * p.W * p.Ci;
+    if (smem <= 40 * 1024 && p.KW < 256 && p.KW * p.Ci < 65536) {
+        const int rows = p.N * p.OH;
+        switch (p.Kpad) {
+            case 32: thin_im2col_row_k<32><<<rows, 256, smem, st>>>(x, A, p); break;
+            case 64: thin_im2col_row_k<64><<<rows, 256, smem, st>>>(x, A, p); break;
+            case 96: thin_im2col_row_k<96><<<rows, 256, smem, st>>>(x, A, p); break;
+            default: thin_im2col_row_k<128><<<rows, 256, smem, st>>>(x, A, p); break;
+        }
+    } else {
+        const long long total4 = P * (p.Kpad / 4);
+        thin_im2col_k<<<eg_ceil_div(total4, 256), 256, 0, st>>>(x, A, p, total4);
+    }
+    EG_CHECK_LAUNCH();
+    return 0;
+}
+
+bool thin_common(const eg_conv_shape* s) {
+    if (s->Ci < 1 || s->Ci > kThinMaxCi) return false;
+    if (s->KH * s->KW * s->Ci > kThinMaxK) return false;
+    if ((long long)s->N * s->OH * s->OW >= (1ll << 31)) return false;
+    return s->stride >= 1;
+}
+
+}  // namespace
+
+int eg_thin_supported_fwd(const eg_conv_shape* s) { return thin_common(s) && s->Co % 64 == 0; }
+int eg_thin_supported_bwd_data(const eg_conv_shape* s) { return thin_common(s) && s->Co % 32 == 0; }
+int eg_thin_supported_bwd_weight(const eg_conv_shape* s) { return thin_common(s) && s->Co % 32 == 0; }
+
+int eg_thin_conv2d_fwd(const eg_conv_shape* s, const float* x, const float* w, const float* bias, float* y, int three_x,
+                       cudaStream_t st) {
+    const ThinP p = make_p(s);
+    const long long P = (long long)s->N * s->OH * s->OW;
+    float *A = nullptr, *wp = nullptr;
+    if (int r = eg_tc_scratch(st, 1, sizeof(float) * (size_t)P * p.Kpad, &A)) return r;
+    if (int r = eg_tc_scratch(st, 2, sizeof(float) * (size_t)p.Kpad * s->Co, &wp)) return r;
+    if (int r = launch_im2col(x, A, p, P, st)) return r;
+    thin_pad_rows_k<<<eg_ceil_div((long long)p.Kpad * s->Co, 256), 256, 0, st>>>(w, wp, p.K, p.Kpad, s->Co);
+    EG_CHECK_LAUNCH();
+    const eg_conv_shape g = gemm_shape(P, p.Kpad, s->Co);
+    return eg_tc_conv2d_fwd(&g, A, wp, bias, y, three_x, st);
+}
+
+int eg_thin_conv2d_bwd_data(const eg_conv_shape* s, const float* dy, const float* w, const float* bias, float* dx,
+                            int three_x, cudaStream_t st) {
+    const ThinP p = make_p(s);
+    const long long P = (long long)s->N * s->OH * s->OW;
+    const int Npad = p.K <= 64 ? 64 : 128;
+    float *C = nullptr, *wt = nullptr;
+    if (int r = eg_tc_scratch(st, 1, sizeof(float) * (size_t)P * Npad, &C)) return r;
+    if (int r = eg_tc_scratch(st, 2, sizeof(float) * (size_t)Npad * s->Co, &wt)) return r;
+    thin_transpose_w_k<<<eg_ceil_div((long long)Npad * s->Co, 256), 256, 0, st>>>(w, wt, p.K, Npad, s->Co);
+    EG_CHECK_LAUNCH();
+    const eg_conv_shape g = gemm_shape(P, s->Co, Npad);
+    if (int r = eg_tc_conv2d_fwd(&g, dy, wt, nullptr, C, three_x, st)) return r;
+    const int threads = s->W >= 256 ? 256 : (s->W + 31) / 32 * 32;
+    const size_t smem = sizeof(float) * (size_t)((s->KH + s->stride - 1) / s->stride) * s->OW * s->KW * s->Ci;
+    if (s->stride == 1 && smem <= 40 * 1024) thin_col2im_row_k<1><<<s->N * s->H, threads, smem, st>>>(C, bias, dx, p, Npad);
+    else if (s->stride == 2 && smem <= 40 * 1024) thin_col2im_row_k<2><<<s->N * s->H, threads, smem, st>>>(C, bias, dx, p, Npad);
+    else {
+        const long long pixels = (long long)s->N * s->H * s->W;
+        thin_col2im_k<<<eg_ceil_div(pixels, 256), 256, 0, st>>>(C, bias, dx, p, Npad, pixels);
+    }
+    EG_CHECK_LAUNCH();
+    return 0;
+}
+
+int eg_thin_conv2d_bwd_weight(const eg_conv_shape* s, const float* x, const float* dy, float* dw, int accumulate,
+                              int three_x, cudaStream_t st) {
+    const ThinP p = make_p(s);
+    const long long P = (long long)s->N * s->OH * s->OW;
+    float *A = nullptr, *dW = nullptr;
+    if (int r = eg_tc_scratch(st, 1, sizeof(float) * (size_t)P * p.Kpad, &A)) return r;
+    if (int r = eg_tc_scratch(st, 2, sizeof(float) * (size_t)p.Kpad * s->Co, &dW)) return r;
+    if (int r = launch_im2col(x, A, p, P, st)) return r;
+    const eg_conv_shape g = gemm_shape(P, p.Kpad, s->Co);
+    if (int r = eg_tc_conv2d_bwd_weight(&g, A, dy, dW, 0, three_x, st)) return r;
+    const int n = p.K * s->Co;
+    thin_dw_out_k<<<eg_ceil_div(n, 256), 256, 0, st>>>(dW, dw, n, accumulate);
+    EG_CHECK_LAUNCH();
+    return 0;
+}

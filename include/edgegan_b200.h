@@ -39,7 +39,9 @@ int eg_abi_version(void);
 int eg_device_info(int* sm_count, int* cc_major, int* cc_minor);
 
 /* What EG_ALGO_AUTO resolves to for layers the tensor-core kernels support (default EG_ALGO_TC3X);
- * layers they do not support (thin channels) always take the fp32 SIMT kernel. */
+ * layers they do not support (channel counts that are not multiples of 32 / 64; the forward and filter-gradient
+ * passes of the 3-channel image layers) take the fp32 SIMT kernel.  The input gradient of the 3-channel layers runs
+ * on the tensor cores as a dense product plus col2im (csrc/conv_thin.cu). */
 int eg_set_default_algo(int algo);
 int eg_get_default_algo(void);
 

@@ -24,6 +24,14 @@ CASES = [
     (2, 32, 32, 64, 128, 1, 1, 0, 32, 32),     # 1x1 shortcut
     (3, 16, 16, 128, 128, 3, 1, 1, 16, 16),    # SAME 3x3 stride 1 (classifier style), batch not a tile multiple
     (8, 8, 8, 256, 512, 5, 2, 1, 4, 4),        # few output tiles, long K -> split-K path (generator at small batch)
+    # thin layers (conv_thin.cu: patch matrix + dense product on the same kernels)
+    (3, 16, 32, 3, 64, 4, 2, 1, 8, 16),        # critic first layer, pixel count not a tile multiple
+    (2, 20, 12, 3, 64, 5, 2, 1, 10, 6),        # generator last conv-transpose seen as a conv (75 -> 96 / 128 columns)
+    (2, 9, 9, 3, 64, 3, 1, 1, 9, 9),           # stride 1, odd extent
+    (2, 8, 8, 1, 128, 4, 2, 1, 4, 4),          # single channel
+    # filter gradient whose row side is below 128 channels (TMA zero-fills the missing rows)
+    (2, 16, 16, 64, 64, 3, 1, 1, 16, 16),
+    (2, 8, 8, 192, 64, 1, 1, 0, 8, 8),         # 1.5 row tiles
 ]
 
 
@@ -59,7 +67,7 @@ ALGO_TOL = {"tc": 2e-3, "tc3x": 2e-5}
 
 @pytest.mark.parametrize("algo", ["tc", "tc3x"])
 @pytest.mark.parametrize("case", CASES)
-def test_tc_conv_trio(dev, ref, case, algo):
+def test_tc_conv_trio(dev, ref, case, algo, request):
     import ctypes as C
     TOL = ALGO_TOL[algo]
     N, H, W, Ci, Co, k, s, p, OH, OW = case
@@ -67,6 +75,9 @@ def test_tc_conv_trio(dev, ref, case, algo):
     x, w, b = rnd(rs, N, H, W, Ci), rnd(rs, k, k, Ci, Co, scale=0.05), rnd(rs, Co)
     dy, bi = rnd(rs, N, OH, OW, Co), rnd(rs, Ci)
     cs = dev._cs(x.shape, w.shape, dy.shape, s, p)
+    # thin layers: route all three passes through conv_thin.cu (by default only the input gradient goes there)
+    dev.lib.eg_debug_set(5, 7 if Ci <= 4 else 2)
+    request.addfinalizer(lambda: dev.lib.eg_debug_set(5, 2))
     used = [dev.lib.eg_conv2d_algo_for(C.byref(cs), i, 2) for i in range(3)]
     # these shapes are the ones the tensor-core path must cover
     assert used == [2, 2, 2], used
