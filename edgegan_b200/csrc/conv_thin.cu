@@ -1,4 +1,4 @@
-// Thin-channel convolutions (Ci <= 4: the image-side layers of the critics, the encoder and the generator) on the
+// Thin-channel convolutions (Ci <= 8: the image-side layers of the critics, the encoder and the generator) on the
 // tensor-core path.
 //
 // Replaces for those layers: tf.nn.conv2d / tf.nn.conv2d_transpose (edgegan/nn/modules/conv.py:29,49-53) and their
@@ -21,7 +21,7 @@ int eg_tc_conv2d_bwd_weight(const eg_conv_shape* s, const float* x, const float*
 
 namespace {
 
-constexpr int kThinMaxCi = 4;
+constexpr int kThinMaxCi = 8;
 constexpr int kThinMaxK = 128;
 
 struct ThinP {

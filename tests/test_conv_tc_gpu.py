@@ -29,6 +29,7 @@ CASES = [
     (2, 20, 12, 3, 64, 5, 2, 1, 10, 6),        # generator last conv-transpose seen as a conv (75 -> 96 / 128 columns)
     (2, 9, 9, 3, 64, 3, 1, 1, 9, 9),           # stride 1, odd extent
     (2, 8, 8, 1, 128, 4, 2, 1, 4, 4),          # single channel
+    (2, 12, 12, 8, 128, 3, 1, 1, 12, 12),      # classifier first layer (8 channels, 72 -> 96 / 128 columns)
     # filter gradient whose row side is below 128 channels (TMA zero-fills the missing rows)
     (2, 16, 16, 64, 64, 3, 1, 1, 16, 16),
     (2, 8, 8, 192, 64, 1, 1, 0, 8, 8),         # 1.5 row tiles
@@ -76,7 +77,7 @@ def test_tc_conv_trio(dev, ref, case, algo, request):
     dy, bi = rnd(rs, N, OH, OW, Co), rnd(rs, Ci)
     cs = dev._cs(x.shape, w.shape, dy.shape, s, p)
     # thin layers: route all three passes through conv_thin.cu (by default only the input gradient goes there)
-    dev.lib.eg_debug_set(5, 7 if Ci <= 4 else 2)
+    dev.lib.eg_debug_set(5, 7 if Ci <= 8 else 2)
     request.addfinalizer(lambda: dev.lib.eg_debug_set(5, 2))
     used = [dev.lib.eg_conv2d_algo_for(C.byref(cs), i, 2) for i in range(3)]
     # these shapes are the ones the tensor-core path must cover
