@@ -286,7 +286,7 @@ def main():
         for k in range(args.warmup + args.steps):
             step_resident(k)
         torch.cuda.synchronize()
-        print(json.dumps({"ncu_run": True, "launches_per_step": ops.launches // (args.warmup + args.steps)}))
+        print(json.dumps({"ncu_run": True, "launches_per_step": launches_per_step[0]}))
         return
     ms_step, launches = timed(step_resident, args.steps, max(args.warmup, 3))
     clocks = sampler.stop() if rank == 0 else None

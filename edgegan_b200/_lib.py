@@ -28,6 +28,8 @@ SIGNATURES = {
     "eg_set_default_algo": [i32],
     "eg_get_default_algo": [],
     "eg_debug_set": [i32, i32],
+    "eg_kernel_launches": [],
+    "eg_crc32c": [vp, i64, C.c_uint],
     "eg_conv2d_algo_for": [_csp, i32, i32],
     "eg_conv2d_fwd": [_csp, vp, vp, vp, vp, i32, vp],
     "eg_conv2d_bwd_data": [_csp, vp, vp, vp, vp, i32, vp],
@@ -80,7 +82,7 @@ SIGNATURES = {
     "eg_onehot_concat": [vp, i32, i32, i32, vp, vp],
     "eg_rmsprop": [vp, vp, vp, i64, f32, f32, f32, vp],
 }
-_RESTYPE = {"eg_last_error": C.c_char_p}
+_RESTYPE = {"eg_last_error": C.c_char_p, "eg_kernel_launches": C.c_longlong, "eg_crc32c": C.c_uint}
 
 _lib = None
 
@@ -100,7 +102,7 @@ def load():
     for name, args in SIGNATURES.items():
         fn = getattr(lib, name)          # AttributeError here == header / library mismatch
         fn.argtypes = args
-        fn.restype = C.c_int
+        fn.restype = _RESTYPE.get(name, C.c_int)
     _lib = lib
     return lib
 

@@ -17,6 +17,7 @@ int eg_tc_conv2d_fwd(const eg_conv_shape* s, const float* x, const float* w, con
 int eg_tc_conv2d_bwd_data(const eg_conv_shape* s, const float* dy, const float* w, const float* bias, float* dx, int three_x, cudaStream_t st);
 int eg_tc_conv2d_bwd_weight(const eg_conv_shape* s, const float* x, const float* dy, float* dw, int accumulate, int three_x, cudaStream_t st);
 
+unsigned long long g_eg_kernel_launches = 0;
 static thread_local char g_err[512] = "";
 
 int eg_fail(cudaError_t e, const char* file, int line) {
@@ -69,6 +70,7 @@ int eg_set_default_algo(int algo) {
     return 0;
 }
 int eg_get_default_algo(void) { return g_default_algo; }
+long long eg_kernel_launches(void) { return (long long)g_eg_kernel_launches; }
 
 static int resolve(int algo, int supported) {
     if (algo == EG_ALGO_AUTO) algo = g_default_algo;

@@ -4,8 +4,11 @@
 #include <stdint.h>
 #include "../../include/edgegan_b200.h"
 
+// every kernel launch of the library is followed by this check; it also feeds eg_kernel_launches()
+extern unsigned long long g_eg_kernel_launches;
 #define EG_CHECK_LAUNCH()                                                       \
     do {                                                                        \
+        ++g_eg_kernel_launches;                                                 \
         cudaError_t e__ = cudaGetLastError();                                   \
         if (e__ != cudaSuccess) return eg_fail(e__, __FILE__, __LINE__);        \
     } while (0)

@@ -123,6 +123,86 @@ class EdgeGAN(object):
             out.update(st.export(what))
         return out
 
+    # ---- checkpoints (edgegan.py:421,547 tf.train.Saver over all global variables; :635-657 save / load) ---------
+    @property
+    def model_name(self):
+        """edgegan.py:659-661."""
+        return "EdgeGAN-Model"
+
+    @staticmethod
+    def _tf_name(name):
+        """internal variable name -> the name tf.train.Saver stores.  Only the spectral-norm vectors differ: the
+        reference creates `u` under variable_scope(W.name.rsplit('/', 1)[0]) opened INSIDE the layer scope
+        (nn/modules/normalization.py:40-42), which doubles the path: D2/Conv/u -> D2/Conv/D2/Conv/u."""
+        if name.endswith("/u"):
+            scope = name[:-2]
+            return f"{scope}/{scope}/u"
+        return name
+
+    def checkpoint_tensors(self):
+        """Everything the reference's Saver writes: variables, the generators' batch-norm moving statistics (never
+        updated by the reference: its update ops are not run), spectral-norm vectors, and per trained variable the
+        RMSProp slots `<var>/RMSProp` (rms) and `<var>/RMSProp_1` (momentum, dead state at momentum = 0)."""
+        out = {}
+        for key, st in self.stores.items():
+            var = st.export("var")
+            for n, a in var.items():
+                out[self._tf_name(n)] = a
+            if self._built == "train" and not key.endswith("/aux"):
+                for n, a in st.export("ms").items():
+                    out[n + "/RMSProp"] = a
+                    out[n + "/RMSProp_1"] = np.zeros_like(a)
+        for g in ("G1", "G2"):
+            c = self.gf_dim * 8
+            out[f"{g}/batch_norm/BatchNorm/moving_mean"] = np.zeros((c,), np.float32)
+            out[f"{g}/batch_norm/BatchNorm/moving_variance"] = np.ones((c,), np.float32)
+        return out
+
+    def save(self, saver, checkpoint_dir, step):
+        """edgegan.py:635-639: writes <checkpoint_dir>/EdgeGAN-Model-<step>.{index,data-00000-of-00001} in the
+        TensorFlow bundle format and updates <checkpoint_dir>/checkpoint.  `saver` is unused (signature parity)."""
+        from .. import checkpoint as ckpt
+        import os
+        print(" [*] Saving checkpoints...")
+        os.makedirs(checkpoint_dir, exist_ok=True)
+        prefix = os.path.join(checkpoint_dir, f"{self.model_name}-{int(step)}")
+        if self.comm.rank == 0:
+            ckpt.write_bundle(prefix, self.checkpoint_tensors())
+            ckpt.update_checkpoint_state(checkpoint_dir, prefix)
+        return prefix
+
+    def load(self, saver, checkpoint_dir):
+        """edgegan.py:641-657 -> (found, step).  Variables are matched by name; a checkpoint without the RMSProp slots
+        (or a test-time model, which has none) loads the variables only.  Missing variables raise, like Saver.restore."""
+        from .. import checkpoint as ckpt
+        import os
+        print(" [*] Reading checkpoints {}...".format(checkpoint_dir))
+        state = ckpt.get_checkpoint_state(checkpoint_dir)
+        if not state:
+            print(" [*] Failed to find a checkpoint")
+            return False, 0
+        name = os.path.basename(state["model_checkpoint_path"])
+        rd = ckpt.BundleReader(os.path.join(checkpoint_dir, name))
+        try:
+            for key, st in self.stores.items():
+                vals, slots = {}, {}
+                for n in st.offsets:
+                    tn = self._tf_name(n)
+                    if tn not in rd:
+                        raise KeyError(f"{tn} not found in checkpoint {name}")
+                    vals[n] = rd.tensor(tn)
+                    if n + "/RMSProp" in rd:
+                        slots[n] = rd.tensor(n + "/RMSProp")
+                st.load(vals, strict=True)
+                if slots and self._built == "train":
+                    st.load(slots, strict=False, what="ms")
+        finally:
+            rd.close()
+        if hasattr(self, "classifier"):
+            self.classifier.invalidate()
+        print(" [*] Success to read {}".format(name))
+        return True, ckpt.step_of(name)
+
     def num_params(self):
         return {k: st.num_params for k, st in self.stores.items()}
 

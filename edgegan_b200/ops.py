@@ -41,8 +41,12 @@ class DeviceOps:
         self.sm_count, self.cc = sm.value, (maj.value, mnr.value)
         self._bufs = {}
         self._shape_cache = {}
-        self.launches = 0
         self.pass_algo = {}          # debugging: per-pass algorithm override {'fwd'|'dgrad'|'wgrad': name}
+
+    @property
+    def launches(self):
+        """kernels launched by the library so far (counted inside the library, eg_kernel_launches)"""
+        return int(self.lib.eg_kernel_launches())
 
     # ---- memory -----------------------------------------------------------------------------
     def empty(self, shape):
@@ -100,24 +104,20 @@ class DeviceOps:
     def conv_fwd(self, x, w, bias, y, stride, pad, algo=None):
         """y = conv(x, w) (+bias): x[N,H,W,Ci] w[KH,KW,Ci,Co] y[N,OH,OW,Co]; zero pad `pad` before."""
         s = self._cs(x.shape, w.shape, y.shape, stride, pad)
-        self.launches += 1
         _lib.check(self.lib.eg_conv2d_fwd(C.byref(s), _p(x), _p(w), _p(bias), _p(y), ALGO[algo or self.pass_algo.get("fwd")], self._st), "conv2d_fwd")
 
     def conv_bwd_data(self, dy, w, bias, dx, stride, pad, algo=None):
         """dx = conv input-gradient (== conv2d_transpose forward) (+bias over dx channels)."""
         s = self._cs(dx.shape, w.shape, dy.shape, stride, pad)
-        self.launches += 1
         _lib.check(self.lib.eg_conv2d_bwd_data(C.byref(s), _p(dy), _p(w), _p(bias), _p(dx), ALGO[algo or self.pass_algo.get("dgrad")], self._st), "conv2d_bwd_data")
 
     def conv_bwd_weight(self, x, dy, dw, stride, pad, accumulate=False, algo=None):
         """dw (+)= filter gradient."""
         s = self._cs(x.shape, dw.shape, dy.shape, stride, pad)
-        self.launches += 2
         _lib.check(self.lib.eg_conv2d_bwd_weight(C.byref(s), _p(x), _p(dy), _p(dw), int(accumulate), ALGO[algo or self.pass_algo.get("wgrad")], self._st), "conv2d_bwd_weight")
 
     def bias_grad(self, dy, db, accumulate=False):
         Cn = dy.shape[-1]
-        self.launches += 1
         _lib.check(self.lib.eg_bias_grad(_p(dy), dy.numel() // Cn, Cn, _p(db), int(accumulate), self._st), "bias_grad")
 
     # ---- norms / activations ----------------------------------------------------------------
@@ -128,216 +128,173 @@ class DeviceOps:
 
     def instnorm_fwd(self, x, y, stats, act):
         N, P, Cn = self._npc(x)
-        self.launches += 1
         _lib.check(self.lib.eg_instnorm_fwd(_p(x), _p(y), _p(stats), N, P, Cn, IN_EPS, ACT[act], self._st), "instnorm_fwd")
 
     def instnorm_bwd(self, x, stats, gy, addend, gx, act):
         N, P, Cn = self._npc(x)
-        self.launches += 1
         _lib.check(self.lib.eg_instnorm_bwd(_p(x), _p(stats), _p(gy), _p(addend), _p(gx), N, P, Cn, IN_EPS, ACT[act], self._st), "instnorm_bwd")
 
     def instnorm_bwd2(self, x, stats, gy, t, out_gy, out_x, act):
         N, P, Cn = self._npc(x)
-        self.launches += 1
         _lib.check(self.lib.eg_instnorm_bwd2(_p(x), _p(stats), _p(gy), _p(t), _p(out_gy), _p(out_x), N, P, Cn, IN_EPS, ACT[act], self._st), "instnorm_bwd2")
 
     def act_fwd(self, x, y, act):
-        self.launches += 1
         _lib.check(self.lib.eg_act_fwd(_p(x), _p(y), x.numel(), ACT[act], self._st), "act_fwd")
 
     def act_bwd(self, x_pre, gy, gx, act):
-        self.launches += 1
         _lib.check(self.lib.eg_act_bwd(_p(x_pre), _p(gy), _p(gx), x_pre.numel(), ACT[act], self._st), "act_bwd")
 
     def bn_stats(self, x, sums):
         Cn = x.shape[-1]
-        self.launches += 1
         _lib.check(self.lib.eg_bn_stats(_p(x), _p(sums), x.numel() // Cn, Cn, self._st), "bn_stats")
 
     def bn_apply(self, x, sums, count, gamma, beta, y, act):
         Cn = x.shape[-1]
-        self.launches += 1
         _lib.check(self.lib.eg_bn_apply(_p(x), _p(sums), float(count), _p(gamma), _p(beta), _p(y), x.numel() // Cn, Cn, BN_EPS, ACT[act], self._st), "bn_apply")
 
     def bn_bwd_reduce(self, x, sums, count, gamma, beta, gy, red, act):
         Cn = x.shape[-1]
-        self.launches += 1
         _lib.check(self.lib.eg_bn_bwd_reduce(_p(x), _p(sums), float(count), _p(gamma), _p(beta), _p(gy), _p(red), x.numel() // Cn, Cn, BN_EPS, ACT[act], self._st), "bn_bwd_reduce")
 
     def bn_bwd_apply(self, x, sums, count, gamma, beta, gy, red, gx, act):
         Cn = x.shape[-1]
-        self.launches += 1
         _lib.check(self.lib.eg_bn_bwd_apply(_p(x), _p(sums), float(count), _p(gamma), _p(beta), _p(gy), _p(red), _p(gx), x.numel() // Cn, Cn, BN_EPS, ACT[act], self._st), "bn_bwd_apply")
 
     # ---- discriminator head -------------------------------------------------------------------
     def rowdot_fwd(self, h, w, bias, d):
         B = h.shape[0]
-        self.launches += 1
         _lib.check(self.lib.eg_rowdot_fwd(_p(h), _p(w), _p(bias), _p(d), B, h.numel() // B, self._st), "rowdot_fwd")
 
     def rowdot_bwd_input(self, gd, w, gh):
         B = gh.shape[0]
-        self.launches += 1
         _lib.check(self.lib.eg_rowdot_bwd_input(_p(gd), _p(w), _p(gh), B, gh.numel() // B, self._st), "rowdot_bwd_input")
 
     def rowdot_bwd_weight(self, gd, h, gw, gb, accumulate=False):
         B = h.shape[0]
-        self.launches += 1
         _lib.check(self.lib.eg_rowdot_bwd_weight(_p(gd), _p(h), _p(gw), _p(gb), B, h.numel() // B, int(accumulate), self._st), "rowdot_bwd_weight")
 
     # ---- resize / slices ----------------------------------------------------------------------
     def bicubic_up2_fwd(self, x, y):
         N, H, W, Cn = x.shape
-        self.launches += 1
         _lib.check(self.lib.eg_bicubic_up2_fwd(_p(x), _p(y), N, H, W, Cn, self._st), "bicubic_up2_fwd")
 
     def bicubic_up2_bwd(self, gy, gx):
         N, H, W, Cn = gx.shape
-        self.launches += 1
         _lib.check(self.lib.eg_bicubic_up2_bwd(_p(gy), _p(gx), N, H, W, Cn, self._st), "bicubic_up2_bwd")
 
     def copy_wslice(self, src, src_w0, dst, dst_w0, width):
         """dst[:, :, dst_w0:dst_w0+width, :] = src[:, :, src_w0:src_w0+width, :]  (NHWC width slices)"""
         N, H, Ws, Cn = src.shape
         Wd = dst.shape[2]
-        self.launches += 1
         _lib.check(self.lib.eg_copy2d(src.data_ptr() + 4 * src_w0 * Cn, Ws * Cn, dst.data_ptr() + 4 * dst_w0 * Cn,
                                       Wd * Cn, N * H, width * Cn, self._st), "copy2d")
 
     def copy2d(self, src, src_off, src_stride, dst, dst_off, dst_stride, rows, cols):
         """dst.flat[dst_off + r*dst_stride + c] = src.flat[src_off + r*src_stride + c]  (element units)"""
-        self.launches += 1
         _lib.check(self.lib.eg_copy2d(src.data_ptr() + 4 * src_off, src_stride, dst.data_ptr() + 4 * dst_off, dst_stride,
                                       rows, cols, self._st), "copy2d")
 
     def copy(self, src, dst):
-        self.launches += 1
         _lib.check(self.lib.eg_copy2d(_p(src), src.numel(), _p(dst), dst.numel(), 1, src.numel(), self._st), "copy2d")
 
     def fill(self, dst, value):
-        self.launches += 1
         _lib.check(self.lib.eg_fill(_p(dst), dst.numel(), float(value), self._st), "fill")
 
     def axpby(self, x, y, a, b):
         """y = a*x + b*y"""
-        self.launches += 1
         _lib.check(self.lib.eg_axpby(_p(x), _p(y), x.numel(), float(a), float(b), self._st), "axpby")
 
     # ---- WGAN-GP --------------------------------------------------------------------------------
     def gp_interpolate(self, real, fake, alpha, xhat):
         B = real.shape[0]
-        self.launches += 1
         _lib.check(self.lib.eg_gp_interpolate(_p(real), _p(fake), _p(alpha), _p(xhat), B, real.numel() // B, self._st), "gp_interpolate")
 
     def gp_seed(self, d, dd):
-        self.launches += 1
         _lib.check(self.lib.eg_gp_seed(_p(d), _p(dd), d.numel(), self._st), "gp_seed")
 
     def gp_penalty(self, g, gbar, norms, loss, weight, inv_global_batch):
         B = g.shape[0]
-        self.launches += 1
         _lib.check(self.lib.eg_gp_penalty(_p(g), _p(gbar), _p(norms), _p(loss), B, g.numel() // B, float(weight), float(inv_global_batch), self._st), "gp_penalty")
 
     def gp_seed_bwd(self, d, ddbar, dbar):
-        self.launches += 1
         _lib.check(self.lib.eg_gp_seed_bwd(_p(d), _p(ddbar), _p(dbar), d.numel(), self._st), "gp_seed_bwd")
 
     def sum_scaled(self, x, scale, out, accumulate=False):
-        self.launches += 1
         _lib.check(self.lib.eg_sum_scaled(_p(x), x.numel(), float(scale), _p(out), int(accumulate), self._st), "sum_scaled")
 
     # ---- encoder pieces ---------------------------------------------------------------------------
     def reflect_pad_fwd(self, x, y, p):
         N, H, W, Cn = x.shape
-        self.launches += 1
         _lib.check(self.lib.eg_reflect_pad_fwd(_p(x), _p(y), N, H, W, Cn, p, self._st), "reflect_pad_fwd")
 
     def reflect_pad_bwd(self, gy, gx, p):
         N, H, W, Cn = gx.shape
-        self.launches += 1
         _lib.check(self.lib.eg_reflect_pad_bwd(_p(gy), _p(gx), N, H, W, Cn, p, self._st), "reflect_pad_bwd")
 
     def addrelu_pool2_fwd(self, a, b, y):
         N, H, W, Cn = a.shape
-        self.launches += 1
         _lib.check(self.lib.eg_addrelu_pool2_fwd(_p(a), _p(b), _p(y), N, H, W, Cn, self._st), "addrelu_pool2_fwd")
 
     def addrelu_pool2_bwd(self, a, b, gy, g):
         N, H, W, Cn = a.shape
-        self.launches += 1
         _lib.check(self.lib.eg_addrelu_pool2_bwd(_p(a), _p(b), _p(gy), _p(g), N, H, W, Cn, self._st), "addrelu_pool2_bwd")
 
     def relu_globalmean_fwd(self, x, y):
         N, P, Cn = self._npc(x)
-        self.launches += 1
         _lib.check(self.lib.eg_relu_globalmean_fwd(_p(x), _p(y), N, P, Cn, self._st), "relu_globalmean_fwd")
 
     def relu_globalmean_bwd(self, x, gy, gx):
         N, P, Cn = self._npc(x)
-        self.launches += 1
         _lib.check(self.lib.eg_relu_globalmean_bwd(_p(x), _p(gy), _p(gx), N, P, Cn, self._st), "relu_globalmean_bwd")
 
     def reparam_fwd(self, mu, ls, eps, z):
-        self.launches += 1
         ed = eps if isinstance(eps, torch.Tensor) else None       # device scalar (graph replay) or python float
         _lib.check(self.lib.eg_reparam_fwd(_p(mu), _p(ls), 0.0 if ed is not None else float(eps), _p(ed), _p(z), mu.numel(), self._st), "reparam_fwd")
 
     def zl1_loss_bwd(self, mu, ls, eps, target, weight, inv_global_count, gmu, gls, loss):
         B, Z = mu.shape
-        self.launches += 1
         ed = eps if isinstance(eps, torch.Tensor) else None
         _lib.check(self.lib.eg_zl1_loss_bwd(_p(mu), _p(ls), 0.0 if ed is not None else float(eps), _p(ed), _p(target), target.shape[1], B, Z, float(weight),
                                             float(inv_global_count), _p(gmu), _p(gls), _p(loss), self._st), "zl1_loss_bwd")
 
     def onehot_concat(self, z, zdim, classes, out):
-        self.launches += 1
         _lib.check(self.lib.eg_onehot_concat(_p(z), z.shape[0], zdim, classes, _p(out), self._st), "onehot_concat")
 
     # ---- classifier pieces ------------------------------------------------------------------------
     def prelu_fwd(self, x, leak, y):
-        self.launches += 1
         _lib.check(self.lib.eg_prelu_fwd(_p(x), _p(leak), _p(y), x.numel(), self._st), "prelu_fwd")
 
     def prelu_bwd(self, x, leak, gy, gx, gleak, accumulate_leak=False):
-        self.launches += 1
         _lib.check(self.lib.eg_prelu_bwd(_p(x), _p(leak), _p(gy), _p(gx), _p(gleak), x.numel(), int(accumulate_leak), self._st), "prelu_bwd")
 
     def minmax_fwd(self, x, y, stats):
         N, P, Cn = self._npc(x)
-        self.launches += 1
         _lib.check(self.lib.eg_minmax_fwd(_p(x), _p(y), _p(stats), N, P, Cn, self._st), "minmax_fwd")
 
     def minmax_bwd(self, x, stats, gy, gx):
         N, P, Cn = self._npc(x)
-        self.launches += 1
         _lib.check(self.lib.eg_minmax_bwd(_p(x), _p(stats), _p(gy), _p(gx), N, P, Cn, self._st), "minmax_bwd")
 
     def fma3(self, a, b, c, out):
-        self.launches += 1
         _lib.check(self.lib.eg_fma3(_p(a), _p(b), _p(c), _p(out), a.numel(), self._st), "fma3")
 
     def mul(self, a, b, out):
-        self.launches += 1
         _lib.check(self.lib.eg_mul(_p(a), _p(b), _p(out), a.numel(), self._st), "mul")
 
     def add_pool2_fwd(self, a, b, y):
         N, H, W, Cn = a.shape
-        self.launches += 1
         _lib.check(self.lib.eg_add_pool2_fwd(_p(a), _p(b), _p(y), N, H, W, Cn, self._st), "add_pool2_fwd")
 
     def pool2_bwd(self, gy, gx, accumulate=False):
         N, H, W, Cn = gx.shape
-        self.launches += 1
         _lib.check(self.lib.eg_pool2_bwd(_p(gy), _p(gx), N, H, W, Cn, int(accumulate), self._st), "pool2_bwd")
 
     def globalmean_fwd(self, x, y):
         N, P, Cn = self._npc(x)
-        self.launches += 1
         _lib.check(self.lib.eg_globalmean_fwd(_p(x), _p(y), N, P, Cn, self._st), "globalmean_fwd")
 
     def globalmean_bwd(self, gy, gx):
         N, P, Cn = self._npc(gx)
-        self.launches += 1
         _lib.check(self.lib.eg_globalmean_bwd(_p(gy), _p(gx), N, P, Cn, self._st), "globalmean_bwd")
 
     def sn_ws_floats(self, K, Cn):
@@ -345,17 +302,14 @@ class DeviceOps:
 
     def spectral_norm_fwd(self, W, u, Wbar, ws):
         Cn = W.shape[-1]
-        self.launches += 4
         _lib.check(self.lib.eg_spectral_norm_fwd(_p(W), _p(u), _p(Wbar), _p(ws), W.numel() // Cn, Cn, self._st), "spectral_norm_fwd")
 
     def spectral_norm_bwd(self, W, u, ws, Gbar, gW):
         Cn = W.shape[-1]
-        self.launches += 4
         _lib.check(self.lib.eg_spectral_norm_bwd(_p(W), _p(u), _p(ws), _p(Gbar), _p(gW), W.numel() // Cn, Cn, self._st), "spectral_norm_bwd")
 
     def softmax_ce_bwd(self, logits, z, label_col, focal, weight, inv_global_batch, glogits, loss):
         B, Cn = logits.shape
-        self.launches += 1
         _lib.check(self.lib.eg_softmax_ce_bwd(_p(logits), _p(z), z.shape[1], label_col, B, Cn, int(focal), float(weight),
                                               float(inv_global_batch), _p(glogits), _p(loss), self._st), "softmax_ce_bwd")
 
@@ -363,10 +317,8 @@ class DeviceOps:
         """dst[..., dst_c0:dst_c0+width] = src[..., src_c0:src_c0+width]  (channel slices / tf.concat on channels)"""
         Cs, Cd = src.shape[-1], dst.shape[-1]
         rows = src.numel() // Cs
-        self.launches += 1
         _lib.check(self.lib.eg_copy2d(src.data_ptr() + 4 * src_c0, Cs, dst.data_ptr() + 4 * dst_c0, Cd, rows, width, self._st), "copy2d")
 
     # ---- optimizer ----------------------------------------------------------------------------------
     def rmsprop(self, var, grad, ms, lr, decay=0.9, eps=1e-10):
-        self.launches += 1
         _lib.check(self.lib.eg_rmsprop(_p(var), _p(grad), _p(ms), var.numel(), float(lr), float(decay), float(eps), self._st), "rmsprop")

@@ -127,8 +127,9 @@ class ParamStore:
     def names(self):
         return list(self.offsets)
 
-    def load(self, values, strict=True):
-        """values: name -> numpy array (e.g. oracle / checkpoint weights)."""
+    def load(self, values, strict=True, what="var"):
+        """values: name -> numpy array (e.g. oracle / checkpoint weights); what = 'var' or 'ms' (the RMSProp rms slot)."""
+        dst = {"var": self.flat, "ms": self.ms}[what]
         host = np.zeros(self.size, np.float32)
         cur = None
         for s in self.specs:
@@ -143,9 +144,9 @@ class ParamStore:
                 raise KeyError(s.name)
             else:
                 if cur is None:
-                    cur = self.ops.to_numpy(self.flat)
+                    cur = self.ops.to_numpy(dst)
                 host[o:o + n] = cur[o:o + n]
-        self.ops.upload(self.flat, host)
+        self.ops.upload(dst, host)
 
     def export(self, what="var"):
         src = {"var": self.flat, "grad": self.grad, "ms": self.ms}[what]

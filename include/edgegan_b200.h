@@ -48,6 +48,14 @@ int eg_get_default_algo(void);
 /* development knob (kernel layout experiments from tools/tc_probe.py); not part of the stable surface */
 int eg_debug_set(int key, int value);
 
+/* number of CUDA kernels the library has launched so far in this process (host-side counter, one host thread per
+ * rank; launches recorded into a CUDA graph count once, at capture) -- bench.py's gpu_launches */
+long long eg_kernel_launches(void);
+
+/* CRC-32C (Castagnoli) of `n` bytes of HOST memory continuing from `crc` (0 to start): the checksum of the TensorFlow
+ * tensor-bundle files tf.train.Saver writes (edgegan/models/edgegan.py:421,547,635-657); returns the checksum */
+unsigned int eg_crc32c(const void* data, long long n, unsigned int crc);
+
 /* A strided convolution y[N,OH,OW,Co] = conv(x[N,H,W,Ci], w[KH,KW,Ci,Co]) with zero padding pad_t/pad_l before
  * the first row/column (whatever is needed after the last one is implied by OH/OW):
  *   y[n,oh,ow,co] = sum_{r,q,ci} x[n, oh*stride - pad_t + r, ow*stride - pad_l + q, ci] * w[r,q,ci,co]
