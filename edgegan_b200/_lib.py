@@ -51,6 +51,7 @@ SIGNATURES = {
     "eg_bicubic_up2_bwd": [vp, vp, i32, i32, i32, i32, vp],
     "eg_copy2d": [vp, i64, vp, i64, i64, i64, vp],
     "eg_fill": [vp, i64, f32, vp],
+    "eg_u8_lut_f32": [vp, vp, vp, i64, vp],
     "eg_axpby": [vp, vp, i64, f32, f32, vp],
     "eg_gp_interpolate": [vp, vp, vp, vp, i32, i64, vp],
     "eg_gp_seed": [vp, vp, i32, vp],

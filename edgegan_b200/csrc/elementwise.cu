@@ -106,6 +106,25 @@ __global__ void fill_k(float* dst, long long n, float v) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) dst[i] = v;
 }
+// dst[i] = lut[src[i]]: the loader uploads image bytes and the byte -> [-1, 1] table of utils.transform
+// (edgegan/utils/utils.py:160: x / 127.5 - 1); 16 bytes in, 64 bytes out per thread, table in shared memory
+__global__ void u8_lut_f32_k(const uint8_t* __restrict__ src, const float* __restrict__ lut, float* __restrict__ dst, long long n) {
+    __shared__ float tab[256];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) tab[i] = lut[i];
+    __syncthreads();
+    const long long i0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 16;
+    if (i0 >= n) return;
+    if (i0 + 16 <= n && (reinterpret_cast<uintptr_t>(src) & 15u) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15u) == 0) {
+        const uint4 v = *reinterpret_cast<const uint4*>(src + i0);
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            *reinterpret_cast<float4*>(dst + i0 + 4 * k) =
+                make_float4(tab[w[k] & 255u], tab[(w[k] >> 8) & 255u], tab[(w[k] >> 16) & 255u], tab[w[k] >> 24]);
+    } else {
+        for (long long i = i0; i < n && i < i0 + 16; ++i) dst[i] = tab[src[i]];
+    }
+}
 __global__ void axpby_k(const float* __restrict__ x, float* __restrict__ y, long long n, float a, float b) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) y[i] = a * x[i] + (b == 0.f ? 0.f : b * y[i]);
@@ -384,6 +403,11 @@ int eg_copy2d(const float* src, long long src_stride, float* dst, long long dst_
 int eg_fill(float* dst, long long n, float value, void* stream) {
     EG_REQUIRE(dst && n > 0);
     fill_k<<<grid1d(n), TB, 0, ST>>>(dst, n, value);
+    EG_CHECK_LAUNCH(); return 0;
+}
+int eg_u8_lut_f32(const void* src, const float* lut, float* dst, long long n, void* stream) {
+    EG_REQUIRE(src && lut && dst && n > 0);
+    u8_lut_f32_k<<<grid1d((n + 15) / 16), TB, 0, ST>>>(static_cast<const uint8_t*>(src), lut, dst, n);
     EG_CHECK_LAUNCH(); return 0;
 }
 int eg_axpby(const float* x, float* y, long long n, float a, float b, void* stream) {

@@ -197,6 +197,11 @@ class DeviceOps:
     def copy(self, src, dst):
         _lib.check(self.lib.eg_copy2d(_p(src), src.numel(), _p(dst), dst.numel(), 1, src.numel(), self._st), "copy2d")
 
+    def u8_lut(self, src_u8, lut, dst, stream=None):
+        """dst[i] = lut[src[i]] (image bytes -> float with a 256-entry device table); `stream`: torch stream or None"""
+        st = self._st if stream is None else C.c_void_p(stream.cuda_stream)
+        _lib.check(self.lib.eg_u8_lut_f32(_p(src_u8), _p(lut), _p(dst), src_u8.numel(), st), "u8_lut")
+
     def fill(self, dst, value):
         _lib.check(self.lib.eg_fill(_p(dst), dst.numel(), float(value), self._st), "fill")
 

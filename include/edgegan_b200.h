@@ -127,6 +127,9 @@ int eg_bicubic_up2_bwd(const float* gy, float* gx, int N, int H, int W, int C, v
 int eg_copy2d(const float* src, long long src_stride, float* dst, long long dst_stride, long long rows,
               long long cols, void* stream);
 int eg_fill(float* dst, long long n, float value, void* stream);
+/* dst[i] = lut[src[i]] for n bytes (lut: 256 floats in device memory): image bytes -> [-1, 1] on the device with the
+ * table of utils.transform (edgegan/utils/utils.py:160), so the loader uploads 1 byte per value */
+int eg_u8_lut_f32(const void* src, const float* lut, float* dst, long long n, void* stream);
 /* y = a*x + b*y */
 int eg_axpby(const float* x, float* y, long long n, float a, float b, void* stream);
 
