@@ -77,3 +77,33 @@ def update_flags(flags: Flags) -> Flags:
     flags.checkpoint_dir = os.path.join(path, "checkpoints")
     flags.logdir = os.path.join(path, "logs")
     return flags
+
+
+def update_test_flags(flags: Flags) -> Flags:
+    """test.py:83-96 (note: batch size forced to 1; num_classes is left alone)."""
+    if flags.input_width is None:
+        flags.input_width = flags.input_height
+    if flags.output_width is None:
+        flags.output_width = flags.output_height
+    flags.batch_size = 1
+    path = os.path.join(flags.outputsroot, flags.name)
+    flags.checkpoint_dir = os.path.join(path, "checkpoints")
+    flags.logdir = os.path.join(path, "logs")
+    flags.test_output_dir = os.path.join(path, "test_output")
+    return flags
+
+
+def parse_flags(argv=None, description=""):
+    """tf.app.flags-style command line: --name value / --name=value, booleans as --flag / --noflag / --flag=false."""
+    import argparse
+    import dataclasses
+    ap = argparse.ArgumentParser(description=description)
+    for f in dataclasses.fields(Flags):
+        if f.type in ("bool", bool):
+            ap.add_argument("--" + f.name, dest=f.name, nargs="?", const=True, default=f.default,
+                            type=lambda s: str(s).lower() in ("1", "true", "yes"))
+            ap.add_argument("--no" + f.name, dest=f.name, action="store_false")
+        else:
+            typ = {"int": int, "float": float, "str": str}.get(f.type if isinstance(f.type, str) else f.type.__name__, str)
+            ap.add_argument("--" + f.name, type=typ, default=f.default)
+    return Flags(**vars(ap.parse_args(argv)))

@@ -123,6 +123,110 @@ class EdgeGAN(object):
             out.update(st.export(what))
         return out
 
+    # ---- train / test loops (edgegan.py:425-489, 551-633) ----------------------------------------------------------
+    def train(self, max_steps=None, prefetch_workers=None, log=print):
+        """edgegan.py:425-489.  Restores the latest checkpoint if there is one, then per epoch: shuffle, and per batch
+        one `update_model` and the loss line of the reference.  The reference re-evaluates five loss tensors with three
+        extra graph runs after every step (:461-477); here the line is printed from the scalars the step itself
+        produced (`read_losses`, one 64-byte read-back), i.e. each loss is the value its own run minimised.
+        TensorBoard summaries are not written.  `max_steps` bounds the run (tests); `prefetch_workers` > 0 feeds the
+        device through DevicePrefetcher (default: 8 on a GPU operator set, 0 otherwise)."""
+        import time
+        from ..utils.data import DevicePrefetcher
+        cfg, ops = self.config, self.ops
+        if self._built != "train":
+            self.build_train_model()
+        counter = 1
+        start_time = time.time()
+        loaded, checkpoint_counter = self.load(None, cfg.checkpoint_dir)
+        if loaded:
+            counter = checkpoint_counter
+            log(" [*] Load SUCCESS")
+        else:
+            log(" [!] Load failed...")
+        if prefetch_workers is None:
+            prefetch_workers = 8 if getattr(getattr(ops, "device", None), "type", "cpu") == "cuda" else 0
+        steps = 0
+        for epoch in range(cfg.epoch):
+            self.dataset.shuffle()
+            if prefetch_workers > 0:
+                batches = DevicePrefetcher(self.dataset, ops, workers=prefetch_workers)
+            else:
+                batches = ((ops.from_numpy(im), ops.from_numpy(z.astype(np.float32)), f)
+                           for im, z, f in (self.dataset[i] for i in range(len(self.dataset))))
+            for idx, (batch_images, batch_z, _files) in enumerate(batches):
+                self.update_model(batch_images, batch_z)
+                L = self.read_losses()
+                discriminator_err = L["joint_dis_dloss"] + L["image_dis_dloss"] + L["edge_dis_dloss"]
+                generator_err = L["edge_gloss"] + L["image_gloss"]
+                counter += 1
+                steps += 1
+                log("Epoch: [%2d/%2d] [%4d/%4d] time: %4.4f, joint_dis_dloss: %.8f, joint_dis_gloss: %.8f"
+                    % (epoch, cfg.epoch, idx, len(self.dataset), time.time() - start_time,
+                       2 * discriminator_err, generator_err))
+                if np.mod(counter, cfg.save_checkpoint_frequency) == 2:
+                    self.save(None, cfg.checkpoint_dir, counter)
+                if max_steps is not None and steps >= max_steps:
+                    return counter
+        return counter
+
+    def test(self, log=print):
+        """edgegan.py:551-633: restore, then for every test picture E(left half) -> G1, G2 and write the combination
+        chosen by `output_combination` below <test_output_dir>/<dataset>/<path below 'test'>.  Like the reference the
+        edge and the image output come from two separate passes (two draws of the encoder noise).  The reference's
+        'outputL_inputR' branch reads an undefined name; here it is the right half of the input."""
+        import os
+        from ..utils import pathsplit, save_images
+        cfg, ops = self.config, self.ops
+        if self._built is None:
+            self.build_test_model()
+        loaded, _ = self.load(None, cfg.checkpoint_dir)
+        if not loaded:
+            log(" [!] Load failed...")
+            return 0
+        log(" [*] Load SUCCESS")
+        written = 0
+        for idx in range(len(self.dataset)):
+            batch_images, filenames = self.dataset[idx]
+            keep = np.ones(len(filenames), bool)
+            classes = None
+            if self.multiclass:
+                ids = []
+                for k, path in enumerate(filenames):
+                    try:
+                        cid = int(pathsplit(path)[-2])
+                        if cid >= cfg.num_classes:
+                            raise ValueError
+                        ids.append(cid)
+                    except ValueError:
+                        keep[k] = False
+                if not ids:
+                    continue
+                classes = ops.from_numpy(np.asarray(ids, np.float32))
+            x = ops.from_numpy(np.ascontiguousarray(batch_images[keep]))
+            half = int(cfg.output_width / 2)
+            outputL = ops.to_numpy(self.test_forward(x, classes, eps=float(np.random.normal()))[0])
+            outputR = ops.to_numpy(self.test_forward(x, classes, eps=float(np.random.normal()))[1])
+            inputs = batch_images[keep]
+            if cfg.output_combination == "inputL_outputR":
+                results = np.append(inputs[:, :, 0:half, :], outputR, axis=2)
+            elif cfg.output_combination == "outputL_inputR":
+                results = np.append(outputL, inputs[:, :, half:, :], axis=2)
+            elif cfg.output_combination == "outputR":
+                results = outputR
+            else:
+                results = np.append(np.append(inputs, outputL, axis=2), outputR, axis=2)
+            names = [f for f, k in zip(filenames, keep) if k]
+            for fname, img in zip(names, results):
+                parts = pathsplit(fname)
+                name = os.path.join(*parts[parts.index("test") + 1:])
+                out = os.path.join(cfg.test_output_dir, cfg.dataset, name)
+                os.makedirs(os.path.dirname(out), exist_ok=True)
+                save_images(img[np.newaxis, ...], [1, 1], out)
+                written += 1
+            log("Test: [%4d/%4d]" % (idx, len(self.dataset)))
+        return written
+
     # ---- checkpoints (edgegan.py:421,547 tf.train.Saver over all global variables; :635-657 save / load) ---------
     @property
     def model_name(self):
