@@ -343,9 +343,9 @@ conv_tc_kmajor(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
             for (int id = blockIdx.x; id < total_ids; id += gridDim.x) {
                 if (!get_item(P, id, t)) continue;
                 const TcPhase& ph = P.ph[t.pz];
+                int tap = t.it0 / ph.kchunks, kc = t.it0 - tap * ph.kchunks;      // advanced incrementally: the single
+                TcTap tp = ph.taps[tap];                                           // producer thread is latency-critical
                 for (int it = 0; it < t.niter; ++it) {
-                    const int tap = (t.it0 + it) / ph.kchunks, kc = (t.it0 + it) - tap * ph.kchunks;
-                    const TcTap tp = ph.taps[tap];
                     mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
                     const uint32_t sa = smem_base + stage * stage_bytes;
                     const uint32_t fb = smem_u32(&full_bar[stage]);
@@ -354,6 +354,7 @@ conv_tc_kmajor(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
                     tma_load_3d(sa + b_off, &maps.b[0], fb, kc * 32, t.col0, tp.bsel);
                     if (mode == 3) tma_load_3d(sa + b_lo_off, &maps.b[0], fb, kc * 32, t.col0, tp.bsel + P.b_lo_tap_off);
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
+                    if (++kc == ph.kchunks) { kc = 0; ++tap; if (it + 1 < t.niter) tp = ph.taps[tap]; }
                 }
             }
         }
@@ -550,6 +551,8 @@ struct WgParams {
     int BN;                           // column tile
     long long tap_stride, sm, sn;     // dw element = tap*tap_stride + m*sm + n*sn
     int rows_total, cols_total;       // valid rows / columns (channels)
+    int tap_group;                    // taps packed side by side into the column tile (x on the column side, cols <= 64):
+                                      // column c of the tile = tap (group*tap_group + c / cols_total), channel c % cols_total
     int layout_type, sbo;             // UMMA smem descriptor layout type / stride-byte-offset
     int mode;                         // 1 = TF32 rounded, 3 = 3xTF32
     float* out;
@@ -584,9 +587,11 @@ conv_tc_wgrad(const __grid_constant__ TcMaps maps, const __grid_constant__ WgPar
     __shared__ uint32_t tmem_base_slot;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int tap = blockIdx.z % P.ntaps, split = blockIdx.z / P.ntaps;
+    const int G = P.tap_group, ngroups = (P.ntaps + G - 1) / G;
+    const int tap = (blockIdx.z % ngroups) * G, split = blockIdx.z / ngroups;     // first tap of this CTA's group
     const TcTap tp = P.taps[tap];
-    const int row0 = blockIdx.x * 128, col0 = blockIdx.y * BN;
+    const int row0 = blockIdx.x * 128, col0 = G > 1 ? 0 : blockIdx.y * BN;
+    const int slabs_per_tap = G > 1 ? P.cols_total / 32 : BN / 32;
     const int ntiles = P.tiles_w * P.tiles_h * P.tiles_n;
     const int t_beg = split * P.chunks_per_split;
     const int t_end = min(ntiles, t_beg + P.chunks_per_split);
@@ -613,12 +618,19 @@ conv_tc_wgrad(const __grid_constant__ TcMaps maps, const __grid_constant__ WgPar
 
     if (warp == 0) {
         if (elect_one()) {
+            // column slabs (x on the column side): slab j belongs to tap (tap + j / slabs_per_tap); a group past the
+            // last tap re-reads the last one (its columns are masked in the epilogue)
+            int s_amap[4], s_ax[4], s_ay[4], s_ch[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const TcTap tq = P.taps[min(tap + j / slabs_per_tap, P.ntaps - 1)];
+                s_amap[j] = tq.amap; s_ax[j] = tq.ax; s_ay[j] = tq.ay; s_ch[j] = col0 + (j % slabs_per_tap) * 32;
+            }
             int stage = 0; uint32_t phase = 0;
+            int tw = t_beg % P.tiles_w, th = (t_beg / P.tiles_w) % P.tiles_h, tn = t_beg / (P.tiles_w * P.tiles_h);
             for (int it = 0; it < niter; ++it) {
-                int t = t_beg + it;
-                const int tw = t % P.tiles_w; t /= P.tiles_w;
-                const int th = t % P.tiles_h; const int tn = t / P.tiles_h;
                 const int w0 = tw * P.bw, h0 = th * P.bh, n0 = tn * P.bn;
+                if (++tw == P.tiles_w) { tw = 0; if (++th == P.tiles_h) { th = 0; ++tn; } }
                 mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
                 const uint32_t sa = smem_base + stage * stage_bytes, sb = sa + a_bytes;
                 const uint32_t fb = smem_u32(&full_bar[stage]);
@@ -628,9 +640,12 @@ conv_tc_wgrad(const __grid_constant__ TcMaps maps, const __grid_constant__ WgPar
                     if (P.x_is_a) tma_load_4d(sa + i * sub_bytes, &maps.a[tp.amap], fb, row0 + i * 32, w0 + tp.ax, h0 + tp.ay, n0);
                     else          tma_load_4d(sa + i * sub_bytes, &maps.b[0], fb, row0 + i * 32, w0, h0, n0);
                 }
-                for (int j = 0; j < BN / 32; ++j) {
-                    if (P.x_is_a) tma_load_4d(sb + j * sub_bytes, &maps.b[0], fb, col0 + j * 32, w0, h0, n0);
-                    else          tma_load_4d(sb + j * sub_bytes, &maps.a[tp.amap], fb, col0 + j * 32, w0 + tp.ax, h0 + tp.ay, n0);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if (j < BN / 32) {
+                        if (P.x_is_a) tma_load_4d(sb + j * sub_bytes, &maps.b[0], fb, col0 + j * 32, w0, h0, n0);
+                        else          tma_load_4d(sb + j * sub_bytes, &maps.a[s_amap[j]], fb, s_ch[j], w0 + s_ax[j], h0 + s_ay[j], n0);
+                    }
                 }
                 if (++stage == kStages) { stage = 0; phase ^= 1; }
             }
@@ -716,7 +731,7 @@ conv_tc_wgrad(const __grid_constant__ TcMaps maps, const __grid_constant__ WgPar
         }
         const int row = row0 + q * 32 + lane;
         const bool valid = row < P.rows_total;
-        float* obase = P.out + (long long)tap * P.tap_stride + (long long)row * P.sm;
+        float* obase = P.out + (long long)row * P.sm;
         mbar_wait(smem_u32(&tmem_full_bar), 0);
         tc_fence_after();
         for (int c = 0; c < BN; c += 32) {
@@ -724,10 +739,16 @@ conv_tc_wgrad(const __grid_constant__ TcMaps maps, const __grid_constant__ WgPar
             tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, r);
             tmem_ld_wait();
             if (valid) {
+                // 32 consecutive columns never straddle two taps (cols_total is a multiple of 32 when taps are packed)
+                const int tj = G > 1 ? tap + c / P.cols_total : tap;
+                const int cbase = G > 1 ? c % P.cols_total : col0 + c;
+                float* ob = obase + (long long)tj * P.tap_stride;
+                if (tj < P.ntaps) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const int col = col0 + c + j;
-                    if (col < P.cols_total) atomicAdd(obase + (long long)col * P.sn, __uint_as_float(r[j]));
+                    for (int j = 0; j < 32; ++j) {
+                        const int col = cbase + j;
+                        if (col < P.cols_total) atomicAdd(ob + (long long)col * P.sn, __uint_as_float(r[j]));
+                    }
                 }
             }
         }
@@ -1093,12 +1114,18 @@ int eg_tc_conv2d_bwd_weight(const eg_conv_shape* s, const float* x, const float*
     const int rows = P.x_is_a ? s->Ci : s->Co, cols = P.x_is_a ? s->Co : s->Ci;
     P.BN = cols % 128 == 0 ? 128 : (cols % 64 == 0 ? 64 : 32);
     P.rows_total = rows; P.cols_total = cols;
+    // a 64-channel x side: two taps side by side fill the 128-column tile (N = 64 MMAs leave the tensor pipe half
+    // empty and every extra CTA re-conditions the same row operand)
+    P.tap_group = 1;
+    if (!P.x_is_a && cols == 64 && (g_dbg[6] & 1) == 0) { P.tap_group = 2; P.BN = 128; }
     P.tap_stride = (long long)s->Ci * s->Co;
     P.sm = P.x_is_a ? s->Co : 1; P.sn = P.x_is_a ? 1 : s->Co;
     P.tiles_w = s->OW / P.bw; P.tiles_h = s->OH / P.bh; P.tiles_n = eg_ceil_div(s->N, P.bn);
     const int ntiles = P.tiles_w * P.tiles_h * P.tiles_n;
     const int row_tiles = eg_ceil_div(rows, 128);
-    const int base_ctas = row_tiles * (cols / P.BN) * P.ntaps;
+    const int col_tiles = P.tap_group > 1 ? 1 : cols / P.BN;
+    const int tap_groups = eg_ceil_div(P.ntaps, P.tap_group);
+    const int base_ctas = row_tiles * col_tiles * tap_groups;
     int splits = eg_ceil_div(2 * 148, base_ctas);
     if (splits > ntiles) splits = ntiles;
     if (splits < 1) splits = 1;
@@ -1110,7 +1137,7 @@ int eg_tc_conv2d_bwd_weight(const eg_conv_shape* s, const float* x, const float*
         cudaError_t e = cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)P.ntaps * s->Ci * s->Co, st);
         if (e != cudaSuccess) return eg_fail(e, __FILE__, __LINE__);
     }
-    dim3 grid(row_tiles, cols / P.BN, P.ntaps * splits);
+    dim3 grid(row_tiles, col_tiles, tap_groups * splits);
     if (P.mode == 3) {
         const size_t smem = (size_t)kStagesW3 * ((4 + 2 * (P.BN / 32)) * P.pix * 128) + 1024;
         conv_tc_wgrad<kStagesW3, true><<<grid, kThreadsW3, smem, st>>>(maps, P);
