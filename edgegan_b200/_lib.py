@@ -34,6 +34,8 @@ SIGNATURES = {
     "eg_conv2d_fwd": [_csp, vp, vp, vp, vp, i32, vp],
     "eg_conv2d_bwd_data": [_csp, vp, vp, vp, vp, i32, vp],
     "eg_conv2d_bwd_weight": [_csp, vp, vp, vp, i32, i32, vp],
+    "eg_conv2d_fwd_ex": [_csp, vp, vp, vp, vp, i32, i32, vp, i32, vp],
+    "eg_conv2d_bwd_data_ex": [_csp, vp, vp, vp, vp, i32, i32, vp, i32, vp],
     "eg_bias_grad": [vp, i64, i32, vp, i32, vp],
     "eg_instnorm_fwd": [vp, vp, vp, i32, i32, i32, f32, i32, vp],
     "eg_instnorm_bwd": [vp, vp, vp, vp, vp, i32, i32, i32, f32, i32, vp],

@@ -6,15 +6,15 @@
 
 // conv_simt.cu
 int eg_conv_shape_check(const eg_conv_shape* s);
-int eg_simt_conv2d_fwd(const eg_conv_shape* s, const float* x, const float* w, const float* bias, float* y, cudaStream_t st);
-int eg_simt_conv2d_bwd_data(const eg_conv_shape* s, const float* dy, const float* w, const float* bias, float* dx, cudaStream_t st);
+int eg_simt_conv2d_fwd(const eg_conv_shape* s, const float* x, const float* w, const float* bias, float* y, const EgEpi* epi, cudaStream_t st);
+int eg_simt_conv2d_bwd_data(const eg_conv_shape* s, const float* dy, const float* w, const float* bias, float* dx, const EgEpi* epi, cudaStream_t st);
 int eg_simt_conv2d_bwd_weight(const eg_conv_shape* s, const float* x, const float* dy, float* dw, int accumulate, int sm_count, cudaStream_t st);
 // conv_tc.cu
 int eg_tc_supported_fwd(const eg_conv_shape* s);
 int eg_tc_supported_bwd_data(const eg_conv_shape* s);
 int eg_tc_supported_bwd_weight(const eg_conv_shape* s);
-int eg_tc_conv2d_fwd(const eg_conv_shape* s, const float* x, const float* w, const float* bias, float* y, int three_x, cudaStream_t st);
-int eg_tc_conv2d_bwd_data(const eg_conv_shape* s, const float* dy, const float* w, const float* bias, float* dx, int three_x, cudaStream_t st);
+int eg_tc_conv2d_fwd(const eg_conv_shape* s, const float* x, const float* w, const float* bias, float* y, int three_x, cudaStream_t st, const EgEpi* epi);
+int eg_tc_conv2d_bwd_data(const eg_conv_shape* s, const float* dy, const float* w, const float* bias, float* dx, int three_x, cudaStream_t st, const EgEpi* epi);
 int eg_tc_conv2d_bwd_weight(const eg_conv_shape* s, const float* x, const float* dy, float* dw, int accumulate, int three_x, cudaStream_t st);
 
 unsigned long long g_eg_kernel_launches = 0;
@@ -85,22 +85,47 @@ int eg_conv2d_algo_for(const eg_conv_shape* s, int pass, int algo) {
     return resolve(algo, sup);
 }
 
-int eg_conv2d_fwd(const eg_conv_shape* s, const float* x, const float* w, const float* bias, float* y, int algo,
-                  void* stream) {
+// the epilogue as separate in-place passes, for the routes that have no fused one (rc == 1 from the implementation)
+static int run_epilogue(const EgEpi& e, float* out, long long n, void* stream) {
+    if (e.mode == EG_EPI_ACT) return eg_act_fwd(out, out, n, e.act, stream);
+    if (e.mode == EG_EPI_MASK) return eg_act_bwd(e.mask, out, out, n, e.act, stream);
+    return 0;
+}
+
+int eg_conv2d_fwd_ex(const eg_conv_shape* s, const float* x, const float* w, const float* bias, float* y, int epi,
+                     int act, const float* mask_src, int algo, void* stream) {
     if (int r = eg_conv_shape_check(s)) return r;
     EG_REQUIRE(x && w && y);
+    EG_REQUIRE(epi >= EG_EPI_NONE && epi <= EG_EPI_MASK && (epi != EG_EPI_MASK || mask_src));
+    const EgEpi e{epi, act, mask_src};
     const int a = resolve(algo, eg_tc_supported_fwd(s));
-    if (a == EG_ALGO_SIMT) return eg_simt_conv2d_fwd(s, x, w, bias, y, (cudaStream_t)stream);
-    return eg_tc_conv2d_fwd(s, x, w, bias, y, a == EG_ALGO_TC3X, (cudaStream_t)stream);
+    int rc = a == EG_ALGO_SIMT ? eg_simt_conv2d_fwd(s, x, w, bias, y, &e, (cudaStream_t)stream)
+                               : eg_tc_conv2d_fwd(s, x, w, bias, y, a == EG_ALGO_TC3X, (cudaStream_t)stream, &e);
+    if (rc == 1) rc = run_epilogue(e, y, (long long)s->N * s->OH * s->OW * s->Co, stream);
+    return rc;
+}
+
+int eg_conv2d_fwd(const eg_conv_shape* s, const float* x, const float* w, const float* bias, float* y, int algo,
+                  void* stream) {
+    return eg_conv2d_fwd_ex(s, x, w, bias, y, EG_EPI_NONE, 0, nullptr, algo, stream);
+}
+
+int eg_conv2d_bwd_data_ex(const eg_conv_shape* s, const float* dy, const float* w, const float* bias, float* dx, int epi,
+                          int act, const float* mask_src, int algo, void* stream) {
+    if (int r = eg_conv_shape_check(s)) return r;
+    EG_REQUIRE(dy && w && dx);
+    EG_REQUIRE(epi >= EG_EPI_NONE && epi <= EG_EPI_MASK && (epi != EG_EPI_MASK || mask_src));
+    const EgEpi e{epi, act, mask_src};
+    const int a = resolve(algo, eg_tc_supported_bwd_data(s));
+    int rc = a == EG_ALGO_SIMT ? eg_simt_conv2d_bwd_data(s, dy, w, bias, dx, &e, (cudaStream_t)stream)
+                               : eg_tc_conv2d_bwd_data(s, dy, w, bias, dx, a == EG_ALGO_TC3X, (cudaStream_t)stream, &e);
+    if (rc == 1) rc = run_epilogue(e, dx, (long long)s->N * s->H * s->W * s->Ci, stream);
+    return rc;
 }
 
 int eg_conv2d_bwd_data(const eg_conv_shape* s, const float* dy, const float* w, const float* bias, float* dx,
                        int algo, void* stream) {
-    if (int r = eg_conv_shape_check(s)) return r;
-    EG_REQUIRE(dy && w && dx);
-    const int a = resolve(algo, eg_tc_supported_bwd_data(s));
-    if (a == EG_ALGO_SIMT) return eg_simt_conv2d_bwd_data(s, dy, w, bias, dx, (cudaStream_t)stream);
-    return eg_tc_conv2d_bwd_data(s, dy, w, bias, dx, a == EG_ALGO_TC3X, (cudaStream_t)stream);
+    return eg_conv2d_bwd_data_ex(s, dy, w, bias, dx, EG_EPI_NONE, 0, nullptr, algo, stream);
 }
 
 int eg_conv2d_bwd_weight(const eg_conv_shape* s, const float* x, const float* dy, float* dw, int accumulate,

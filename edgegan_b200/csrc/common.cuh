@@ -21,6 +21,9 @@ extern unsigned long long g_eg_kernel_launches;
 int eg_fail(cudaError_t e, const char* file, int line);
 int eg_fail_arg(const char* what, const char* file, int line);
 
+// fused conv epilogue (include/edgegan_b200.h: EG_EPI_*): y = act(v) or y = v * act'(mask[same index])
+struct EgEpi { int mode; int act; const float* mask; };
+
 static inline int eg_ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 __device__ __forceinline__ float warp_sum(float v) {

@@ -12,7 +12,7 @@
 
 namespace {
 
-struct ConvP { int N, H, W, Ci, OH, OW, Co, KH, KW, S, PT, PL; };
+struct ConvP { int N, H, W, Ci, OH, OW, Co, KH, KW, S, PT, PL; int epi, epi_ge; float epi_neg; const float* mask; };
 
 enum { M_FWD = 0, M_DGRAD = 1, M_WGRAD = 2 };
 
@@ -247,6 +247,11 @@ igemm_simt(const float* __restrict__ asrc, const float* __restrict__ bsrc, const
             if (n >= f.N) continue;
             float v = acc[i][j];
             if (MODE != M_WGRAD && bias != nullptr) v += __ldg(bias + n);
+            if (MODE != M_WGRAD && p.epi == EG_EPI_ACT) v = (p.epi_ge ? v >= 0.f : v > 0.f) ? v : p.epi_neg * v;
+            if (MODE != M_WGRAD && p.epi == EG_EPI_MASK) {
+                const float m = __ldg(p.mask + base + n);
+                v *= (p.epi_ge ? m >= 0.f : m > 0.f) ? 1.f : p.epi_neg;
+            }
             if (MODE == M_WGRAD && atomic_out) atomicAdd(dst + base + n, v);
             else dst[base + n] = v;
         }
@@ -358,8 +363,22 @@ int launch_mode(const float* a, const float* b, const float* bias, float* dst, c
 }
 
 ConvP to_p(const eg_conv_shape* s) {
-    ConvP p{s->N, s->H, s->W, s->Ci, s->OH, s->OW, s->Co, s->KH, s->KW, s->stride, s->pad_t, s->pad_l};
+    ConvP p{s->N, s->H, s->W, s->Ci, s->OH, s->OW, s->Co, s->KH, s->KW, s->stride, s->pad_t, s->pad_l, EG_EPI_NONE, 0, 0.f, nullptr};
     return p;
+}
+
+// sign-type activations only (value / derivative = 1 on the positive side, epi_neg on the other); -> 1 when `epi` is of
+// another kind and stays with the caller
+int set_epilogue(ConvP& p, const EgEpi* epi) {
+    if (!epi || epi->mode == EG_EPI_NONE) return 0;
+    switch (epi->act) {
+        case EG_ACT_RELU: p.epi_neg = 0.f; p.epi_ge = 0; break;
+        case EG_ACT_LRELU_BLOCK: p.epi_neg = 0.2f; p.epi_ge = 1; break;
+        case EG_ACT_LRELU: p.epi_neg = 0.2f; p.epi_ge = 0; break;
+        default: return 1;
+    }
+    p.epi = epi->mode; p.mask = epi->mask;
+    return 0;
 }
 
 }  // namespace
@@ -377,18 +396,22 @@ int eg_conv_shape_check(const eg_conv_shape* s) {
 }
 
 int eg_simt_conv2d_fwd(const eg_conv_shape* s, const float* x, const float* w, const float* bias, float* y,
-                       cudaStream_t st) {
+                       const EgEpi* epi, cudaStream_t st) {
     ConvP p = to_p(s);
+    const int unfused = set_epilogue(p, epi);
     Phase f{};
     f.M = p.N * p.OH * p.OW; f.N = p.Co; f.K = p.KH * p.KW * p.Ci;
     const bool va = (p.Ci % 4 == 0) && aligned16(x);
     const bool vb = (p.Co % 4 == 0) && aligned16(w);
-    return launch_mode<M_FWD>(x, w, bias, y, p, f, 1, va, vb, 0, st);
+    if (int r = launch_mode<M_FWD>(x, w, bias, y, p, f, 1, va, vb, 0, st)) return r;
+    return unfused;
 }
 
+// returns 1 (instead of 0) when `epi` was NOT applied (the 3-channel kernel has no fused epilogue): the caller runs it
 int eg_simt_conv2d_bwd_data(const eg_conv_shape* s, const float* dy, const float* w, const float* bias, float* dx,
-                            cudaStream_t st) {
+                            const EgEpi* epi, cudaStream_t st) {
     ConvP p = to_p(s);
+    const int unfused = set_epilogue(p, epi);
     Phase f{};
     const int S = p.S;
     f.M = p.N * ((p.H + S - 1) / S) * ((p.W + S - 1) / S);   // largest parity sub-grid (grid sizing only)
@@ -419,10 +442,11 @@ int eg_simt_conv2d_bwd_data(const eg_conv_shape* s, const float* dy, const float
             dim3 grid(tiles_x * tiles_y * p.N, 1, S * S);
             dgrad_thin_k<<<grid, kThinTH * kThinTW, smem, st>>>(dy, bias, dx, p, tiles_x, tiles_y);
             EG_CHECK_LAUNCH();
-            return 0;
+            return (epi && epi->mode != EG_EPI_NONE) ? 1 : 0;
         }
     }
-    return launch_mode<M_DGRAD>(dy, w, bias, dx, p, f, S * S, v, v, 0, st);
+    if (int r = launch_mode<M_DGRAD>(dy, w, bias, dx, p, f, S * S, v, v, 0, st)) return r;
+    return unfused;
 }
 
 int eg_simt_conv2d_bwd_weight(const eg_conv_shape* s, const float* x, const float* dy, float* dw, int accumulate,

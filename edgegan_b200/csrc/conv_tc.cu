@@ -245,6 +245,10 @@ struct TcParams {
     FastDiv fgx, fgy, fks;
     const float* bias;
     float* out;
+    int epi;              // fused epilogue (EG_EPI_*): out = act(v) / out = v * act'(mask[same offset as out]); only the
+    float epi_neg;        // sign-type activations are fused: value (or derivative) = x (1) on the positive side,
+    int epi_ge;           // epi_neg * x (epi_neg) on the other; epi_ge: zero counts as positive (tf.maximum(x, 0.2x))
+    const float* mask;
 };
 
 // ---------------------------------------------------------------------------------------------------
@@ -516,14 +520,48 @@ conv_tc_kmajor(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
                     __syncwarp();
                     float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (brow != nullptr) bb = __ldg(reinterpret_cast<const float4*>(brow + c));
+                    // mask epilogue: the 8 global loads of this column group are issued back to back, then reduced to one
+                    // sign bit per value (the shared-memory asm below is a compiler barrier: a load per row inside the
+                    // loop would cost 8 DRAM latencies, and 32 live floats across it would spill)
+                    uint32_t pos = 0;
+                    if (P.epi == EG_EPI_MASK) {
+                        const float* mbase = P.mask + (obase - P.out) + c;
+                        float4 mk[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i)
+                            mk[i] = (vmask & (1u << i)) ? __ldg(reinterpret_cast<const float4*>(mbase + loff[i]))
+                                                        : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const float4 m = mk[i];
+                            const bool px = P.epi_ge ? m.x >= 0.f : m.x > 0.f, py = P.epi_ge ? m.y >= 0.f : m.y > 0.f;
+                            const bool pz = P.epi_ge ? m.z >= 0.f : m.z > 0.f, pw = P.epi_ge ? m.w >= 0.f : m.w > 0.f;
+                            pos |= ((uint32_t)px | ((uint32_t)py << 1) | ((uint32_t)pz << 2) | ((uint32_t)pw << 3)) << (4 * i);
+                        }
+                    }
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
                         const int rr = i * 4 + sub;
                         const uint4 u = lds128(stg + (uint32_t)rr * 128u + (uint32_t)((cj ^ (rr & 7)) << 4));
                         if (vmask & (1u << i)) {
                             float* dst = obase + loff[i] + c;
-                            const float4 v = make_float4(__uint_as_float(u.x) + bb.x, __uint_as_float(u.y) + bb.y,
-                                                         __uint_as_float(u.z) + bb.z, __uint_as_float(u.w) + bb.w);
+                            float4 v = make_float4(__uint_as_float(u.x) + bb.x, __uint_as_float(u.y) + bb.y,
+                                                   __uint_as_float(u.z) + bb.z, __uint_as_float(u.w) + bb.w);
+                            if (P.epi == EG_EPI_ACT) {
+                                const float ng = P.epi_neg;
+                                if (P.epi_ge) {
+                                    v.x = v.x >= 0.f ? v.x : ng * v.x; v.y = v.y >= 0.f ? v.y : ng * v.y;
+                                    v.z = v.z >= 0.f ? v.z : ng * v.z; v.w = v.w >= 0.f ? v.w : ng * v.w;
+                                } else {
+                                    v.x = v.x > 0.f ? v.x : ng * v.x; v.y = v.y > 0.f ? v.y : ng * v.y;
+                                    v.z = v.z > 0.f ? v.z : ng * v.z; v.w = v.w > 0.f ? v.w : ng * v.w;
+                                }
+                            } else if (P.epi == EG_EPI_MASK) {
+                                const uint32_t b = pos >> (4 * i);
+                                const float ng = P.epi_neg;
+                                v.x *= (b & 1u) ? 1.f : ng; v.y *= (b & 2u) ? 1.f : ng;
+                                v.z *= (b & 4u) ? 1.f : ng; v.w *= (b & 8u) ? 1.f : ng;
+                            }
                             if (P.ksplit > 1) red_add_v4(dst, v);
                             else *reinterpret_cast<float4*>(dst) = v;
                         }
@@ -981,6 +1019,20 @@ static int pick_ksplit(int ctas, int min_iters) {
 static size_t kmajor_smem(int BN, int mode) {
     return (size_t)kStagesK3 * (128 * 128 + (mode == 3 ? 2 : 1) * BN * 128) + 4 * 4096 + 1024;
 }
+// -> 0: epilogue fused (or none requested); 1: requested but not of the sign type -> the caller applies it afterwards
+static int set_epilogue(TcParams& P, const EgEpi* epi) {
+    P.epi = EG_EPI_NONE; P.epi_neg = 0.f; P.epi_ge = 0; P.mask = nullptr;
+    if (!epi || epi->mode == EG_EPI_NONE) return 0;
+    switch (epi->act) {
+        case EG_ACT_RELU: P.epi_neg = 0.f; P.epi_ge = 0; break;
+        case EG_ACT_LRELU_BLOCK: P.epi_neg = 0.2f; P.epi_ge = 1; break;
+        case EG_ACT_LRELU: P.epi_neg = 0.2f; P.epi_ge = 0; break;
+        default: return 1;
+    }
+    P.epi = epi->mode; P.mask = epi->mask;
+    return 0;
+}
+
 static int launch_kmajor(const TcMaps& maps, TcParams& P, int gx, int gy, int mode, cudaStream_t st) {
     P.grid_x = gx; P.grid_y = gy;
     const int total = gx * gy * P.nphases * P.ksplit;
@@ -996,9 +1048,13 @@ static int launch_kmajor(const TcMaps& maps, TcParams& P, int gx, int gy, int mo
     return 0;
 }
 
+// `epi` (may be NULL): fused epilogue; returns 1 instead of 0 when it was NOT applied (thin route): the caller runs it
 int eg_tc_conv2d_fwd(const eg_conv_shape* s, const float* x, const float* w, const float* bias, float* y, int three_x,
-                     cudaStream_t st) {
-    if (thin_fwd(s)) return eg_thin_conv2d_fwd(s, x, w, bias, y, three_x, st);
+                     cudaStream_t st, const EgEpi* epi) {
+    if (thin_fwd(s)) {
+        if (int r = eg_thin_conv2d_fwd(s, x, w, bias, y, three_x, st)) return r;
+        return (epi && epi->mode != EG_EPI_NONE) ? 1 : 0;
+    }
     if (int r = get_encode()) return r;
     if (int r = set_attrs()) return r;
     const int taps = s->KH * s->KW, mode = three_x ? 3 : 1;
@@ -1022,18 +1078,23 @@ int eg_tc_conv2d_fwd(const eg_conv_shape* s, const float* x, const float* w, con
     ph.tiles_w = s->OW / P.bw; ph.tiles_h = s->OH / P.bh; ph.tiles_n = eg_ceil_div(s->N, P.bn);
     ph.out_off = 0; ph.sw = s->Co; ph.sh = (long long)s->OW * s->Co; ph.sn = (long long)s->OH * s->OW * s->Co;
     P.ksplit = pick_ksplit(ph.tiles_w * ph.tiles_h * ph.tiles_n * (s->Co / P.BN), ph.ntaps * ph.kchunks);
+    const int unfused = set_epilogue(P, epi);
+    if (P.epi == EG_EPI_ACT) P.ksplit = 1;                  // a non-linear epilogue needs the whole sum in one CTA
     if (P.ksplit > 1) {
         cudaError_t e = cudaMemsetAsync(y, 0, sizeof(float) * (size_t)s->N * s->OH * s->OW * s->Co, st);
         if (e != cudaSuccess) return eg_fail(e, __FILE__, __LINE__);
     }
     launch_kmajor(maps, P, ph.tiles_w * ph.tiles_h * ph.tiles_n, s->Co / P.BN, mode, st);
     EG_CHECK_LAUNCH();
-    return 0;
+    return unfused;
 }
 
 int eg_tc_conv2d_bwd_data(const eg_conv_shape* s, const float* dy, const float* w, const float* bias, float* dx,
-                          int three_x, cudaStream_t st) {
-    if (thin_bwd_data(s)) return eg_thin_conv2d_bwd_data(s, dy, w, bias, dx, three_x, st);
+                          int three_x, cudaStream_t st, const EgEpi* epi) {
+    if (thin_bwd_data(s)) {
+        if (int r = eg_thin_conv2d_bwd_data(s, dy, w, bias, dx, three_x, st)) return r;
+        return (epi && epi->mode != EG_EPI_NONE) ? 1 : 0;
+    }
     if (int r = get_encode()) return r;
     if (int r = set_attrs()) return r;
     const int S = s->stride, taps = s->KH * s->KW, mode = three_x ? 3 : 1;
@@ -1079,13 +1140,15 @@ int eg_tc_conv2d_bwd_data(const eg_conv_shape* s, const float* dy, const float* 
     int min_iters = 1 << 30;
     for (int i = 0; i < S * S; ++i) min_iters = P.ph[i].ntaps * P.ph[i].kchunks < min_iters ? P.ph[i].ntaps * P.ph[i].kchunks : min_iters;
     P.ksplit = pick_ksplit(max_tiles * (s->Ci / P.BN) * S * S, min_iters);
+    const int unfused = set_epilogue(P, epi);
+    if (P.epi == EG_EPI_ACT) P.ksplit = 1;
     if (P.ksplit > 1) {
         cudaError_t e = cudaMemsetAsync(dx, 0, sizeof(float) * (size_t)s->N * s->H * s->W * s->Ci, st);
         if (e != cudaSuccess) return eg_fail(e, __FILE__, __LINE__);
     }
     launch_kmajor(maps, P, max_tiles, s->Ci / P.BN, mode, st);
     EG_CHECK_LAUNCH();
-    return 0;
+    return unfused;
 }
 
 int eg_tc_conv2d_bwd_weight(const eg_conv_shape* s, const float* x, const float* dy, float* dw, int accumulate,

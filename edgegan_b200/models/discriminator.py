@@ -51,12 +51,14 @@ class Discriminator(object):
         shp = self._shapes(n)
         a, h, st = [None] * 5, [x] + [None] * 4, [None] * 5
         for l in range(1, 5):
-            a[l] = ops.buf(f"{self.name}/{tag}/a{l}", shp[l])
             h[l] = ops.buf(f"{self.name}/{tag}/h{l}", shp[l])
-            ops.conv_fwd(h[l - 1], self.W[l - 1], None, a[l], 2, 1)
             if l == 1:
-                ops.act_fwd(a[l], h[l], "lrelu")
+                # no norm on the first layer: the activation is the conv's epilogue and a_1 is never stored -- lrelu
+                # keeps the sign, so every later act'(a_1) is taken from h_1
+                ops.conv_fwd(h[0], self.W[0], None, h[1], 2, 1, act="lrelu")
             else:
+                a[l] = ops.buf(f"{self.name}/{tag}/a{l}", shp[l])
+                ops.conv_fwd(h[l - 1], self.W[l - 1], None, a[l], 2, 1)
                 st[l] = ops.buf(f"{self.name}/{tag}/st{l}", (n, shp[l][3], 2))
                 ops.instnorm_fwd(a[l], h[l], st[l], "lrelu")
         d = ops.buf(f"{self.name}/{tag}/d", (n,))
@@ -93,21 +95,25 @@ class Discriminator(object):
         hb = ops.buf(f"{self.name}/{tag}/hb4", h[4].shape)
         ops.rowdot_bwd_input(gd, self.w5, hb)
         for l in range(4, 0, -1):
-            ab = ops.buf(f"{self.name}/{tag}/ab{l}", a[l].shape)
             if l == 1:
-                ops.act_bwd(a[1], hb, ab, "lrelu")
-            elif addends is None:
-                ops.instnorm_bwd(a[l], st[l], hb, None, ab, "lrelu")
+                ab = hb                      # the layer-2 input gradient below already carries act'(a_1)
             else:
-                m = n - addends["n"]
-                if m > 0:
-                    ops.instnorm_bwd(a[l][:m], st[l][:m], hb[:m], None, ab[:m], "lrelu")
-                ops.instnorm_bwd(a[l][m:], st[l][m:], hb[m:], addends[l], ab[m:], "lrelu")
+                ab = ops.buf(f"{self.name}/{tag}/ab{l}", h[l].shape)
+                if addends is None:
+                    ops.instnorm_bwd(a[l], st[l], hb, None, ab, "lrelu")
+                else:
+                    m = n - addends["n"]
+                    if m > 0:
+                        ops.instnorm_bwd(a[l][:m], st[l][:m], hb[:m], None, ab[:m], "lrelu")
+                    ops.instnorm_bwd(a[l][m:], st[l][m:], hb[m:], addends[l], ab[m:], "lrelu")
             if param_grads:
                 ops.conv_bwd_weight(h[l - 1], ab, self.gW[l - 1], 2, 1, accumulate)
             if l > 1 or input_grad:
                 hb = ops.buf(f"{self.name}/{tag}/hb{l - 1}", h[l - 1].shape)
-                ops.conv_bwd_data(ab, self.W[l - 1], None, hb, 2, 1)
+                if l == 2:
+                    ops.conv_bwd_data(ab, self.W[1], None, hb, 2, 1, act="lrelu", mask=h[1])
+                else:
+                    ops.conv_bwd_data(ab, self.W[l - 1], None, hb, 2, 1)
         return hb if input_grad else None
 
     def penalty_sweeps(self, c, weight, inv_global_batch, loss, tag="gp"):
@@ -127,13 +133,16 @@ class Discriminator(object):
         dl_h[4] = ops.buf(f"{nm}/{tag}/dl_h4", h[4].shape)
         ops.rowdot_bwd_input(dd, self.w5, dl_h[4])
         for l in range(4, 0, -1):
-            dl_a[l] = ops.buf(f"{nm}/{tag}/dl_a{l}", a[l].shape)
             if l == 1:
-                ops.act_bwd(a[1], dl_h[1], dl_a[1], "lrelu")
+                dl_a[1] = dl_h[1]            # act'(a_1) was applied by the layer-2 input gradient's epilogue
             else:
+                dl_a[l] = ops.buf(f"{nm}/{tag}/dl_a{l}", h[l].shape)
                 ops.instnorm_bwd(a[l], st[l], dl_h[l], None, dl_a[l], "lrelu")
             dl_h[l - 1] = ops.buf(f"{nm}/{tag}/dl_h{l - 1}", h[l - 1].shape)
-            ops.conv_bwd_data(dl_a[l], self.W[l - 1], None, dl_h[l - 1], 2, 1)
+            if l == 2:
+                ops.conv_bwd_data(dl_a[2], self.W[1], None, dl_h[1], 2, 1, act="lrelu", mask=h[1])
+            else:
+                ops.conv_bwd_data(dl_a[l], self.W[l - 1], None, dl_h[l - 1], 2, 1)
         g = dl_h[0]
         gbar = ops.buf(f"{nm}/{tag}/gbar", g.shape)
         norms = ops.buf(f"{nm}/{tag}/norms", (n,))
@@ -144,13 +153,15 @@ class Discriminator(object):
         for l in range(1, 5):
             # dl_h[l-1] = dgrad(dl_a[l], W_l)  (bilinear)
             ops.conv_bwd_weight(db_h, dl_a[l], self.gW[l - 1], 2, 1, False)
-            db_a = ops.buf(f"{nm}/{tag}/db_a{l}", a[l].shape)
-            ops.conv_fwd(db_h, self.W[l - 1], None, db_a, 2, 1)
-            db_h = ops.buf(f"{nm}/{tag}/db_h{l}", h[l].shape)
             if l == 1:
-                ops.act_bwd(a[1], db_a, db_h, "lrelu")
+                nxt = ops.buf(f"{nm}/{tag}/db_h{l}", h[l].shape)
+                ops.conv_fwd(db_h, self.W[0], None, nxt, 2, 1, act="lrelu", mask=h[1])
+                db_h = nxt
             else:
-                addends[l] = ops.buf(f"{nm}/{tag}/ax{l}", a[l].shape)
+                db_a = ops.buf(f"{nm}/{tag}/db_a{l}", h[l].shape)
+                ops.conv_fwd(db_h, self.W[l - 1], None, db_a, 2, 1)
+                db_h = ops.buf(f"{nm}/{tag}/db_h{l}", h[l].shape)
+                addends[l] = ops.buf(f"{nm}/{tag}/ax{l}", h[l].shape)
                 ops.instnorm_bwd2(a[l], st[l], dl_h[l], db_a, db_h, addends[l], "lrelu")
         # dl_h[4] = dd (x) w5
         ops.rowdot_bwd_weight(dd, db_h, self.gw5, None, False)

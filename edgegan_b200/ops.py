@@ -101,15 +101,29 @@ class DeviceOps:
             self._shape_cache[key] = s
         return s
 
-    def conv_fwd(self, x, w, bias, y, stride, pad, algo=None):
-        """y = conv(x, w) (+bias): x[N,H,W,Ci] w[KH,KW,Ci,Co] y[N,OH,OW,Co]; zero pad `pad` before."""
-        s = self._cs(x.shape, w.shape, y.shape, stride, pad)
-        _lib.check(self.lib.eg_conv2d_fwd(C.byref(s), _p(x), _p(w), _p(bias), _p(y), ALGO[algo or self.pass_algo.get("fwd")], self._st), "conv2d_fwd")
+    @staticmethod
+    def _epi(act, mask):
+        """fused epilogue selector: act alone -> out = act(v); act + mask -> out = v * act'(mask)"""
+        if mask is not None:
+            return 2, ACT[act], _p(mask)
+        if act not in (None, "none"):
+            return 1, ACT[act], None
+        return 0, 0, None
 
-    def conv_bwd_data(self, dy, w, bias, dx, stride, pad, algo=None):
-        """dx = conv input-gradient (== conv2d_transpose forward) (+bias over dx channels)."""
+    def conv_fwd(self, x, w, bias, y, stride, pad, algo=None, act=None, mask=None):
+        """y = conv(x, w) (+bias): x[N,H,W,Ci] w[KH,KW,Ci,Co] y[N,OH,OW,Co]; zero pad `pad` before.
+        act: fused activation; act + mask: y = conv * act'(mask) (mask shaped like y)."""
+        s = self._cs(x.shape, w.shape, y.shape, stride, pad)
+        epi, a, m = self._epi(act, mask)
+        _lib.check(self.lib.eg_conv2d_fwd_ex(C.byref(s), _p(x), _p(w), _p(bias), _p(y), epi, a, m,
+                                             ALGO[algo or self.pass_algo.get("fwd")], self._st), "conv2d_fwd")
+
+    def conv_bwd_data(self, dy, w, bias, dx, stride, pad, algo=None, act=None, mask=None):
+        """dx = conv input-gradient (== conv2d_transpose forward) (+bias over dx channels); act / mask as in conv_fwd."""
         s = self._cs(dx.shape, w.shape, dy.shape, stride, pad)
-        _lib.check(self.lib.eg_conv2d_bwd_data(C.byref(s), _p(dy), _p(w), _p(bias), _p(dx), ALGO[algo or self.pass_algo.get("dgrad")], self._st), "conv2d_bwd_data")
+        epi, a, m = self._epi(act, mask)
+        _lib.check(self.lib.eg_conv2d_bwd_data_ex(C.byref(s), _p(dy), _p(w), _p(bias), _p(dx), epi, a, m,
+                                                  ALGO[algo or self.pass_algo.get("dgrad")], self._st), "conv2d_bwd_data")
 
     def conv_bwd_weight(self, x, dy, dw, stride, pad, accumulate=False, algo=None):
         """dw (+)= filter gradient."""

@@ -75,6 +75,19 @@ int eg_conv2d_fwd(const eg_conv_shape* s, const float* x, const float* w, const 
 /* input gradient of the conv == tf.nn.conv2d_transpose forward (conv.py:49-53); bias[Ci] may be NULL */
 int eg_conv2d_bwd_data(const eg_conv_shape* s, const float* dy, const float* w, const float* bias, float* dx,
                        int algo, void* stream);
+/* The same two with a fused epilogue, for a conv_block without a norm (conv.py:61-67 with norm=None: conv ->
+ * activation_fn) and its backward, which tf.gradients emits as separate elementwise kernels:
+ *   EG_EPI_ACT   out = act(conv + bias)
+ *   EG_EPI_MASK  out = (conv + bias) * act'(mask_src[i])   mask_src shaped like out; for relu / lrelu the derivative
+ *                depends only on the sign, so the post-activation tensor serves as mask_src
+ * (EG_EPI_NONE = the plain calls above). */
+#define EG_EPI_NONE 0
+#define EG_EPI_ACT 1
+#define EG_EPI_MASK 2
+int eg_conv2d_fwd_ex(const eg_conv_shape* s, const float* x, const float* w, const float* bias, float* y, int epi,
+                     int act, const float* mask_src, int algo, void* stream);
+int eg_conv2d_bwd_data_ex(const eg_conv_shape* s, const float* dy, const float* w, const float* bias, float* dx, int epi,
+                          int act, const float* mask_src, int algo, void* stream);
 /* filter gradient dw[KH,KW,Ci,Co] (= or +=) sum_pixels x (x) dy */
 int eg_conv2d_bwd_weight(const eg_conv_shape* s, const float* x, const float* dy, float* dw, int accumulate,
                          int algo, void* stream);

@@ -114,16 +114,22 @@ class RefOps:
         pass
 
     # ---- conv -------------------------------------------------------------------------------------
-    def conv_fwd(self, x, w, bias, y, stride, pad, algo=None):
-        y.copy_(conv_fwd_ref(x, w, bias, (y.shape[1], y.shape[2]), stride, pad))
+    @staticmethod
+    def _epilogue(v, act, mask):
+        if mask is not None:
+            return v * act_grad(act, mask)
+        return act_fwd(act, v)
 
-    def conv_bwd_data(self, dy, w, bias, dx, stride, pad, algo=None):
+    def conv_fwd(self, x, w, bias, y, stride, pad, algo=None, act=None, mask=None):
+        y.copy_(self._epilogue(conv_fwd_ref(x, w, bias, (y.shape[1], y.shape[2]), stride, pad), act, mask))
+
+    def conv_bwd_data(self, dy, w, bias, dx, stride, pad, algo=None, act=None, mask=None):
         xz = torch.zeros(dx.shape, dtype=self.dtype, requires_grad=True)
         y = conv_fwd_ref(xz, w, None, (dy.shape[1], dy.shape[2]), stride, pad)
         (g,) = torch.autograd.grad(y, xz, dy)
         if bias is not None:
             g = g + bias
-        dx.copy_(g)
+        dx.copy_(self._epilogue(g, act, mask))
 
     def conv_bwd_weight(self, x, dy, dw, stride, pad, accumulate=False, algo=None):
         wz = torch.zeros(dw.shape, dtype=self.dtype, requires_grad=True)

@@ -122,3 +122,46 @@ def test_tc_matches_simt_at_full_size(dev):
         getattr(dev, name)(*args, a, 2, 1, "simt")
         getattr(dev, name)(*args, b, 2, 1, "tc3x")
         assert relerr(dev.to_numpy(b), dev.to_numpy(a).astype(np.float64)) < 2e-5, name
+
+
+EPI_CASES = [
+    (3, 16, 32, 3, 64, 4, 2, 1, 8, 16),        # critic first layer: forward with act (FFMA kernel), thin input gradient
+    (4, 32, 64, 64, 128, 4, 2, 1, 16, 32),     # critic second layer: input gradient with the first layer's mask
+    (8, 8, 8, 256, 512, 5, 2, 1, 4, 4),        # split-K launch: act forces a single split, mask works through red.add
+    (2, 9, 9, 3, 64, 3, 1, 1, 9, 9),
+]
+
+
+@pytest.mark.parametrize("algo", ["simt", "tc", "tc3x"])
+@pytest.mark.parametrize("case", EPI_CASES)
+def test_fused_epilogues(dev, ref, case, algo):
+    """eg_conv2d_fwd_ex / eg_conv2d_bwd_data_ex: out = act(conv + bias) and out = (conv + bias) * act'(mask)."""
+    tol = {"simt": 2e-5, "tc": 2e-3, "tc3x": 2e-5}[algo]
+    N, H, W, Ci, Co, k, s, p, OH, OW = case
+    rs = np.random.RandomState(abs(hash(case)) % 2**31)
+    x, w, b = rnd(rs, N, H, W, Ci), rnd(rs, k, k, Ci, Co, scale=0.05), rnd(rs, Co)
+    dy = rnd(rs, N, OH, OW, Co)
+    my, mx = rnd(rs, N, OH, OW, Co), rnd(rs, N, H, W, Ci)
+    for act in ("lrelu", "relu"):
+        want = run(ref, "conv_fwd", [x, w, b], (N, OH, OW, Co), s, p, None, act)
+        got = run(dev, "conv_fwd", [x, w, b], (N, OH, OW, Co), s, p, algo, act)
+        # a value within rounding of zero may take the other branch of the activation: compare where |pre| is clear
+        pre = run(ref, "conv_fwd", [x, w, b], (N, OH, OW, Co), s, p)
+        clear = np.abs(pre) > 10 * tol * np.abs(pre).max()
+        assert relerr(got * clear, want * clear) < tol, ("fwd+act", act, relerr(got * clear, want * clear))
+        ti = [ref.from_numpy(a) for a in (x, w, b)]
+        out = ref.zeros((N, OH, OW, Co))
+        ref.conv_fwd(*ti, out, s, p, None, act, ref.from_numpy(my))
+        want = ref.to_numpy(out)
+        td = [dev.from_numpy(a) for a in (x, w, b)]
+        out = dev.zeros((N, OH, OW, Co))
+        dev.conv_fwd(*td, out, s, p, algo, act, dev.from_numpy(my))
+        assert relerr(dev.to_numpy(out), want) < tol, ("fwd*mask", act)
+        ti = [ref.from_numpy(a) for a in (dy, w)]
+        out = ref.zeros((N, H, W, Ci))
+        ref.conv_bwd_data(ti[0], ti[1], None, out, s, p, None, act, ref.from_numpy(mx))
+        want = ref.to_numpy(out)
+        td = [dev.from_numpy(a) for a in (dy, w)]
+        out = dev.zeros((N, H, W, Ci))
+        dev.conv_bwd_data(td[0], td[1], None, out, s, p, algo, act, dev.from_numpy(mx))
+        assert relerr(dev.to_numpy(out), want) < tol, ("dgrad*mask", act)
