@@ -302,11 +302,11 @@ def main():
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        sb = 32
-        sec = oracle_step_time(sb, multiclass, 1, 0, threads)
+        sb, ssteps = min(B, 64), (4 if not multiclass else 2)     # ~10-20 s of CPU work on 16 cores
+        sec = oracle_step_time(sb, multiclass, ssteps, 1, threads)
         cpu = {"value": sb / sec, "unit": "images/s", "cores": threads, "kind": "port",
-               "sample": f"1 update_model at batch {sb} of the same {mode}-class 64x64 workload "
-                         f"({sec:.1f} s of torch-CPU fp32 oracle, {threads} threads)"}
+               "sample": f"{ssteps} update_model steps (after 1 warm-up) at batch {sb} of the same {mode}-class 64x64 "
+                         f"workload ({sec:.1f} s per step, torch-CPU fp32 oracle, {threads} threads)"}
 
     if rank == 0:
         gimg = B * world
