@@ -19,6 +19,7 @@ class _Context:
         self.rs = np.random.RandomState(seed)
         self.scope = []
         self._uid = 0
+        self._used = {}                     # scope path -> names already opened there (tf default_name uniquification)
 
     def name(self, leaf):
         return "/".join(self.scope + [leaf])
@@ -52,9 +53,20 @@ def variable_context(ops, variables=None, seed=0):
 
 
 @contextlib.contextmanager
-def variable_scope(name, reuse=None):
-    """tf.variable_scope(name): pushes a scope component (reuse is implied by the variable table)."""
+def variable_scope(name, reuse=None, default_name=None):
+    """tf.variable_scope(name_or_None, default_name): pushes a scope component (reuse is implied by the variable
+    table).  With name None the component is `default_name`, made unique inside the current scope the way TensorFlow
+    does it: Conv, Conv_1, Conv_2, ... -- the classifier's layer names come from this rule."""
     ctx = _cur()
+    if name is None:
+        used = ctx._used.setdefault("/".join(ctx.scope), set())
+        name, k = default_name, 0
+        while name in used:
+            k += 1
+            name = f"{default_name}_{k}"
+        used.add(name)
+    else:
+        ctx._used.setdefault("/".join(ctx.scope), set()).add(name)
     ctx.scope.append(name)
     try:
         yield ctx
@@ -217,10 +229,172 @@ def mlp(input, out_dim, name, is_train, reuse, norm=None, activation=None, dtype
 
 
 def mean_pool(input, data_format="NHWC"):
-    """pooling.py:4-8 (2x2 mean).  Device tensors are NHWC; pass the NHWC buffer."""
-    assert data_format == "NHWC", "device tensors are NHWC (the reference's NCHW is an API-only layout)"
+    """pooling.py:4-8 (2x2 mean).  Device tensors are always NHWC: `data_format` is accepted for signature parity (the
+    reference's classifier passes 'NCHW') and does not change the buffer layout."""
+    assert data_format in ("NHWC", "NCHW")
     ctx = _cur()
     n, H, W, C = input.shape
     y = ctx.new((n, H // 2, W // 2, C))
     ctx.ops.add_pool2_fwd(input, None, y)
     return y
+
+
+# ---- classifier ops (activation.py:23-27, conv.py:133-357, linear.py:34-76, normalization.py:38-76) -------------------
+def relu(x):
+    """tf.nn.relu, the default `activation_fn` of conv2d2 / mru_conv."""
+    return activation_fn(x, "relu")
+
+
+def prelu(x, name="prelu"):
+    """activation.py:23-27: tf.maximum(leak * x, x) with a trainable scalar `param` (initial value 0.2)."""
+    ctx = _cur()
+    with variable_scope(name):
+        leak = ctx.get_variable("param", (), "const", value=0.2)
+    y = ctx.new(x.shape)
+    ctx.ops.prelu_fwd(x, leak, y)
+    return y
+
+
+def spectral_normed_weight(W, scope_name):
+    """normalization.py:38-76 with num_iters=1 and an update collection (u is read, never assigned inside the step):
+    W / sigma(W).  `u` [1, Cout] ~ truncated normal(0, 1) lives next to the weights (the reference's doubled scope
+    path is a checkpoint-name detail handled by EdgeGAN._tf_name)."""
+    ctx = _cur()
+    ops = ctx.ops
+    cn = W.shape[-1]
+    k = W.numel() // cn
+    name = "/".join(ctx.scope + ["u"])
+    u = ctx.variables.get(name)
+    if u is None:
+        a = ctx.given[name] if name in ctx.given else VarSpec(name, (1, cn), "trunc_normal", 1.0).sample(ctx.rs)
+        u = ctx.variables[name] = ops.from_numpy(np.asarray(a, np.float32).reshape(1, cn))
+    wbar = ctx.new(W.shape)
+    ws = ctx.new((ops.sn_ws_floats(k, cn),))
+    ops.spectral_norm_fwd(W, u, wbar, ws)
+    return wbar
+
+
+def conv2d2(inputs, num_outputs, kernel_size, sn, stride=1, rate=1, data_format='NCHW', activation_fn=relu,
+            normalizer_fn=None, normalizer_params=None, weights_regularizer=None, weights_initializer=None,
+            biases_initializer=0.0, biases_regularizer=None, reuse=None, scope=None,
+            SPECTRAL_NORM_UPDATE_OPS='spectral_norm_update_ops'):
+    """conv.py:246-295: SAME conv with optionally spectrally normalised weights [k,k,Cin,Cout] + bias [1,Cout,1,1],
+    then `activation_fn` (a function of this module or None).  `weights_initializer`: None = xavier uniform, a float =
+    normal(0, that std); `biases_initializer`: a constant or None (no bias).  Device tensors are NHWC whatever
+    `data_format` says (see mean_pool)."""
+    assert data_format == 'NCHW' and rate == 1 and normalizer_fn is None
+    ctx = _cur()
+    ops = ctx.ops
+    n, H, W_, ci = inputs.shape
+    with variable_scope(scope, reuse, default_name='Conv'):
+        shape = (kernel_size, kernel_size, ci, num_outputs)
+        if weights_initializer is None:         # ly.xavier_initializer(): uniform(+-sqrt(6 / (fan_in + fan_out)))
+            w = ctx.get_variable("weights", shape, "uniform", std=float(np.sqrt(6.0 / (kernel_size * kernel_size * (ci + num_outputs)))))
+        else:
+            w = ctx.get_variable("weights", shape, "normal", std=float(weights_initializer))
+        if sn:
+            w = spectral_normed_weight(w, None)
+        b = None
+        if biases_initializer is not None:
+            b = ctx.get_variable("biases", (1, num_outputs, 1, 1), "const", value=float(biases_initializer)).view(-1)
+        oh, ow = _same_out(H, stride), _same_out(W_, stride)
+        pt = max((oh - 1) * stride + kernel_size - H, 0) // 2
+        pl = max((ow - 1) * stride + kernel_size - W_, 0) // 2
+        y = ctx.new((n, oh, ow, num_outputs))
+        ops.conv_fwd(inputs, w, b, y, stride, (pt, pl))
+        if activation_fn is not None:
+            y = activation_fn(y)
+    return y
+
+
+def fully_connected(inputs, num_outputs, sn, activation_fn=None, normalizer_fn=None, normalizer_params=None,
+                    weights_initializer=None, weight_decay_rate=1e-6, biases_initializer=0.0, biases_regularizer=None,
+                    reuse=None, scope=None, SPECTRAL_NORM_UPDATE_OPS='spectral_norm_update_ops'):
+    """linear.py:34-76: x @ W (spectrally normalised when sn) + bias."""
+    assert normalizer_fn is None
+    ctx = _cur()
+    n, k = inputs.shape
+    with variable_scope(scope, reuse, default_name='fully_connected'):
+        w = ctx.get_variable("weights", (k, num_outputs), "uniform", std=float(np.sqrt(6.0 / (k + num_outputs))))
+        if sn:
+            w = spectral_normed_weight(w, None)
+        b = ctx.get_variable("biases", (num_outputs,), "const", value=float(biases_initializer or 0.0))
+        y = ctx.new((n, num_outputs))
+        ctx.ops.conv_fwd(inputs.view(n, 1, 1, k), w.view(1, 1, k, num_outputs), b, y.view(n, 1, 1, num_outputs), 1, 0)
+        if activation_fn is not None:
+            y = activation_fn(y)
+    return y
+
+
+def _concat_channels(a, b):
+    ctx = _cur()
+    n, H, W_, ca = a.shape
+    cb = b.shape[3]
+    out = ctx.new((n, H, W_, ca + cb))
+    ctx.ops.copy_cslice(a, 0, out, 0, ca)
+    ctx.ops.copy_cslice(b, 0, out, ca, cb)
+    return out
+
+
+def mru_conv_block_v3(inp, ht, filter_depth, sn, stride, dilate=1, activation_fn=relu, normalizer_fn=None,
+                      normalizer_params=None, weights_initializer=None, biases_initializer_mask=0.5,
+                      biases_initializer_h=-1, data_format='NCHW', weight_decay_rate=1e-8, norm_mask=False,
+                      norm_input=True, deconv=False):
+    """conv.py:133-243 (deconv=False): gate = minmax(lrelu(conv(concat(act(ht), inp)))) ; ht' = act(ht + gate *
+    conv(inp)) ; out = [1x1 conv](ht) + conv(act(conv(ht'))) ; 2x2 mean pool when stride == 2."""
+    assert not deconv and dilate == 1 and normalizer_fn is None and stride in (1, 2)
+    ctx = _cur()
+    ops = ctx.ops
+    hidden_depth = ht.shape[3]
+    act = activation_fn if activation_fn is not None else (lambda t: t)
+    with variable_scope('norm_activation_in'):
+        full_inp = _concat_channels(act(ht) if norm_input else ht, inp)
+    rg = conv2d2(full_inp, hidden_depth, 3, sn=sn, stride=1, data_format=data_format, activation_fn=lrelu,
+                 weights_initializer=weights_initializer, biases_initializer=biases_initializer_mask, scope='update_gate')
+    n, H, W_, _ = rg.shape
+    gate, mm = ctx.new(rg.shape), ctx.new((n, hidden_depth, 2))
+    ops.minmax_fwd(rg, gate, mm)
+    img_new = conv2d2(inp, hidden_depth, 3, sn=sn, stride=1, data_format=data_format, activation_fn=None,
+                      weights_initializer=weights_initializer)
+    ht_plus = ctx.new(ht.shape)
+    ops.fma3(ht, gate, img_new, ht_plus)
+    with variable_scope('norm_activation_merge_1'):
+        ht_new_in = act(ht_plus)
+    h_new = conv2d2(ht_new_in, filter_depth, 3, sn=sn, stride=1, data_format=data_format, activation_fn=activation_fn,
+                    weights_initializer=weights_initializer)
+    h_new = conv2d2(h_new, filter_depth, 3, sn=sn, stride=1, data_format=data_format, activation_fn=None,
+                    weights_initializer=weights_initializer)
+    ht_orig = ht
+    if hidden_depth != filter_depth:
+        ht_orig = conv2d2(ht, filter_depth, 1, sn=sn, stride=1, data_format=data_format, activation_fn=None,
+                          weights_initializer=weights_initializer)
+    if stride == 2:
+        out = ctx.new((n, H // 2, W_ // 2, filter_depth))
+        ops.add_pool2_fwd(ht_orig, h_new, out)
+    else:
+        out = ctx.new(h_new.shape)
+        ops.copy(ht_orig, out)
+        ops.axpby(h_new, out, 1.0, 1.0)
+    return out
+
+
+def mru_conv(x, ht, filter_depth, sn, stride=2, dilate_rate=1, num_blocks=5, last_unit=False, activation_fn=relu,
+             normalizer_fn=None, normalizer_params=None, weights_initializer=None, weight_decay_rate=1e-5, unit_num=0,
+             data_format='NCHW'):
+    """conv.py:298-357: `num_blocks` chained MRU cells (the classifier uses 1); `last_unit` appends act() under the
+    scope 'mru_conv_unit_last_norm', which sits outside the unit's scope."""
+    assert len(ht) == num_blocks and dilate_rate == 1
+    hts_new, inp = [], x
+    for i in range(num_blocks):
+        h = ht[i]
+        if i > 0 and stride == 2:
+            h = mean_pool(h, data_format=data_format)
+        with variable_scope('mru_conv_unit_t_%d_layer_%d' % (unit_num, i)):
+            inp = mru_conv_block_v3(inp, h, filter_depth, sn=sn, stride=stride if i == 0 else 1,
+                                    activation_fn=activation_fn, weights_initializer=weights_initializer,
+                                    data_format=data_format, weight_decay_rate=weight_decay_rate)
+        hts_new.append(inp)
+    if last_unit:
+        with variable_scope('mru_conv_unit_last_norm'):
+            hts_new[-1] = activation_fn(hts_new[-1]) if activation_fn is not None else hts_new[-1]
+    return hts_new

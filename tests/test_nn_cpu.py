@@ -71,3 +71,46 @@ def test_residual_and_mlp():
     assert np.abs(y.numpy() - want.numpy()).max() < 1e-10
     assert np.abs(f.numpy() - (want.reshape(2, -1)[:, :64] @ v["fc/w"] + v["fc/b"]).numpy()).max() < 1e-10
     assert np.abs(pooled.numpy() - O.avg_pool_same(want, 2).numpy()).max() < 1e-12
+
+
+def test_classifier_built_from_nn_functions():
+    """models/classifier.py:12-119 assembled from nn.conv2d2 / mru_conv / mean_pool / fully_connected / prelu: the
+    auto-generated scope names (Conv, Conv_1, Conv_2, Conv_3 per unit) and the logits match the oracle."""
+    cfg = O.Config(batch_size=2, output_height=32, output_width=64, multiclasses=True)
+    v, u = O.init_variables(cfg, seed=4)
+    v = {k: a for k, a in v.items() if k.startswith("D2/")}
+    rs = np.random.RandomState(3)
+    x = rs.uniform(-1, 1, (2, 32, 32, 3))
+    ops = RefOps(torch.float64)
+    given = dict(v)
+    given.update(u)
+    with nn.variable_context(ops, variables=given) as ctx:
+        xt = ops.from_numpy(x)
+        x_list = [xt]
+        for _ in range(5):
+            x_list.append(nn.mean_pool(x_list[-1], data_format="NCHW"))
+        x_list = x_list[::-1]
+        act, winit, size = nn.prelu, 0.02, 64
+        with nn.variable_scope("D2"):
+            h0 = nn.conv2d2(x_list[-1], 8, kernel_size=7, sn=True, stride=1, data_format="NCHW", activation_fn=act,
+                            weights_initializer=winit)
+            hts = [h0]
+            for t, mult in enumerate((2, 4, 8, 12), start=1):
+                hts = nn.mru_conv(x_list[-t], hts, size * mult, sn=True, stride=2, dilate_rate=1, data_format="NCHW",
+                                  num_blocks=1, last_unit=(t == 4), activation_fn=act, weights_initializer=winit,
+                                  unit_num=t)
+            img = hts[-1]
+            disc = nn.conv2d2(img, 1, kernel_size=1, sn=True, stride=1, data_format="NCHW", activation_fn=None,
+                              weights_initializer=winit)
+            n, H, W, C = img.shape
+            feat = ops.empty((n, C))
+            ops.globalmean_fwd(img, feat)
+            logits = nn.fully_connected(feat, cfg.num_classes, sn=True, activation_fn=None)
+        names = {k for k in ctx.variables}
+        assert {k for k in names if not k.endswith("/u")} == set(v)
+        assert {k for k in names if k.endswith("/u")} == set(u)
+    vt = {k: torch.tensor(a, dtype=torch.float64) for k, a in v.items()}
+    ut = {k: torch.tensor(a, dtype=torch.float64) for k, a in u.items()}
+    want = O.classifier(vt, ut, "D2", torch.tensor(x).permute(0, 3, 1, 2))
+    assert tuple(disc.shape) == (2, 2, 2, 1)          # 32 -> 2 after the four stride-2 units; the head is unused
+    assert np.abs(logits.numpy() - want.numpy()).max() < 1e-9
