@@ -29,6 +29,7 @@ SIGNATURES = {
     "eg_get_default_algo": [],
     "eg_debug_set": [i32, i32],
     "eg_kernel_launches": [],
+    "eg_filter_cache": [i32],
     "eg_crc32c": [vp, i64, C.c_uint],
     "eg_conv2d_algo_for": [_csp, i32, i32],
     "eg_conv2d_fwd": [_csp, vp, vp, vp, vp, i32, vp],
@@ -85,7 +86,7 @@ SIGNATURES = {
     "eg_onehot_concat": [vp, i32, i32, i32, vp, vp],
     "eg_rmsprop": [vp, vp, vp, i64, f32, f32, f32, vp],
 }
-_RESTYPE = {"eg_last_error": C.c_char_p, "eg_kernel_launches": C.c_longlong, "eg_crc32c": C.c_uint}
+_RESTYPE = {"eg_last_error": C.c_char_p, "eg_kernel_launches": C.c_longlong, "eg_filter_cache": C.c_longlong, "eg_crc32c": C.c_uint}
 
 _lib = None
 

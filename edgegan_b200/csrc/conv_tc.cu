@@ -918,12 +918,38 @@ int pick_bn(int n) { return n % 128 == 0 ? 128 : 64; }
 // wgrad operand layout knobs: {TMA swizzle enum, UMMA layout type, SBO bytes} (tools/tc_probe.py can sweep them)
 int g_dbg[8] = {(int)CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, 1, 512, 0, 64, 2, 0, 0};
 
+// Prepared-filter cache (opt-in, eg_filter_cache): a filter is re-laid-out / split into hi + lo before every launch,
+// 137 times per training step, although the weights only change at the optimizer updates.  With the cache on, each
+// (stream, pointer, size, layout, mode) gets its own buffer and is prepared once per EPOCH; the caller bumps the epoch
+// (eg_filter_cache(2)) whenever filter memory may have changed -- eg_rmsprop does it by itself.  Buffers are allocated
+// at first use (warm-up), never inside a captured region; a captured graph replays exactly the preparations of the
+// step it recorded.
+struct FilterCacheEntry { float* buf = nullptr; size_t bytes = 0; unsigned long long epoch = 0; };
+std::map<std::tuple<cudaStream_t, const float*, size_t, int, int>, FilterCacheEntry> g_fcache;
+int g_fcache_on = 0;
+bool g_fcache_bypass = false;             // conv_thin.cu: its operands live in recycled scratch memory
+unsigned long long g_fepoch = 1, g_fcache_hits = 0;
+
 // prepared filter: returns the base of [hi copy (taps*Ci*Co)][lo copy (3x only)]
 int prep_filter(const eg_conv_shape* s, const float* w, int transpose, int mode, cudaStream_t st, float** out) {
     const int taps = s->KH * s->KW;
     const size_t n = (size_t)taps * s->Ci * s->Co;
     float* buf = nullptr;
-    if (int r = get_scratch(st, sizeof(float) * n * 2, &buf)) return r;
+    if (g_fcache_on && !g_fcache_bypass) {
+        std::lock_guard<std::mutex> lk(g_mu);
+        FilterCacheEntry& e = g_fcache[std::make_tuple(st, w, n, transpose, mode)];
+        if (e.buf != nullptr && e.epoch == g_fepoch) { ++g_fcache_hits; *out = e.buf; return 0; }
+        if (e.bytes < sizeof(float) * n * 2) {
+            if (e.buf) { cudaStreamSynchronize(st); cudaFree(e.buf); e.buf = nullptr; e.bytes = 0; }
+            cudaError_t err = cudaMalloc(&e.buf, sizeof(float) * n * 2);
+            if (err != cudaSuccess) return eg_fail(err, __FILE__, __LINE__);
+            e.bytes = sizeof(float) * n * 2;
+        }
+        e.epoch = g_fepoch;
+        buf = e.buf;
+    } else {
+        if (int r = get_scratch(st, sizeof(float) * n * 2, &buf)) return r;
+    }
     dim3 grid(eg_ceil_div(s->Co, 32), eg_ceil_div(s->Ci, 32), taps), block(32, 8);
     prep_filter_k<<<grid, block, 0, st>>>(w, buf, buf + n, taps, s->Ci, s->Co, transpose, mode);
     EG_CHECK_LAUNCH();
@@ -932,6 +958,17 @@ int prep_filter(const eg_conv_shape* s, const float* w, int transpose, int mode,
 }
 
 }  // namespace
+
+void eg_tc_filter_cache_bypass(bool on) { g_fcache_bypass = on; }
+void eg_tc_filter_epoch_bump() { ++g_fepoch; }
+
+extern "C" long long eg_filter_cache(int op) {
+    if (op == 0) g_fcache_on = 0;
+    else if (op == 1) g_fcache_on = 1;
+    else if (op == 2) ++g_fepoch;
+    else if (op != 3) return -2;
+    return (long long)g_fcache_hits;
+}
 
 extern "C" int eg_debug_set(int key, int value) {
     if (key < 0 || key >= 8) return -2;

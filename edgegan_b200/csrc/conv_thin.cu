@@ -16,6 +16,8 @@
 #include "common.cuh"
 
 int eg_tc_scratch(cudaStream_t st, int slot, size_t bytes, float** out);
+void eg_tc_filter_cache_bypass(bool on);      // the dense products below read operands from recycled scratch memory
+struct NoFilterCache { NoFilterCache() { eg_tc_filter_cache_bypass(true); } ~NoFilterCache() { eg_tc_filter_cache_bypass(false); } };
 int eg_tc_conv2d_fwd(const eg_conv_shape* s, const float* x, const float* w, const float* bias, float* y, int three_x, cudaStream_t st, const EgEpi* epi = nullptr);
 int eg_tc_conv2d_bwd_weight(const eg_conv_shape* s, const float* x, const float* dy, float* dw, int accumulate, int three_x, cudaStream_t st);
 
@@ -253,6 +255,7 @@ int eg_thin_conv2d_fwd(const eg_conv_shape* s, const float* x, const float* w, c
     thin_pad_rows_k<<<eg_ceil_div((long long)p.Kpad * s->Co, 256), 256, 0, st>>>(w, wp, p.K, p.Kpad, s->Co);
     EG_CHECK_LAUNCH();
     const eg_conv_shape g = gemm_shape(P, p.Kpad, s->Co);
+    NoFilterCache guard;
     return eg_tc_conv2d_fwd(&g, A, wp, bias, y, three_x, st);
 }
 
@@ -267,7 +270,10 @@ int eg_thin_conv2d_bwd_data(const eg_conv_shape* s, const float* dy, const float
     thin_transpose_w_k<<<eg_ceil_div((long long)Npad * s->Co, 256), 256, 0, st>>>(w, wt, p.K, Npad, s->Co);
     EG_CHECK_LAUNCH();
     const eg_conv_shape g = gemm_shape(P, s->Co, Npad);
-    if (int r = eg_tc_conv2d_fwd(&g, dy, wt, nullptr, C, three_x, st)) return r;
+    {
+        NoFilterCache guard;
+        if (int r = eg_tc_conv2d_fwd(&g, dy, wt, nullptr, C, three_x, st)) return r;
+    }
     const int threads = s->W >= 256 ? 256 : (s->W + 31) / 32 * 32;
     const size_t smem = sizeof(float) * (size_t)((s->KH + s->stride - 1) / s->stride) * s->OW * s->KW * s->Ci;
     if (s->stride == 1 && smem <= 40 * 1024) thin_col2im_row_k<1><<<s->N * s->H, threads, smem, st>>>(C, bias, dx, p, Npad);

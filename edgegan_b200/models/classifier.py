@@ -101,6 +101,7 @@ class Classifier(object):
         if self._wbar_valid:
             return
         ops = self.ops
+        ops.filter_cache_invalidate()         # the normalised copies below are rewritten in place
         self.wbar, self.ws = {}, {}
         for scope in self.layers:
             W = self.store.var[scope + "/weights"]

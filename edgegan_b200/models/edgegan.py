@@ -102,6 +102,9 @@ class EdgeGAN(object):
             self.stores["D2/aux"] = self.classifier.aux      # unused disc head + frozen spectral-norm vectors
         self.losses = ops.zeros((16,))
         self._built = "train" if train else "test"
+        # filters are re-laid-out once per run instead of once per conv call; every place that writes weights outside
+        # rmsprop (loads, the classifier's normalised copies) invalidates, and so does the start of every run
+        ops.filter_cache(True)
 
     def build_train_model(self):
         self.build_networks(True)
@@ -111,6 +114,7 @@ class EdgeGAN(object):
 
     # ---- variables -------------------------------------------------------------------------------
     def load_variables(self, values, strict=True):
+        self.ops.filter_cache_invalidate()
         for st in self.stores.values():
             sub = {k: v for k, v in values.items() if k in st.offsets}
             st.load(sub, strict=strict)
@@ -471,6 +475,7 @@ class EdgeGAN(object):
             return G1.cache["h"][4], G2.cache["h"][4]
 
         for run in todo:
+            ops.filter_cache_invalidate()
             if run == "d_optim":
                 e, i = fakes()
                 D = self.joint_discriminator

@@ -75,6 +75,7 @@ class DeviceOps:
         if isinstance(src_host, np.ndarray):
             src_host = torch.from_numpy(np.ascontiguousarray(src_host, dtype=np.float32))
         dst.copy_(src_host.reshape(dst.shape), non_blocking=True)
+        self.lib.eg_filter_cache(2)          # the destination may be a filter
 
     def bytes_allocated(self):
         return sum(t.numel() * 4 for t in self._bufs.values())
@@ -210,6 +211,17 @@ class DeviceOps:
 
     def copy(self, src, dst):
         _lib.check(self.lib.eg_copy2d(_p(src), src.numel(), _p(dst), dst.numel(), 1, src.numel(), self._st), "copy2d")
+
+    def filter_cache(self, on=True):
+        """prepared-filter cache of the tensor-core convs (eg_filter_cache): the caller promises to call
+        filter_cache_invalidate() whenever filter memory changes other than through rmsprop()"""
+        self.lib.eg_filter_cache(1 if on else 0)
+
+    def filter_cache_invalidate(self):
+        self.lib.eg_filter_cache(2)
+
+    def filter_cache_hits(self):
+        return int(self.lib.eg_filter_cache(3))
 
     def u8_lut(self, src_u8, lut, dst, stream=None):
         """dst[i] = lut[src[i]] (image bytes -> float with a 256-entry device table); `stream`: torch stream or None"""

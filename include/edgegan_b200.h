@@ -48,6 +48,13 @@ int eg_get_default_algo(void);
 /* development knob (kernel layout experiments from tools/tc_probe.py); not part of the stable surface */
 int eg_debug_set(int key, int value);
 
+/* Prepared-filter cache of the tensor-core conv path (off by default).  op 1 / 0: on / off; op 2: the filter memory
+ * may have changed (eg_rmsprop calls this itself; call it after any other write to a filter, and whenever a filter
+ * buffer is recycled for different weights); op 3: query only.  Returns the number of filter preparations skipped so
+ * far.  With the cache on, a filter is re-laid-out once per (pointer, pass) between two invalidations instead of on
+ * every launch; its buffers are allocated at first use, so run one step before capturing a CUDA graph. */
+long long eg_filter_cache(int op);
+
 /* number of CUDA kernels the library has launched so far in this process (host-side counter, one host thread per
  * rank; launches recorded into a CUDA graph count once, at capture) -- bench.py's gpu_launches */
 long long eg_kernel_launches(void);

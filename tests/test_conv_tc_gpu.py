@@ -165,3 +165,35 @@ def test_fused_epilogues(dev, ref, case, algo):
         out = dev.zeros((N, H, W, Ci))
         dev.conv_bwd_data(td[0], td[1], None, out, s, p, algo, act, dev.from_numpy(mx))
         assert relerr(dev.to_numpy(out), want) < tol, ("dgrad*mask", act)
+
+
+def test_prepared_filter_cache(dev, ref):
+    """eg_filter_cache: a filter is prepared once per (pointer, pass) between invalidations; uploads and rmsprop
+    invalidate; results always reflect the current weights."""
+    rs = np.random.RandomState(5)
+    N, H, W, Ci, Co, k, s, p = 2, 16, 16, 64, 128, 3, 1, 1
+    x, w1, w2 = rnd(rs, N, H, W, Ci), rnd(rs, k, k, Ci, Co, scale=0.05), rnd(rs, k, k, Ci, Co, scale=0.05)
+    xd, wd, y = dev.from_numpy(x), dev.from_numpy(w1), dev.zeros((N, H, W, Co))
+    want1 = run(ref, "conv_fwd", [x, w1, None], (N, H, W, Co), s, p)
+    want2 = run(ref, "conv_fwd", [x, w2, None], (N, H, W, Co), s, p)
+    dev.filter_cache(True)
+    try:
+        dev.filter_cache_invalidate()
+        h0 = dev.filter_cache_hits()
+        for _ in range(3):
+            dev.conv_fwd(xd, wd, None, y, s, p, "tc3x")
+        assert dev.filter_cache_hits() == h0 + 2                         # prepared once, reused twice
+        assert relerr(dev.to_numpy(y), want1) < 2e-5
+        dev.conv_bwd_data(y, wd, None, dev.zeros((N, H, W, Ci)), s, p, "tc3x")
+        assert dev.filter_cache_hits() == h0 + 2                         # the input gradient uses another layout
+        dev.upload(wd, w2)                                               # same pointer, new weights
+        dev.conv_fwd(xd, wd, None, y, s, p, "tc3x")
+        assert dev.filter_cache_hits() == h0 + 2
+        assert relerr(dev.to_numpy(y), want2) < 2e-5
+        g, ms = dev.from_numpy(np.ones_like(w2)), dev.from_numpy(np.ones_like(w2))
+        dev.rmsprop(wd, g, ms, 0.1)                                      # w -= 0.1 * 1 / sqrt(0.9 + 0.1 + 1e-10)
+        dev.conv_fwd(xd, wd, None, y, s, p, "tc3x")
+        want3 = run(ref, "conv_fwd", [x, w2 - np.float32(0.1), None], (N, H, W, Co), s, p)
+        assert relerr(dev.to_numpy(y), want3) < 2e-5
+    finally:
+        dev.filter_cache(False)
