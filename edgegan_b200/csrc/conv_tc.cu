@@ -506,6 +506,7 @@ conv_tc_kmajor(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
             if (P.dbg & 4) vmask = 0;
             float* obase = P.out + ph.out_off + (long long)t.n0 * ph.sn + (long long)t.h0 * ph.sh + (long long)t.w0 * ph.sw + t.col0;
             const float* brow = (P.bias != nullptr && t.split == 0) ? P.bias + t.col0 + cj * 4 : nullptr;
+            const bool plain = vmask == 0xffu && brow == nullptr && P.ksplit == 1 && P.epi == EG_EPI_NONE;
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
                 const int c = g * 32;
@@ -518,52 +519,63 @@ conv_tc_kmajor(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
                         acc[c + 4 * j] = 0.f; acc[c + 4 * j + 1] = 0.f; acc[c + 4 * j + 2] = 0.f; acc[c + 4 * j + 3] = 0.f;
                     }
                     __syncwarp();
-                    float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (brow != nullptr) bb = __ldg(reinterpret_cast<const float4*>(brow + c));
-                    // mask epilogue: the 8 global loads of this column group are issued back to back, then reduced to one
-                    // sign bit per value (the shared-memory asm below is a compiler barrier: a load per row inside the
-                    // loop would cost 8 DRAM latencies, and 32 live floats across it would spill)
-                    uint32_t pos = 0;
-                    if (P.epi == EG_EPI_MASK) {
-                        const float* mbase = P.mask + (obase - P.out) + c;
-                        float4 mk[8];
-#pragma unroll
-                        for (int i = 0; i < 8; ++i)
-                            mk[i] = (vmask & (1u << i)) ? __ldg(reinterpret_cast<const float4*>(mbase + loff[i]))
-                                                        : make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (plain) {
+                        // full tile, no bias / epilogue / split: nothing but the transposed copy (short-K tiles are
+                        // bound by the instruction count of these four warps)
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
-                            const float4 m = mk[i];
-                            const bool px = P.epi_ge ? m.x >= 0.f : m.x > 0.f, py = P.epi_ge ? m.y >= 0.f : m.y > 0.f;
-                            const bool pz = P.epi_ge ? m.z >= 0.f : m.z > 0.f, pw = P.epi_ge ? m.w >= 0.f : m.w > 0.f;
-                            pos |= ((uint32_t)px | ((uint32_t)py << 1) | ((uint32_t)pz << 2) | ((uint32_t)pw << 3)) << (4 * i);
+                            const int rr = i * 4 + sub;
+                            const uint4 u = lds128(stg + (uint32_t)rr * 128u + (uint32_t)((cj ^ (rr & 7)) << 4));
+                            *reinterpret_cast<uint4*>(obase + loff[i] + c) = u;
                         }
-                    }
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const int rr = i * 4 + sub;
-                        const uint4 u = lds128(stg + (uint32_t)rr * 128u + (uint32_t)((cj ^ (rr & 7)) << 4));
-                        if (vmask & (1u << i)) {
-                            float* dst = obase + loff[i] + c;
-                            float4 v = make_float4(__uint_as_float(u.x) + bb.x, __uint_as_float(u.y) + bb.y,
-                                                   __uint_as_float(u.z) + bb.z, __uint_as_float(u.w) + bb.w);
-                            if (P.epi == EG_EPI_ACT) {
-                                const float ng = P.epi_neg;
-                                if (P.epi_ge) {
-                                    v.x = v.x >= 0.f ? v.x : ng * v.x; v.y = v.y >= 0.f ? v.y : ng * v.y;
-                                    v.z = v.z >= 0.f ? v.z : ng * v.z; v.w = v.w >= 0.f ? v.w : ng * v.w;
-                                } else {
-                                    v.x = v.x > 0.f ? v.x : ng * v.x; v.y = v.y > 0.f ? v.y : ng * v.y;
-                                    v.z = v.z > 0.f ? v.z : ng * v.z; v.w = v.w > 0.f ? v.w : ng * v.w;
-                                }
-                            } else if (P.epi == EG_EPI_MASK) {
-                                const uint32_t b = pos >> (4 * i);
-                                const float ng = P.epi_neg;
-                                v.x *= (b & 1u) ? 1.f : ng; v.y *= (b & 2u) ? 1.f : ng;
-                                v.z *= (b & 4u) ? 1.f : ng; v.w *= (b & 8u) ? 1.f : ng;
+                    } else {
+                        float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (brow != nullptr) bb = __ldg(reinterpret_cast<const float4*>(brow + c));
+                        // mask epilogue: the 8 global loads of this column group are issued back to back, then reduced to one
+                        // sign bit per value (the shared-memory asm below is a compiler barrier: a load per row inside the
+                        // loop would cost 8 DRAM latencies, and 32 live floats across it would spill)
+                        uint32_t pos = 0;
+                        if (P.epi == EG_EPI_MASK) {
+                            const float* mbase = P.mask + (obase - P.out) + c;
+                            float4 mk[8];
+    #pragma unroll
+                            for (int i = 0; i < 8; ++i)
+                                mk[i] = (vmask & (1u << i)) ? __ldg(reinterpret_cast<const float4*>(mbase + loff[i]))
+                                                            : make_float4(0.f, 0.f, 0.f, 0.f);
+    #pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                const float4 m = mk[i];
+                                const bool px = P.epi_ge ? m.x >= 0.f : m.x > 0.f, py = P.epi_ge ? m.y >= 0.f : m.y > 0.f;
+                                const bool pz = P.epi_ge ? m.z >= 0.f : m.z > 0.f, pw = P.epi_ge ? m.w >= 0.f : m.w > 0.f;
+                                pos |= ((uint32_t)px | ((uint32_t)py << 1) | ((uint32_t)pz << 2) | ((uint32_t)pw << 3)) << (4 * i);
                             }
-                            if (P.ksplit > 1) red_add_v4(dst, v);
-                            else *reinterpret_cast<float4*>(dst) = v;
+                        }
+    #pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const int rr = i * 4 + sub;
+                            const uint4 u = lds128(stg + (uint32_t)rr * 128u + (uint32_t)((cj ^ (rr & 7)) << 4));
+                            if (vmask & (1u << i)) {
+                                float* dst = obase + loff[i] + c;
+                                float4 v = make_float4(__uint_as_float(u.x) + bb.x, __uint_as_float(u.y) + bb.y,
+                                                       __uint_as_float(u.z) + bb.z, __uint_as_float(u.w) + bb.w);
+                                if (P.epi == EG_EPI_ACT) {
+                                    const float ng = P.epi_neg;
+                                    if (P.epi_ge) {
+                                        v.x = v.x >= 0.f ? v.x : ng * v.x; v.y = v.y >= 0.f ? v.y : ng * v.y;
+                                        v.z = v.z >= 0.f ? v.z : ng * v.z; v.w = v.w >= 0.f ? v.w : ng * v.w;
+                                    } else {
+                                        v.x = v.x > 0.f ? v.x : ng * v.x; v.y = v.y > 0.f ? v.y : ng * v.y;
+                                        v.z = v.z > 0.f ? v.z : ng * v.z; v.w = v.w > 0.f ? v.w : ng * v.w;
+                                    }
+                                } else if (P.epi == EG_EPI_MASK) {
+                                    const uint32_t b = pos >> (4 * i);
+                                    const float ng = P.epi_neg;
+                                    v.x *= (b & 1u) ? 1.f : ng; v.y *= (b & 2u) ? 1.f : ng;
+                                    v.z *= (b & 4u) ? 1.f : ng; v.w *= (b & 8u) ? 1.f : ng;
+                                }
+                                if (P.ksplit > 1) red_add_v4(dst, v);
+                                else *reinterpret_cast<float4*>(dst) = v;
+                            }
                         }
                     }
                     __syncwarp();
