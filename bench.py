@@ -170,6 +170,9 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        sys.exit("bench.py: edgegan_b200 needs a CUDA device (B200, sm_100a); it has no CPU path "
+                 "(`--impl reference` times the CPU restatement of the reference)")
     torch.cuda.set_device(local)
     comm = LocalComm()
     if world > 1:
