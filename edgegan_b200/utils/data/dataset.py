@@ -50,30 +50,34 @@ def extension_match_recursive(root, exts):
 
 
 class Dataset():
+    """Same constructor arguments, attributes (`data`, `size`, `batchsize`, ...) and error messages as the reference."""
+
     def __init__(self, dataroot, name, size, batchsize, config, num_classes=None, phase='train'):
-        assert phase in ['train', 'test', ]
-        self.batchsize = batchsize
-        self.num_classes = num_classes
-        self.config = config
-        self.phase = phase
-        if phase == 'train':
-            if num_classes is not None:
-                self.data = []
-                for i in range(num_classes):
-                    for ext in ['*.png', '*.jpg']:
-                        data_path = os.path.join(dataroot, name, phase, str(i), ext)
-                        self.data.extend(glob(data_path))
-            else:
-                data_path = os.path.join(dataroot, name, phase, '*.png')
-                self.data = glob(data_path)
+        if phase not in ('train', 'test'):
+            raise AssertionError(phase)
+        self.batchsize, self.num_classes, self.config, self.phase = batchsize, num_classes, config, phase
+        base = os.path.join(dataroot, name, phase)
+        if phase == 'test':
+            # every picture below the test directory, in sorted order
+            where = base
+            files = sorted(extension_match_recursive(base, ['*.png', '*.jpg']))
+        elif num_classes is None:
+            # single class: png files directly in the train directory
+            where = os.path.join(base, '*.png')
+            files = glob(where)
         else:
-            data_path = os.path.join(dataroot, name, phase)
-            self.data = sorted(extension_match_recursive(data_path, ['*.png', '*.jpg']))
-        if len(self.data) == 0:
-            raise Exception("[!] No data found in '" + data_path + "'")
-        if len(self.data) < self.batchsize:
+            # one directory per class id 0 .. num_classes-1 (png first, then jpg, class by class)
+            files = []
+            for cls in range(num_classes):
+                for pattern in ('*.png', '*.jpg'):
+                    where = os.path.join(base, str(cls), pattern)
+                    files += glob(where)
+        self.data = files
+        if not files:
+            raise Exception("[!] No data found in '" + where + "'")
+        if len(files) < batchsize:
             raise Exception("[!] Entire dataset size is less than the configured batch_size")
-        self.size = min(len(self.data), size)
+        self.size = min(len(files), size)
 
     def shuffle(self):
         np.random.shuffle(self.data)
