@@ -11,9 +11,14 @@
 //       TMA pixel boxes, consumed as MN-major (channel-contiguous) UMMA operands; split over pixels with a
 //       red.global.add epilogue.
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane) + TMEM owner,
-// warps 2-5 = epilogue (tcgen05.ld 32x32b -> registers -> global).  smem ring of kStages stages with
-// full/empty mbarriers; accumulator hand-off through a tcgen05.commit mbarrier.
+// Forward / input-gradient kernel (conv_tc_kmajor): ONE persistent CTA per SM, 512 threads in warpgroup-aligned roles
+// (setmaxnreg moves registers to the drain warps): warps 0-7 move the A operand into tensor memory (TS-mode MMA; in
+// the 3xTF32 mode as hi + lo), warps 8-11 drain the chunk accumulators into fp32 registers and store finished tiles
+// through a transposing staging tile (optionally with a fused activation / activation-derivative mask), warp 12 is
+// the TMA producer, warp 13 the MMA issuer and TMEM owner.  Filter-gradient kernel (conv_tc_wgrad): one CTA per
+// (row tile, column tile or tap pair, pixel split), 320 threads: warp 0 TMA, warp 1 MMA, warps 2-5 row operand ->
+// TMEM + epilogue, warps 6-9 lo copy of the column operand.  Both use smem rings with full / ready / empty
+// mbarriers; see DESIGN.md section 3.1 for the measurements behind each choice.
 //
 // Replaces tf.nn.conv2d / tf.nn.conv2d_transpose and their gradients
 // (reference nn/modules/conv.py:26,29,49).
