@@ -152,7 +152,13 @@ class EdgeGAN(object):
             prefetch_workers = 8 if getattr(getattr(ops, "device", None), "type", "cpu") == "cuda" else 0
         steps = 0
         for epoch in range(cfg.epoch):
-            self.dataset.shuffle()
+            if self.comm.world_size > 1:
+                # one global permutation per epoch (seed drawn on rank 0), disjoint shards per rank
+                seed = ops.from_numpy(np.asarray([np.random.randint(0, 2 ** 24) if self.comm.rank == 0 else 0], np.float32))
+                self.comm.allreduce(seed)
+                self.dataset.shuffle(int(ops.to_numpy(seed)[0]), self.comm.rank, self.comm.world_size)
+            else:
+                self.dataset.shuffle()
             if prefetch_workers > 0:
                 batches = DevicePrefetcher(self.dataset, ops, workers=prefetch_workers)
             else:

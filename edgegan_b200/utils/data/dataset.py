@@ -77,10 +77,22 @@ class Dataset():
             raise Exception("[!] No data found in '" + where + "'")
         if len(files) < batchsize:
             raise Exception("[!] Entire dataset size is less than the configured batch_size")
+        self._cap = size
         self.size = min(len(files), size)
 
-    def shuffle(self):
-        np.random.shuffle(self.data)
+    def shuffle(self, seed=None, rank=0, world=1):
+        """dataset.py:53-54: shuffle in place with numpy's global generator.  Data-parallel training passes a `seed`
+        shared by all ranks plus (rank, world): every rank then applies the SAME permutation to the full file list and
+        keeps every world-th file, so the ranks see disjoint shards of one global epoch."""
+        if seed is None:
+            np.random.shuffle(self.data)
+            return
+        if not hasattr(self, "_all"):
+            self._all = sorted(self.data)
+        files = list(self._all)
+        np.random.RandomState(seed).shuffle(files)
+        self.data = files[rank::world]
+        self.size = int(min(len(self.data), self._cap / world))      # `train_size` caps the GLOBAL epoch
 
     def __len__(self):
         return self.size // self.batchsize

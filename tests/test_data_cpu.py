@@ -160,6 +160,22 @@ def test_dataset_layout_classes_and_z(tmp_path):
         Dataset(root, "flat", 10, 8, CFG, num_classes=None)
 
 
+def test_rank_shards_are_disjoint_and_cover_the_epoch(tmp_path):
+    rs = np.random.RandomState(6)
+    root = str(tmp_path)
+    _make_tree(root, rs, per_class=6)
+    shards = []
+    for rank in range(3):
+        ds = Dataset(root, "data", 1000, 2, CFG, num_classes=3, phase="train")
+        ds.shuffle(seed=1234, rank=rank, world=3)
+        assert len(ds.data) == 6 and len(ds) == 3
+        shards.append(list(ds.data))
+    flat = [f for s in shards for f in s]
+    assert len(set(flat)) == 18                                                   # disjoint, complete
+    ds.shuffle(seed=99, rank=2, world=3)
+    assert set(ds.data) != set(shards[2]) and len(ds.data) == 6                   # a new epoch reshuffles the FULL list
+
+
 def test_prefetcher_matches_sequential_loader(tmp_path):
     from ref_ops import RefOps
     rs = np.random.RandomState(4)
