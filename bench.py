@@ -389,7 +389,16 @@ def conv_roofline(model, ops, step_fn, algo):
     tc_fl = sum(v[0] for k, v in agg.items() if k[1] == "tc")
     tc_ms = sum(v[1] for k, v in agg.items() if k[1] == "tc")
     all_ms = sum(v[1] for v in agg.values())
-    peak = float(pk.get("bf16_tflops_sustained", pk.get("bf16_tflops", FALLBACK_PEAKS["bf16_tflops_sustained"])))
+    def num(v):                      # plain number, or an object carrying it under "value"
+        if isinstance(v, dict):
+            v = v.get("value")
+        try:
+            return float(v)
+        except (TypeError, ValueError):
+            return None
+    peak = num(pk.get("bf16_tflops_sustained")) or num(pk.get("bf16_tflops")) or FALLBACK_PEAKS["bf16_tflops_sustained"]
+    if peak > 1e5:                   # given in GFLOP/s
+        peak /= 1e3
     # kind::tf32 runs at half the bf16 rate: the peak of the MMA kind actually used
     peak_kind = peak / 2.0
     detail = {f"{k[0]}/{k[1]}": {"launches": v[2], "ms": round(v[1], 3), "tflops": (v[0] / v[1] / 1e9 if v[1] > 0 else None)}
