@@ -133,7 +133,8 @@ class EdgeGAN(object):
         one `update_model` and the loss line of the reference.  The reference re-evaluates five loss tensors with three
         extra graph runs after every step (:461-477); here the line is printed from the scalars the step itself
         produced (`read_losses`, one 64-byte read-back), i.e. each loss is the value its own run minimised.
-        TensorBoard summaries are not written.  `max_steps` bounds the run (tests); `prefetch_workers` > 0 feeds the
+        Scalar summaries go to <logdir>/events.out.tfevents.* under the reference's tags (edgegan_b200/summary.py; image
+        and histogram summaries are not written).  `max_steps` bounds the run (tests); `prefetch_workers` > 0 feeds the
         device through DevicePrefetcher (default: 8 on a GPU operator set, 0 otherwise)."""
         import time
         from ..utils.data import DevicePrefetcher
@@ -150,6 +151,10 @@ class EdgeGAN(object):
             log(" [!] Load failed...")
         if prefetch_workers is None:
             prefetch_workers = 8 if getattr(getattr(ops, "device", None), "type", "cpu") == "cuda" else 0
+        writer = None
+        if cfg.logdir and self.comm.rank == 0:              # edgegan.py:443 nn.SummaryWriter(logdir, graph): scalars only here
+            from ..summary import SummaryWriter
+            writer = SummaryWriter(cfg.logdir)
         steps = 0
         for epoch in range(cfg.epoch):
             if self.comm.world_size > 1:
@@ -169,6 +174,8 @@ class EdgeGAN(object):
                 L = self.read_losses()
                 discriminator_err = L["joint_dis_dloss"] + L["image_dis_dloss"] + L["edge_dis_dloss"]
                 generator_err = L["edge_gloss"] + L["image_gloss"]
+                if writer is not None:
+                    writer.add_losses(L, counter)
                 counter += 1
                 steps += 1
                 log("Epoch: [%2d/%2d] [%4d/%4d] time: %4.4f, joint_dis_dloss: %.8f, joint_dis_gloss: %.8f"
@@ -176,8 +183,14 @@ class EdgeGAN(object):
                        2 * discriminator_err, generator_err))
                 if np.mod(counter, cfg.save_checkpoint_frequency) == 2:
                     self.save(None, cfg.checkpoint_dir, counter)
+                    if writer is not None:
+                        writer.flush()
                 if max_steps is not None and steps >= max_steps:
+                    if writer is not None:
+                        writer.close()
                     return counter
+        if writer is not None:
+            writer.close()
         return counter
 
     def test(self, log=print):

@@ -59,6 +59,11 @@ def test_train_resume_and_test_cli(tmp_path, multiclass):
     # the reference saves when counter % frequency == 2 (edgegan.py:487): with frequency 3 that is counter 2
     st = ck.get_checkpoint_state(os.path.join(out, "checkpoints"))
     assert st is not None and st["model_checkpoint_path"] == "EdgeGAN-Model-2"
+    # scalar summaries of the two steps under the reference's tags
+    from edgegan_b200 import summary as sm
+    logs = os.path.join(out, "logs")
+    ev = sm.read_events(os.path.join(logs, sorted(os.listdir(logs))[0]))
+    assert [e["step"] for e in ev] == [0, 1, 2] and "joint_dis_dloss" in ev[1]["scalars"] and "zl_loss" in ev[2]["scalars"]
     # resume: the counter continues from the checkpoint's step
     counter = train_cli.main(train_args, ops=RefOps(torch.float32), max_steps=1)
     assert counter == 3
