@@ -186,15 +186,24 @@ class Classifier(object):
 
     def __call__(self, x, num_classes=None, labels=None, reuse=False, data_format="NCHW"):
         """Reference signature (classifier.py:12): x NCHW view of an NHWC buffer -> (disc, prob, logits).
-        `disc` (the unused head) is not computed."""
+        `disc` is the 1x1 'discriminator end' head (classifier.py:104-107, [n, h, w, 1] here); nothing in the training
+        step reads it, so only this call computes it."""
         assert data_format == "NCHW"
         xn = x.permute(0, 2, 3, 1)
         if not xn.is_contiguous():
             raise ValueError("pass the NCHW *view* of an NHWC buffer (edgegan.py:28-29 transposes right before the call)")
+        ops, nm = self.ops, self.name
         logits = self.forward(xn, "call")
-        prob = self.ops.buf(f"{self.name}/call/prob", logits.shape)
-        self.ops.act_fwd(logits, prob, "sigmoid")
-        return None, prob, logits
+        prob = ops.buf(f"{nm}/call/prob", logits.shape)
+        ops.act_fwd(logits, prob, "sigmoid")
+        hl = self.cache["hl"]
+        W, u = self.aux.var[f"{nm}/Conv_1/weights"], self.aux.var[f"{nm}/Conv_1/u"]
+        wb = ops.buf(f"{nm}/Conv_1/wbar", W.shape)
+        ws = ops.buf(f"{nm}/Conv_1/sn_ws", (ops.sn_ws_floats(W.numel() // W.shape[-1], W.shape[-1]),))
+        ops.spectral_norm_fwd(W, u, wb, ws)
+        disc = ops.buf(f"{nm}/call/disc", (hl.shape[0], hl.shape[1], hl.shape[2], 1))
+        ops.conv_fwd(hl, wb, self.aux.var[f"{nm}/Conv_1/biases"].view(-1), disc, 1, 0)
+        return disc, prob, logits
 
     # ---- backward ------------------------------------------------------------------------------------
     def _wgrad(self, scope, x, dy, k, tag):

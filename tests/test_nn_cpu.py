@@ -114,3 +114,40 @@ def test_classifier_built_from_nn_functions():
     want = O.classifier(vt, ut, "D2", torch.tensor(x).permute(0, 3, 1, 2))
     assert tuple(disc.shape) == (2, 2, 2, 1)          # 32 -> 2 after the four stride-2 units; the head is unused
     assert np.abs(logits.numpy() - want.numpy()).max() < 1e-9
+
+
+def test_classifier_call_returns_the_reference_triple():
+    """Classifier.__call__ (classifier.py:12-119): (disc, sigmoid(logits), logits); disc and logits equal the network
+    assembled from the nn functions on the same variables."""
+    from edgegan_b200.models.classifier import Classifier, classifier_specs
+    from edgegan_b200.variables import ParamStore
+    cfg = O.Config(batch_size=2, output_height=32, output_width=64, multiclasses=True)
+    v, u = O.init_variables(cfg, seed=6)
+    given = {k: a for k, a in v.items() if k.startswith("D2/")}
+    given.update(u)
+    rs = np.random.RandomState(8)
+    x = rs.uniform(-1, 1, (2, 32, 32, 3))
+    ops = RefOps(torch.float64)
+    store = ParamStore(ops, classifier_specs("D2", cfg.num_classes), np.random.RandomState(0))
+    clf = Classifier("D2", ops=ops, store=store, num_classes=cfg.num_classes)
+    store.load({k: a for k, a in given.items() if k in store.offsets})
+    clf.aux.load({k: a for k, a in given.items() if k in clf.aux.offsets}, strict=True)
+    disc, prob, logits = clf(ops.from_numpy(x).permute(0, 3, 1, 2), cfg.num_classes)
+    with nn.variable_context(ops, variables=given):
+        xt = ops.from_numpy(x)
+        pyr = [xt]
+        for _ in range(3):
+            pyr.append(nn.mean_pool(pyr[-1], data_format="NCHW"))
+        with nn.variable_scope("D2"):
+            hts = [nn.conv2d2(xt, 8, kernel_size=7, sn=True, activation_fn=nn.prelu, weights_initializer=0.02)]
+            for t, mult in enumerate((2, 4, 8, 12), start=1):
+                hts = nn.mru_conv(pyr[t - 1], hts, 64 * mult, sn=True, stride=2, num_blocks=1, last_unit=(t == 4),
+                                  activation_fn=nn.prelu, weights_initializer=0.02, unit_num=t)
+            want_disc = nn.conv2d2(hts[-1], 1, kernel_size=1, sn=True, activation_fn=None, weights_initializer=0.02)
+    assert tuple(disc.shape) == tuple(want_disc.shape) == (2, 2, 2, 1)
+    assert np.abs(disc.numpy() - want_disc.numpy()).max() < 1e-10
+    assert np.abs(prob.numpy() - 1 / (1 + np.exp(-logits.numpy()))).max() < 1e-12
+    vt = {k: torch.tensor(a, dtype=torch.float64) for k, a in v.items() if k.startswith("D2/")}
+    ut = {k: torch.tensor(a, dtype=torch.float64) for k, a in u.items()}
+    want = O.classifier(vt, ut, "D2", torch.tensor(x).permute(0, 3, 1, 2))
+    assert np.abs(logits.numpy() - want.numpy()).max() < 1e-9
