@@ -105,6 +105,7 @@ class EdgeGAN(object):
         # filters are re-laid-out once per run instead of once per conv call; every place that writes weights outside
         # rmsprop (loads, the classifier's normalised copies) invalidates, and so does the start of every run
         ops.filter_cache(True)
+        ops.filter_cache_invalidate()        # the stores above may sit where an earlier model's filters were
 
     def build_train_model(self):
         self.build_networks(True)

@@ -65,6 +65,7 @@ class DeviceOps:
         return t
 
     def from_numpy(self, a):
+        self.lib.eg_filter_cache(2)          # a new tensor may reuse the address of a freed filter (caching allocator)
         return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(self.device)
 
     def to_numpy(self, t):
