@@ -5,10 +5,13 @@
   N > 1:  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
               --master-port P bench.py --gpus N --steps K --warmup W
 
-A "step" is one `EdgeGAN.update_model` (reference edgegan/models/edgegan.py:126-130): the 6 sequential
-RMSProp runs of the single-class model (7 with the classifier) on one synthetic batch.  Workload at N = 1:
-BASELINE.json configs[1] = single-class 64x64 training, batch 64 per GPU; weak scaling for N > 1 (batch 64
-per rank, gradients all-reduced over NCCL, sync-BN sums all-reduced).
+A "step" is one `EdgeGAN.update_model` (reference edgegan/models/edgegan.py:126-130): the 7 sequential
+RMSProp runs of the 14-class model (6 without the classifier) on one synthetic batch.  Default workload =
+BASELINE.json configs[2]: 14-class 64x64 training, batch 128 per GPU (the reference's own default,
+train.py:44-45, and the config the north-star targets are stated on); weak scaling for N > 1, so `--gpus 8`
+IS configs[3] (global batch 1024; gradients all-reduced over NCCL, sync-BN sums all-reduced).  `--config 2`
+= single-class 64x64 batch 64 (configs[1]); `--config 5` = 14-class 128x128 batch 64 per GPU (configs[4], 4 GPUs).
+At N = 1 the default run also times configs[1] as a second leg and reports it under the extra key "config2".
 
 Prints ONE JSON line (rank 0).  `value` = images/s with inputs resident in HBM; `e2e` = images/s through the
 public API with pinned HOST buffers (H2D of images/z/alpha and D2H of the losses inside the timed region).
@@ -27,7 +30,10 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 # algorithmic GFLOP per image per update_model (2*MAC of conv / conv-transpose / linear)
-GFLOP_PER_IMAGE = {"single": 43.49, "multi": 93.76}
+GFLOP_PER_IMAGE = {2: 43.49, 3: 93.76, 5: 295.32}
+# BASELINE.json configs -> (multiclass, per-GPU batch, height, pair width, label)
+CONFIGS = {2: (False, 64, 64, 128, "single-class 64x64"), 3: (True, 128, 64, 128, "14-class 64x64"),
+           5: (True, 64, 128, 256, "14-class 128x128")}
 FALLBACK_PEAKS = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
 
 
@@ -38,8 +44,10 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--algo", default="auto", choices=["auto", "tc", "tc3x", "simt"])
-    ap.add_argument("--batch", type=int, default=64, help="per-GPU batch")
-    ap.add_argument("--multiclass", action="store_true")
+    ap.add_argument("--config", type=int, default=3, choices=[2, 3, 5], help="BASELINE.json config number (1-based)")
+    ap.add_argument("--batch", type=int, default=None, help="per-GPU batch (default: the config's)")
+    ap.add_argument("--multiclass", action="store_true", help="(kept for compatibility) same as --config 3")
+    ap.add_argument("--no-second-leg", action="store_true", help="skip the configs[1] leg of the default N = 1 run")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile-pass", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
@@ -108,13 +116,33 @@ class ClockSampler:
                 "reasons": sorted(reasons)}
 
 
-def oracle_step_time(batch, multiclass, steps, warmup, threads):
+def resolve(args):
+    """-> (config number, multiclass, per-GPU batch, H, pair width, label)"""
+    cfg = 3 if args.multiclass else args.config
+    multiclass, B, H, W, label = CONFIGS[cfg]
+    if args.batch is not None:
+        B = args.batch
+    return cfg, multiclass, B, H, W, label
+
+
+def workload_config(cfg, label, B, world):
+    """`config` of the JSON line: identical in both arms (the reference arm runs on OUR arm's config)."""
+    return {"workload": f"{label} EdgeGAN update_model (G1+G2, 3 critics with WGAN-GP, "
+                        f"{'classifier D2, ' if CONFIGS[cfg][0] else ''}E; BASELINE.json configs[{cfg - 1}]), batch {B}/GPU",
+            "baseline_config": cfg, "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world}",
+            "gflop_per_image": GFLOP_PER_IMAGE[cfg],
+            "l2": "no flush: one step rewrites a multi-GB activation working set (>> 126 MB L2) and the inputs rotate over 4 sets"}
+
+
+def oracle_step_time(batch, multiclass, steps, warmup, threads, H=64, W=128):
     """The reference's CPU path restated (oracle/edgegan_oracle.py, torch-CPU fp32) -- TF 1.14 itself cannot run
     here.  Returns seconds per step (mean of `steps`)."""
     import torch
     from oracle import edgegan_oracle as O
     torch.set_num_threads(threads)
-    cfg = O.Config(batch_size=batch, multiclasses=multiclass)
+    dis = 128
+    cfg = O.Config(batch_size=batch, multiclasses=multiclass, output_height=H, output_width=W,
+                   image_dis_size=dis, edge_dis_size=dis)
     v, u = O.init_variables(cfg, seed=0)
     st = O.OracleState(cfg, v, u)
     ts = []
@@ -129,30 +157,152 @@ def oracle_step_time(batch, multiclass, steps, warmup, threads):
 
 
 def run_reference(args):
-    """--impl reference: the reference's own CPU implementation of the path, all host threads, bounded sample."""
+    """--impl reference: the reference's own CPU implementation of the path (the restated oracle: TF 1.14 cannot be
+    installed), all host threads, SAME config and batch as our arm; each step is one full update_model."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    total = args.steps + args.warmup
-    b = 64
-    while b > 4 and b * total > 640:      # ~3 images/s on 8 cores -> keep the whole run within a few minutes
-        b //= 2
-    mode = "multi" if args.multiclass else "single"
-    sec = oracle_step_time(b, args.multiclass, args.steps, args.warmup, threads)
-    val = b / sec
-    sample = f"{args.steps} steps of one update_model at batch {b} (bounded sample of the batch-{args.batch} workload)"
+    cfg, multiclass, B, H, W, label = resolve(args)
+    # bounded run: the whole arm has to end within a few minutes (driver limit 1800 s).  A batch-128 14-class step
+    # costs ~10 s on 16-32 cores, so long --steps/--warmup requests are served by fewer timed repetitions of the
+    # SAME full-batch step (stated in `sample`); the per-step workload is never shrunk.
+    probe_t0 = time.perf_counter()
+    sec_probe = oracle_step_time(B, multiclass, 1, 0, threads, H, W)          # also the warm-up of the process
+    budget = 600.0 - (time.perf_counter() - probe_t0)
+    steps = max(1, min(args.steps, int(budget / max(sec_probe, 1e-3)) - 1))
+    sec = oracle_step_time(B, multiclass, steps, 1 if steps > 1 else 0, threads, H, W)
+    val = B / sec
+    sample = (f"{steps} full update_model steps at batch {B} of the same {label} workload after warm-up "
+              f"({sec:.1f} s per step, torch-CPU fp32 restatement of the reference, {threads} threads)")
     line = {
         "impl": "reference", "metric": "G+D+GP step images/sec at 64x64", "value": val, "unit": "images/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{mode}-class 64x64 EdgeGAN update_model, batch {b} (CPU sample)",
-                   "note": "restated-reference CPU path (torch-CPU fp32 oracle); TensorFlow 1.14 cannot be installed here"},
+        "config": workload_config(cfg, label, B, max(1, args.gpus)),
+        "timed_steps": steps,
+        "note": "restated-reference CPU path (torch-CPU fp32 oracle); TensorFlow 1.14 cannot be installed here (SURVEY.md D9)",
         "cpu_baseline": {"value": val, "unit": "images/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+class Leg:
+    """One workload (a BASELINE config) built on this rank: model, synthetic inputs, graph; timing helpers."""
+
+    def __init__(self, args, cfg, multiclass, B, H, W, ops, comm, world, rank):
+        import numpy as np
+        import torch
+        from edgegan_b200.config import Flags
+        from edgegan_b200.models.edgegan import EdgeGAN
+        self.args, self.ops, self.comm, self.world, self.rank, self.B = args, ops, comm, world, rank, B
+        flags = Flags(batch_size=B, multiclasses=multiclass, input_height=H, input_width=W, output_height=H,
+                      output_width=W)
+        if not multiclass:
+            flags.num_classes = None
+        self.model = model = EdgeGAN(None, flags, None, ops=ops, comm=comm, seed=1234)
+        model.build_train_model()
+        # synthetic data (SURVEY.md 8d): images ~ U(-1,1), z ~ N(0,1) (+ class id), alpha ~ U(0,1), scalar eps
+        rs = np.random.RandomState(2333 + rank)
+        self.n_sets = n_sets = 4
+        self.host = host = []
+        for _ in range(n_sets):
+            img = torch.from_numpy(rs.uniform(-1, 1, (B, H, W, 3)).astype(np.float32)).pin_memory()
+            z = rs.normal(size=(B, 100)).astype(np.float32)
+            if multiclass:
+                z = np.concatenate([z, rs.randint(0, 14, (B, 1)).astype(np.float32)], 1)
+            z = torch.from_numpy(z).pin_memory()
+            al = torch.from_numpy(rs.uniform(0, 1, (3, B)).astype(np.float32)).pin_memory()
+            host.append((img, z, al, float(rs.normal())))
+        self.dev_sets = [(i.cuda(non_blocking=True), z.cuda(non_blocking=True), a.cuda(non_blocking=True), e)
+                         for i, z, a, e in host]
+        self.d_in = tuple(torch.empty_like(t, device=ops.device) for t in host[0][:3])
+        self.loss_host = torch.empty(16, dtype=torch.float32).pin_memory()
+        self.h2d_bytes = sum(t.numel() * 4 for t in host[0][:3])
+        self.d2h_bytes = self.loss_host.numel() * 4
+        # the step as a CUDA graph over static input buffers (falls back to eager launches if capture is refused)
+        self.graph, self.graph_note = None, "eager launches"
+        self.s_in = tuple(torch.empty_like(t, device=ops.device) for t in host[0][:3])
+        self.s_eps = torch.zeros(1, dtype=torch.float32, device=ops.device)
+        self.eps_host = [torch.tensor([e], dtype=torch.float32).pin_memory() for _, _, _, e in host]
+        self.eps_dev = [t.cuda() for t in self.eps_host]
+        if not args.no_graph and not args.ncu:
+            try:
+                for s, d in zip(self.s_in, self.dev_sets[0][:3]):
+                    s.copy_(d)
+                self.graph = model.capture_step(*self.s_in, self.s_eps)
+                self.graph_note = "CUDA graph replay" + (" (NCCL all-reduces captured)" if world > 1 else "")
+            except Exception as e:          # noqa: BLE001
+                self.graph, self.graph_note = None, f"eager launches (graph capture failed: {type(e).__name__}: {e})"[:200]
+                torch.cuda.synchronize()
+        # kernels per step, counted by one eager step (the graph replays exactly these)
+        l0 = ops.launches
+        model.update_model(*self.dev_sets[0])
+        torch.cuda.synchronize()
+        self.launches_per_step = ops.launches - l0
+
+    def barrier(self):
+        import torch
+        torch.cuda.synchronize()
+        if self.world > 1:
+            self.comm.barrier()
+            torch.cuda.synchronize()
+
+    def step_resident(self, k):
+        i, z, a, e = self.dev_sets[k % self.n_sets]
+        if self.graph is None:
+            self.model.update_model(i, z, a, e)
+        else:                            # inputs already in HBM: device-to-device refill of the static buffers
+            for s, d in zip(self.s_in, (i, z, a)):
+                s.copy_(d, non_blocking=True)
+            self.s_eps.copy_(self.eps_dev[k % self.n_sets], non_blocking=True)
+            self.graph.replay()
+
+    def step_e2e(self, k):
+        import torch
+        i, z, a, e = self.host[k % self.n_sets]
+        if self.graph is None:
+            for d, h in zip(self.d_in, (i, z, a)):
+                d.copy_(h, non_blocking=True)
+            self.model.update_model(*self.d_in, e)
+        else:
+            for s, h in zip(self.s_in, (i, z, a)):
+                s.copy_(h, non_blocking=True)
+            self.s_eps.copy_(self.eps_host[k % self.n_sets], non_blocking=True)
+            self.graph.replay()
+        self.loss_host.copy_(self.model.losses, non_blocking=True)
+        torch.cuda.current_stream().synchronize()          # the user reads the losses every step
+
+    def timed(self, fn, steps, warmup):
+        import torch
+        for k in range(warmup):
+            fn(k)
+        self.barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = self.ops.launches
+        ev0.record()
+        for k in range(steps):
+            fn(warmup + k)
+        ev1.record()
+        self.barrier()
+        ms = ev0.elapsed_time(ev1)
+        launches = self.ops.launches - l0
+        if self.graph is not None:       # replayed launches do not pass through ops.*: count what the graph holds
+            launches = steps * self.launches_per_step
+        if self.world > 1:
+            t = torch.tensor([ms], device=self.ops.device)
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms / steps, launches
+
+    def release(self):
+        import torch
+        self.graph = None
+        self.model = None
+        self.ops._bufs.clear()
+        torch.cuda.empty_cache()
 
 
 def main():
@@ -163,8 +313,7 @@ def main():
     import numpy as np
     import torch
 
-    from edgegan_b200.config import Flags
-    from edgegan_b200.models.edgegan import EdgeGAN, LocalComm
+    from edgegan_b200.models.edgegan import LocalComm
     from edgegan_b200.ops import DeviceOps
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -178,159 +327,77 @@ def main():
     if world > 1:
         from edgegan_b200.comm import TorchDistComm
         comm = TorchDistComm("nccl")
-    B = args.batch
-    multiclass = args.multiclass
-    mode = "multi" if multiclass else "single"
-    flags = Flags(batch_size=B, multiclasses=multiclass)
-    if not multiclass:
-        flags.num_classes = None
+    cfg, multiclass, B, H, W, label = resolve(args)
     ops = DeviceOps(f"cuda:{local}")
     algo = "tc3x" if args.algo == "auto" else args.algo
     ops.set_default_algo(algo)
-    model = EdgeGAN(None, flags, None, ops=ops, comm=comm, seed=1234)
-    model.build_train_model()
+    leg = Leg(args, cfg, multiclass, B, H, W, ops, comm, world, rank)
+    model = leg.model
 
-    # synthetic data: images ~ U(-1,1), z ~ N(0,1) (+ class id), alpha ~ U(0,1), scalar eps
-    rs = np.random.RandomState(2333 + rank)
-    n_sets = 4
-    host = []
-    for _ in range(n_sets):
-        img = torch.from_numpy(rs.uniform(-1, 1, (B, 64, 128, 3)).astype(np.float32)).pin_memory()
-        z = rs.normal(size=(B, 100)).astype(np.float32)
-        if multiclass:
-            z = np.concatenate([z, rs.randint(0, 14, (B, 1)).astype(np.float32)], 1)
-        z = torch.from_numpy(z).pin_memory()
-        al = torch.from_numpy(rs.uniform(0, 1, (3, B)).astype(np.float32)).pin_memory()
-        host.append((img, z, al, float(rs.normal())))
-    dev_sets = [(i.cuda(non_blocking=True), z.cuda(non_blocking=True), a.cuda(non_blocking=True), e) for i, z, a, e in host]
-    d_img, d_z, d_al = (torch.empty_like(t, device=ops.device) for t in host[0][:3])
-    loss_host = torch.empty(16, dtype=torch.float32).pin_memory()
-    h2d_bytes = sum(t.numel() * 4 for t in host[0][:3])
-    d2h_bytes = loss_host.numel() * 4
-
-    # the step as a CUDA graph over static input buffers (falls back to eager launches if capture is refused)
-    graph, graph_note = None, "eager launches"
-    s_img, s_z, s_al = (torch.empty_like(t, device=ops.device) for t in host[0][:3])
-    s_eps = torch.zeros(1, dtype=torch.float32, device=ops.device)
-    eps_host = [torch.tensor([e], dtype=torch.float32).pin_memory() for _, _, _, e in host]
-    eps_dev = [t.cuda() for t in eps_host]
-    if world > 1:
-        graph_note = "eager launches (NCCL all-reduces between the runs are not captured)"
-    elif not args.no_graph and not args.ncu:
-        try:
-            s_img.copy_(dev_sets[0][0]); s_z.copy_(dev_sets[0][1]); s_al.copy_(dev_sets[0][2])
-            graph = model.capture_step(s_img, s_z, s_al, s_eps)
-            graph_note = "CUDA graph replay"
-        except Exception as e:          # noqa: BLE001
-            graph, graph_note = None, f"eager launches (graph capture failed: {type(e).__name__})"
-            torch.cuda.synchronize()
-    launches_per_step = [None]
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            comm.barrier()
-            torch.cuda.synchronize()
-
-    def step_resident(k):
-        i, z, a, e = dev_sets[k % n_sets]
-        if graph is None:
-            model.update_model(i, z, a, e)
-        else:                            # inputs already in HBM: device-to-device refill of the static buffers
-            s_img.copy_(i, non_blocking=True); s_z.copy_(z, non_blocking=True); s_al.copy_(a, non_blocking=True)
-            s_eps.copy_(eps_dev[k % n_sets], non_blocking=True)
-            graph.replay()
-
-    def step_e2e(k):
-        i, z, a, e = host[k % n_sets]
-        if graph is None:
-            d_img.copy_(i, non_blocking=True)
-            d_z.copy_(z, non_blocking=True)
-            d_al.copy_(a, non_blocking=True)
-            model.update_model(d_img, d_z, d_al, e)
-        else:
-            s_img.copy_(i, non_blocking=True); s_z.copy_(z, non_blocking=True); s_al.copy_(a, non_blocking=True)
-            s_eps.copy_(eps_host[k % n_sets], non_blocking=True)
-            graph.replay()
-        loss_host.copy_(model.losses, non_blocking=True)
-        torch.cuda.current_stream().synchronize()          # the user reads the losses every step
-
-    def timed(fn, steps, warmup):
-        for k in range(warmup):
-            fn(k)
-        barrier()
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        l0 = ops.launches
-        ev0.record()
-        for k in range(steps):
-            fn(warmup + k)
-        ev1.record()
-        barrier()
-        ms = ev0.elapsed_time(ev1)
-        launches = ops.launches - l0
-        if graph is not None:            # replayed launches do not pass through ops.*: count what the graph holds
-            launches = steps * launches_per_step[0]
-        if world > 1:
-            t = torch.tensor([ms], device=ops.device)
-            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
-            ms = float(t.item())
-        return ms / steps, launches
-
-    # kernels per step, counted by one eager step (the graph replays exactly these)
-    l0 = ops.launches
-    i0, z0, a0, e0 = dev_sets[0]
-    model.update_model(i0, z0, a0, e0)
-    torch.cuda.synchronize()
-    launches_per_step[0] = ops.launches - l0
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     if args.ncu:
         for k in range(args.warmup + args.steps):
-            step_resident(k)
+            leg.step_resident(k)
         torch.cuda.synchronize()
-        print(json.dumps({"ncu_run": True, "launches_per_step": launches_per_step[0]}))
+        print(json.dumps({"ncu_run": True, "launches_per_step": leg.launches_per_step}))
         return
-    ms_step, launches = timed(step_resident, args.steps, max(args.warmup, 3))
+    warm = max(args.warmup, 3)
+    ms_step, launches = leg.timed(leg.step_resident, args.steps, warm)
     clocks = sampler.stop() if rank == 0 else None
-    ms_e2e, _ = timed(step_e2e, args.steps, 1)
+    ms_e2e, _ = leg.timed(leg.step_e2e, args.steps, 1)
     losses = model.read_losses()
     finite = all(np.isfinite(v) for v in losses.values())
 
     # ---- roofline of the dominant kernel family (the implicit-GEMM conv kernels), timed live with CUDA events
     roof = None
     if not args.no_profile_pass:
-        roof = conv_roofline(model, ops, lambda k: model.update_model(*dev_sets[k % n_sets]), algo)
+        roof = conv_roofline(model, ops, lambda k: model.update_model(*leg.dev_sets[k % leg.n_sets]), algo)
+    ws_gb = ops.bytes_allocated() / 1e9
+    graph_note = leg.graph_note
+    h2d_bytes, d2h_bytes = leg.h2d_bytes, leg.d2h_bytes
+
+    # ---- second leg (default N = 1 run only): BASELINE configs[1], reported under "config2"
+    second = None
+    if world == 1 and cfg == 3 and args.batch is None and not args.no_second_leg:
+        leg.release()
+        mc2, B2, H2, W2, label2 = CONFIGS[2]
+        leg2 = Leg(args, 2, mc2, B2, H2, W2, ops, comm, world, rank)
+        ms2, l2n = leg2.timed(leg2.step_resident, args.steps, warm)
+        ms2e, _ = leg2.timed(leg2.step_e2e, args.steps, 1)
+        second = {"config": workload_config(2, label2, B2, 1), "value": B2 / (ms2 * 1e-3), "unit": "images/s",
+                  "ms_per_step": ms2, "e2e": {"value": B2 / (ms2e * 1e-3), "unit": "images/s", "ms_per_step": ms2e,
+                                              "h2d_bytes_per_step": leg2.h2d_bytes, "d2h_bytes_per_step": leg2.d2h_bytes},
+                  "gpu_launches": l2n, "launch": leg2.graph_note, "step_tflops": B2 * GFLOP_PER_IMAGE[2] / ms2}
+        leg2.release()
 
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        sb, ssteps = min(B, 64), (4 if not multiclass else 2)     # ~10-20 s of CPU work on 16 cores
-        sec = oracle_step_time(sb, multiclass, ssteps, 1, threads)
-        cpu = {"value": sb / sec, "unit": "images/s", "cores": threads, "kind": "port",
-               "sample": f"{ssteps} update_model steps (after 1 warm-up) at batch {sb} of the same {mode}-class 64x64 "
+        sec = oracle_step_time(B, multiclass, 1, 1, threads, H, W)     # ~20-30 s of CPU work on 16 cores
+        cpu = {"value": B / sec, "unit": "images/s", "cores": threads, "kind": "port",
+               "sample": f"1 update_model step (after 1 warm-up step) at batch {B} of the same {label} "
                          f"workload ({sec:.1f} s per step, torch-CPU fp32 oracle, {threads} threads)"}
 
     if rank == 0:
         gimg = B * world
-        ws_gb = ops.bytes_allocated() / 1e9
         line = {
             "metric": "G+D+GP step images/sec at 64x64", "value": gimg / (ms_step * 1e-3), "unit": "images/s",
-            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,
+            "n_gpus": world, "steps": args.steps, "warmup": warm, "ms_per_step": ms_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": {"tc": "tf32", "tc3x": "3xtf32", "simt": "f32"}[algo], "data": "synthetic",
-            "config": {"workload": f"{mode}-class 64x64 EdgeGAN update_model (G1+G2, 3 critics with WGAN-GP, "
-                                   f"{'classifier, ' if multiclass else ''}E), batch {B}/GPU",
-                       "global_batch": gimg, "parallelism": f"dp{world}", "conv_algo": algo, "launch": graph_note,
-                       "l2": f"step working set {ws_gb:.2f} GB >> 126 MB L2 (every activation is rewritten each step); no flush",
-                       "gflop_per_image": GFLOP_PER_IMAGE[mode], "losses_finite": finite},
+            "config": workload_config(cfg, label, B, world),
+            "impl_detail": {"conv_algo": algo, "launch": graph_note, "working_set_gb": round(ws_gb, 2),
+                            "losses_finite": finite},
             "e2e": {"value": gimg / (ms_e2e * 1e-3), "unit": "images/s", "h2d_bytes_per_step": h2d_bytes,
                     "d2h_bytes_per_step": d2h_bytes, "ms_per_step": ms_e2e},
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": roof,
             "cpu_baseline": cpu,
-            "step_tflops": gimg * GFLOP_PER_IMAGE[mode] / ms_step,      # GFLOP / ms = TFLOP/s (whole job)
+            "step_tflops": gimg * GFLOP_PER_IMAGE[cfg] / ms_step,      # GFLOP / ms = TFLOP/s (whole job)
+            "config2": second,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
