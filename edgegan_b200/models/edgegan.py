@@ -268,9 +268,15 @@ class EdgeGAN(object):
         return name
 
     def checkpoint_tensors(self):
-        """Everything the reference's Saver writes: variables, the generators' batch-norm moving statistics (never
-        updated by the reference: its update ops are not run), spectral-norm vectors, and per trained variable the
-        RMSProp slots `<var>/RMSProp` (rms) and `<var>/RMSProp_1` (momentum, dead state at momentum = 0)."""
+        """Everything the reference's Saver writes: variables, the generators' batch-norm moving statistics,
+        spectral-norm vectors, and per trained variable the RMSProp slots `<var>/RMSProp` (rms) and `<var>/RMSProp_1`
+        (momentum, dead state at momentum = 0).
+        The moving statistics are written at their INITIAL values (0 / 1).  The reference does update them in place on
+        every generator forward (`tf.contrib.layers.batch_norm(..., updates_collections=None, is_training=True)`,
+        nn/modules/normalization.py:21-25), so a reference-written checkpoint holds other numbers there; but
+        `is_training` is hard-wired to True, so no graph -- training or test -- ever READS them and the difference
+        cannot reach any output.  (How often the reference updates them depends on how many sess.run calls re-execute
+        the generator per iteration, which this implementation deliberately does not imitate.)"""
         out = {}
         for key, st in self.stores.items():
             var = st.export("var")

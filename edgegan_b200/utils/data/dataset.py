@@ -83,7 +83,10 @@ class Dataset():
     def shuffle(self, seed=None, rank=0, world=1):
         """dataset.py:53-54: shuffle in place with numpy's global generator.  Data-parallel training passes a `seed`
         shared by all ranks plus (rank, world): every rank then applies the SAME permutation to the full file list and
-        keeps every world-th file, so the ranks see disjoint shards of one global epoch."""
+        keeps every world-th file, so the ranks see disjoint shards of one global epoch.  The permuted list is first
+        truncated to a multiple of `world`: all shards have the SAME length, hence every rank runs the same number of
+        batches and issues the same sequence of collectives (a shard one file longer could otherwise mean one more
+        batch -- and one more gradient all-reduce -- on some ranks only)."""
         if seed is None:
             np.random.shuffle(self.data)
             return
@@ -91,8 +94,10 @@ class Dataset():
             self._all = sorted(self.data)
         files = list(self._all)
         np.random.RandomState(seed).shuffle(files)
+        files = files[:(len(files) // world) * world]
         self.data = files[rank::world]
-        self.size = int(min(len(self.data), self._cap / world))      # `train_size` caps the GLOBAL epoch
+        cap = self._cap if self._cap == float("inf") else int(self._cap) // world    # `train_size` caps the GLOBAL epoch
+        self.size = int(min(len(files) // world, cap))
 
     def __len__(self):
         return self.size // self.batchsize
@@ -251,6 +256,14 @@ class DevicePrefetcher:
         last_slot = None
         try:
             while True:
+                if last_slot is not None:
+                    # The consumer is back for the next batch, so all work on the previous one has been enqueued.  Its
+                    # "done" event must be published BEFORE the dequeue below: that dequeue is what lets the producer
+                    # move on to staging a later batch into this very slot, and it only waits on events it can see.
+                    done = torch.cuda.Event()
+                    done.record(torch.cuda.current_stream(self.ops.device))
+                    self._done_ev[last_slot] = done
+                    last_slot = None
                 item = q.get()
                 if item is None:
                     return
@@ -258,12 +271,7 @@ class DevicePrefetcher:
                     raise item
                 staged, ev, filenames, slot = item
                 if ev is not None:
-                    cur = torch.cuda.current_stream(self.ops.device)
-                    if last_slot is not None:            # work on the previous batch has been enqueued by now
-                        done = torch.cuda.Event()
-                        done.record(cur)
-                        self._done_ev[last_slot] = done
-                    cur.wait_event(ev)
+                    torch.cuda.current_stream(self.ops.device).wait_event(ev)
                     last_slot = slot
                 yield (*staged, filenames)
         finally:

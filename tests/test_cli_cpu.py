@@ -79,3 +79,36 @@ def test_train_resume_and_test_cli(tmp_path, multiclass):
     assert im.shape == (32, 64 + 32 + 32, 3) and im.min() == 0 and im.max() == 255
     written = test_cli.main(common + ["--output_combination", "outputR"], ops=RefOps(torch.float32))
     assert np.array(Image.open(os.path.join(tdir, "0", "00.png"))).shape == (32, 32, 3)
+
+
+def test_reference_module_paths_resolve(tmp_path):
+    """`python -m edgegan.train --nomulticlasses ...` / `from edgegan import nn` (reference README.md:80,89,
+    train.py:138, test.py:130): the `edgegan` alias package serves the reference's module paths with the SAME module
+    objects as edgegan_b200 (one variable store, one CUDA library)."""
+    import subprocess
+    import sys
+    import edgegan
+    import edgegan.models.edgegan as a
+    import edgegan.test as cli_test
+    import edgegan.train as cli_train
+    import edgegan_b200.models.edgegan as b
+    from edgegan import models, nn, utils  # noqa: F401
+    from edgegan.models import Discriminator, Generator  # noqa: F401
+    assert a is b and nn.conv2d is __import__("edgegan_b200.nn", fromlist=["conv2d"]).conv2d
+    assert cli_train.main is train_cli.main and cli_test.main is test_cli.main
+    root = str(tmp_path)
+    _tree(root, classes=(0,), n=2)
+    for f in sorted(os.listdir(os.path.join(root, "data", "toy", "train", "0"))):
+        os.replace(os.path.join(root, "data", "toy", "train", "0", f), os.path.join(root, "data", "toy", "train", f))
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "edgegan.train", "--nomulticlasses", "--dataroot", os.path.join(root, "data"), "--dataset", "toy",
+           "--outputsroot", os.path.join(root, "outputs"), "--name", "t", "--input_height", "32", "--input_width", "64",
+           "--output_height", "32", "--output_width", "64", "--image_dis_size", "64", "--edge_dis_size", "64", "--batch_size", "2",
+           "--epoch", "1"]
+    out = subprocess.run(cmd, cwd=repo, capture_output=True, text=True, timeout=600)
+    if torch.cuda.is_available():
+        assert out.returncode == 0, out.stderr[-2000:]
+    else:
+        # flags parsed, outputs dir + flags.json written, dataset built -- then the product refuses to run without a GPU
+        assert out.returncode != 0 and "CUDA device" in out.stderr
+    assert json.load(open(os.path.join(root, "outputs", "t", "flags.json")))["multiclasses"] is False

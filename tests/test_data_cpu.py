@@ -176,6 +176,21 @@ def test_rank_shards_are_disjoint_and_cover_the_epoch(tmp_path):
     assert set(ds.data) != set(shards[2]) and len(ds.data) == 6                   # a new epoch reshuffles the FULL list
 
 
+def test_rank_shards_have_equal_batch_counts_for_awkward_file_counts():
+    """ceil(n / world) a multiple of the batch while n % world != 0 (e.g. 255 files, 2 ranks, batch 64) used to give
+    rank 0 one more batch than the last rank -> mismatched collectives.  All ranks must agree on len(dataset)."""
+    for n, world, batch, cap in ((255, 2, 64, float("inf")), (17, 3, 2, float("inf")), (31, 4, 4, 30), (9, 8, 1, 1000)):
+        lens, sizes = [], []
+        for rank in range(world):
+            ds = Dataset.__new__(Dataset)
+            ds.data = [f"f{i:04d}.png" for i in range(n)]
+            ds.batchsize, ds._cap = batch, cap
+            ds.shuffle(seed=7, rank=rank, world=world)
+            lens.append(len(ds)); sizes.append(len(ds.data))
+        assert len(set(lens)) == 1 and len(set(sizes)) == 1, (n, world, batch, lens, sizes)
+        assert sizes[0] == n // world and lens[0] == int(min(n // world, cap // world if cap != float("inf") else n)) // batch
+
+
 def test_prefetcher_matches_sequential_loader(tmp_path):
     from ref_ops import RefOps
     rs = np.random.RandomState(4)

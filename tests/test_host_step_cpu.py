@@ -99,3 +99,32 @@ def test_full_single_class_step_matches_oracle():
     assert abs(losses["zl_loss"] - st.losses["e_optim"]) < 1e-9 * max(1, abs(st.losses["e_optim"]))
     assert abs(losses["edge_gloss"] - st.losses["g_optim_u/edge_gloss"]) < 1e-9
     assert abs(losses["image_gloss_b"] - st.losses["g_optim_b/image_gloss"]) < 1e-9
+
+
+def test_teacher_forced_checker_on_the_cpu_operator_set():
+    """tests/parity_util.teacher_forced_step (the whole-step checker of the -m gpu tests) exercised without a GPU: the
+    fp64 CPU operator set must pass every run strictly (no tensor through the noise clause), and a deliberately
+    corrupted run must be caught."""
+    from parity_util import teacher_forced_step
+    ocfg, flags = small_cfg(True, 2)
+    v, u = O.init_variables(ocfg, seed=3)
+    inp = O.make_inputs(ocfg, seed=11)
+
+    def build():
+        ops = RefOps(torch.float64)
+        m = EdgeGAN(None, flags, None, ops=ops)
+        m.build_train_model()
+        allv = dict(v)
+        allv.update(u)
+        m.load_variables(allv)
+        return m, ops
+
+    m, ops = build()
+    stats, fails = teacher_forced_step(m, ops, ocfg, v, u, inp, 1e-6, weight_tol=1e-4, sens_samples=0, log=lambda *_: None)
+    assert not fails, fails[:3]
+    assert len(stats) == 7 and all(r["noise_clause"] == 0 for r in stats.values())
+    # corrupt the encoder gradient scale: the loss weight is read by run 6 only
+    m, ops = build()
+    m.config.stage1_zl_loss = 10.5
+    stats, fails = teacher_forced_step(m, ops, ocfg, v, u, inp, 1e-6, weight_tol=1e-4, sens_samples=0, log=lambda *_: None)
+    assert fails and all(f[1] == "e_optim" for f in fails), fails[:3]
