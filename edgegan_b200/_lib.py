@@ -21,6 +21,11 @@ class ConvShape(C.Structure):
 
 _csp = C.POINTER(ConvShape)
 
+
+class FilterDesc(C.Structure):
+    """eg_filter_desc (include/edgegan_b200.h)"""
+    _fields_ = [("w", C.c_void_p), ("taps", C.c_int), ("Ci", C.c_int), ("Co", C.c_int)]
+
 # name -> argtypes ; every function returns int (0 = ok) unless listed in _RESTYPE
 SIGNATURES = {
     "eg_abi_version": [],
@@ -29,7 +34,10 @@ SIGNATURES = {
     "eg_get_default_algo": [],
     "eg_debug_set": [i32, i32],
     "eg_kernel_launches": [],
-    "eg_filter_cache": [i32],
+    "eg_filter_set_create": [vp, i32, i32, C.POINTER(i64)],
+    "eg_filter_set_prepare": [i64, vp],
+    "eg_filter_set_destroy": [i64],
+    "eg_filter_set_hits": [],
     "eg_crc32c": [vp, i64, C.c_uint],
     "eg_conv2d_algo_for": [_csp, i32, i32],
     "eg_conv2d_fwd": [_csp, vp, vp, vp, vp, i32, vp],
@@ -86,7 +94,7 @@ SIGNATURES = {
     "eg_onehot_concat": [vp, i32, i32, i32, vp, vp],
     "eg_rmsprop": [vp, vp, vp, i64, f32, f32, f32, vp],
 }
-_RESTYPE = {"eg_last_error": C.c_char_p, "eg_kernel_launches": C.c_longlong, "eg_filter_cache": C.c_longlong, "eg_crc32c": C.c_uint}
+_RESTYPE = {"eg_last_error": C.c_char_p, "eg_kernel_launches": C.c_longlong, "eg_filter_set_hits": C.c_longlong, "eg_crc32c": C.c_uint}
 
 _lib = None
 

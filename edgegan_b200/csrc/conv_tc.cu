@@ -28,7 +28,6 @@
 #include <cudaTypedefs.h>
 #include <map>
 #include <mutex>
-#include <tuple>
 #include <vector>
 
 namespace {
@@ -935,38 +934,78 @@ int pick_bn(int n) { return n % 128 == 0 ? 128 : 64; }
 // wgrad operand layout knobs: {TMA swizzle enum, UMMA layout type, SBO bytes} (tools/tc_probe.py can sweep them)
 int g_dbg[8] = {(int)CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, 1, 512, 0, 64, 2, 0, 0};
 
-// Prepared-filter cache (opt-in, eg_filter_cache): a filter is re-laid-out / split into hi + lo before every launch,
-// 137 times per training step, although the weights only change at the optimizer updates.  With the cache on, each
-// (stream, pointer, size, layout, mode) gets its own buffer and is prepared once per EPOCH; the caller bumps the epoch
-// (eg_filter_cache(2)) whenever filter memory may have changed -- eg_rmsprop does it by itself.  Buffers are allocated
-// at first use (warm-up), never inside a captured region; a captured graph replays exactly the preparations of the
-// step it recorded.
-struct FilterCacheEntry { float* buf = nullptr; size_t bytes = 0; unsigned long long epoch = 0; };
-std::map<std::tuple<cudaStream_t, const float*, size_t, int, int>, FilterCacheEntry> g_fcache;
-int g_fcache_on = 0;
-bool g_fcache_bypass = false;             // conv_thin.cu: its operands live in recycled scratch memory
-unsigned long long g_fepoch = 1, g_fcache_hits = 0;
+// Prepared-filter sets (eg_filter_set_*): the tensor-core kernels read a re-laid-out / hi+lo-split copy of the filter.
+// Preparing it before every launch cost 221 small kernels per 14-class training step although the weights only change
+// at the optimizer updates.  A set holds, for ALL conv filters of one network, persistent buffers with both prepared
+// forms (forward: [tap][Co][Ci] hi, lo; input gradient: [tap][Ci][Co] hi, lo) and refreshes them with ONE launch
+// (eg_filter_set_prepare) that the owner of the weights enqueues right after it writes them (RMSProp apply, upload,
+// spectral normalisation).  Conv calls find the prepared copy by filter pointer and launch nothing.  Freshness is a
+// stream-order property (writer kernel -> prepare kernel -> conv kernels, eager or replayed from a CUDA graph), not a
+// host-side flag, so a replayed graph cannot leave a stale copy behind.  Filters outside any set are prepared per call.
+struct FilterSetEntry {          // device-side descriptor of one filter
+    const float* w; float* fwd; float* dgr;
+    int taps, A, B;              // filter [taps][A][B]  (A = conv input channels, B = output channels)
+    int tile0, tiles_b, tiles_ab;
+};
+struct ManagedFilter { float* fwd; float* dgr; size_t n; int mode; int set; };
+struct FilterSet { std::vector<const float*> keys; float* buf = nullptr; FilterSetEntry* table = nullptr; int nfilters = 0, tiles = 0, mode = 0; bool live = false; };
+std::map<const float*, ManagedFilter> g_managed;
+std::vector<FilterSet> g_sets;
+unsigned long long g_managed_hits = 0;
+
+__global__ void prep_filter_set_k(const FilterSetEntry* __restrict__ table, int nfilters, int mode) {
+    __shared__ float tile[32][33];
+    __shared__ FilterSetEntry e;
+    if (threadIdx.x == 0 && threadIdx.y == 0) {
+        int lo = 0, hi = nfilters - 1;                       // last filter with tile0 <= blockIdx.x
+        while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (table[mid].tile0 <= (int)blockIdx.x) lo = mid; else hi = mid - 1; }
+        e = table[lo];
+    }
+    __syncthreads();
+    const int local = (int)blockIdx.x - e.tile0;
+    const int tap = local / e.tiles_ab, rem = local - tap * e.tiles_ab;
+    const int a0 = (rem / e.tiles_b) * 32, b0 = (rem % e.tiles_b) * 32;
+    const size_t n = (size_t)e.taps * e.A * e.B, tb = (size_t)tap * e.A * e.B;
+    for (int i = threadIdx.y; i < 32; i += 8) {
+        const int a = a0 + i, b = b0 + threadIdx.x;
+        float v = 0.f;
+        if (a < e.A && b < e.B) {
+            v = e.w[tb + (size_t)a * e.B + b];
+            const uint32_t u = __float_as_uint(v);
+            const size_t o = tb + (size_t)a * e.B + b;
+            if (mode == 3) { e.dgr[o] = v; e.dgr[n + o] = __uint_as_float(tf32_lo(u)); }
+            else e.dgr[o] = __uint_as_float(tf32_rna(u));
+        }
+        tile[i][threadIdx.x] = v;
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += 8) {
+        const int b = b0 + i, a = a0 + threadIdx.x;
+        if (a < e.A && b < e.B) {
+            const float v = tile[threadIdx.x][i];
+            const uint32_t u = __float_as_uint(v);
+            const size_t o = tb + (size_t)b * e.A + a;
+            if (mode == 3) { e.fwd[o] = v; e.fwd[n + o] = __uint_as_float(tf32_lo(u)); }
+            else e.fwd[o] = __uint_as_float(tf32_rna(u));
+        }
+    }
+}
 
 // prepared filter: returns the base of [hi copy (taps*Ci*Co)][lo copy (3x only)]
 int prep_filter(const eg_conv_shape* s, const float* w, int transpose, int mode, cudaStream_t st, float** out) {
     const int taps = s->KH * s->KW;
     const size_t n = (size_t)taps * s->Ci * s->Co;
-    float* buf = nullptr;
-    if (g_fcache_on && !g_fcache_bypass) {
+    {
         std::lock_guard<std::mutex> lk(g_mu);
-        FilterCacheEntry& e = g_fcache[std::make_tuple(st, w, n, transpose, mode)];
-        if (e.buf != nullptr && e.epoch == g_fepoch) { ++g_fcache_hits; *out = e.buf; return 0; }
-        if (e.bytes < sizeof(float) * n * 2) {
-            if (e.buf) { cudaStreamSynchronize(st); cudaFree(e.buf); e.buf = nullptr; e.bytes = 0; }
-            cudaError_t err = cudaMalloc(&e.buf, sizeof(float) * n * 2);
-            if (err != cudaSuccess) return eg_fail(err, __FILE__, __LINE__);
-            e.bytes = sizeof(float) * n * 2;
+        auto it = g_managed.find(w);
+        if (it != g_managed.end() && it->second.n == n && it->second.mode == mode) {
+            ++g_managed_hits;
+            *out = transpose ? it->second.fwd : it->second.dgr;
+            return 0;
         }
-        e.epoch = g_fepoch;
-        buf = e.buf;
-    } else {
-        if (int r = get_scratch(st, sizeof(float) * n * 2, &buf)) return r;
     }
+    float* buf = nullptr;
+    if (int r = get_scratch(st, sizeof(float) * n * 2, &buf)) return r;
     dim3 grid(eg_ceil_div(s->Co, 32), eg_ceil_div(s->Ci, 32), taps), block(32, 8);
     prep_filter_k<<<grid, block, 0, st>>>(w, buf, buf + n, taps, s->Ci, s->Co, transpose, mode);
     EG_CHECK_LAUNCH();
@@ -976,16 +1015,78 @@ int prep_filter(const eg_conv_shape* s, const float* w, int transpose, int mode,
 
 }  // namespace
 
-void eg_tc_filter_cache_bypass(bool on) { g_fcache_bypass = on; }
-void eg_tc_filter_epoch_bump() { ++g_fepoch; }
-
-extern "C" long long eg_filter_cache(int op) {
-    if (op == 0) g_fcache_on = 0;
-    else if (op == 1) g_fcache_on = 1;
-    else if (op == 2) ++g_fepoch;
-    else if (op != 3) return -2;
-    return (long long)g_fcache_hits;
+extern "C" int eg_filter_set_create(const eg_filter_desc* descs, int n, int algo, long long* handle) {
+    if (!descs || n <= 0 || !handle) return eg_fail_arg("eg_filter_set_create: arguments", __FILE__, __LINE__);
+    if (algo != EG_ALGO_TC && algo != EG_ALGO_TC3X) return eg_fail_arg("eg_filter_set_create: algo must be EG_ALGO_TC or EG_ALGO_TC3X", __FILE__, __LINE__);
+    const int mode = algo == EG_ALGO_TC3X ? 3 : 1;
+    std::vector<FilterSetEntry> host(n);
+    size_t total = 0;
+    int tiles = 0;
+    for (int i = 0; i < n; ++i) {
+        const eg_filter_desc& d = descs[i];
+        if (!d.w || d.taps <= 0 || d.Ci <= 0 || d.Co <= 0) return eg_fail_arg("eg_filter_set_create: descriptor", __FILE__, __LINE__);
+        FilterSetEntry& e = host[i];
+        e.w = d.w; e.taps = d.taps; e.A = d.Ci; e.B = d.Co;
+        e.tiles_b = eg_ceil_div(d.Co, 32); e.tiles_ab = e.tiles_b * eg_ceil_div(d.Ci, 32);
+        e.tile0 = tiles; tiles += e.taps * e.tiles_ab;
+        total += 4 * (size_t)d.taps * d.Ci * d.Co + 64;
+    }
+    FilterSet fs;
+    cudaError_t err = cudaMalloc(&fs.buf, sizeof(float) * total);
+    if (err != cudaSuccess) return eg_fail(err, __FILE__, __LINE__);
+    err = cudaMalloc(&fs.table, sizeof(FilterSetEntry) * n);
+    if (err != cudaSuccess) { cudaFree(fs.buf); return eg_fail(err, __FILE__, __LINE__); }
+    float* p = fs.buf;
+    for (int i = 0; i < n; ++i) {
+        const size_t ni = (size_t)host[i].taps * host[i].A * host[i].B;
+        host[i].fwd = p; host[i].dgr = p + 2 * ni;
+        p += (4 * ni + 63) / 64 * 64;                        // keep every copy 256-byte aligned (TMA global address)
+    }
+    err = cudaMemcpy(fs.table, host.data(), sizeof(FilterSetEntry) * n, cudaMemcpyHostToDevice);
+    if (err != cudaSuccess) { cudaFree(fs.buf); cudaFree(fs.table); return eg_fail(err, __FILE__, __LINE__); }
+    fs.nfilters = n; fs.tiles = tiles; fs.mode = mode; fs.live = true;
+    std::lock_guard<std::mutex> lk(g_mu);
+    const int id = (int)g_sets.size();
+    for (int i = 0; i < n; ++i) {
+        const size_t ni = (size_t)host[i].taps * host[i].A * host[i].B;
+        auto old = g_managed.find(host[i].w);                // a pointer belongs to at most one set: the newest
+        if (old != g_managed.end()) g_managed.erase(old);
+        g_managed[host[i].w] = ManagedFilter{host[i].fwd, host[i].dgr, ni, mode, id};
+        fs.keys.push_back(host[i].w);
+    }
+    g_sets.push_back(fs);
+    *handle = id;
+    return 0;
 }
+
+extern "C" int eg_filter_set_prepare(long long handle, cudaStream_t st) {
+    FilterSet fs;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        if (handle < 0 || handle >= (long long)g_sets.size() || !g_sets[handle].live) return eg_fail_arg("eg_filter_set_prepare: handle", __FILE__, __LINE__);
+        fs = g_sets[handle];
+    }
+    prep_filter_set_k<<<fs.tiles, dim3(32, 8), 0, st>>>(fs.table, fs.nfilters, fs.mode);
+    EG_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int eg_filter_set_destroy(long long handle) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (handle < 0 || handle >= (long long)g_sets.size() || !g_sets[handle].live) return 0;
+    FilterSet& fs = g_sets[handle];
+    for (const float* k : fs.keys) {
+        auto it = g_managed.find(k);
+        if (it != g_managed.end() && it->second.set == (int)handle) g_managed.erase(it);
+    }
+    cudaDeviceSynchronize();                                 // no kernel may still read the copies
+    cudaFree(fs.buf); cudaFree(fs.table);
+    fs.buf = nullptr; fs.table = nullptr; fs.live = false; fs.keys.clear();
+    return 0;
+}
+
+// conv calls served from a prepared-filter set so far (no preparation launch)
+extern "C" long long eg_filter_set_hits(void) { return (long long)g_managed_hits; }
 
 extern "C" int eg_debug_set(int key, int value) {
     if (key < 0 || key >= 8) return -2;

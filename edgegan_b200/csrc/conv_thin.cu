@@ -16,8 +16,6 @@
 #include "common.cuh"
 
 int eg_tc_scratch(cudaStream_t st, int slot, size_t bytes, float** out);
-void eg_tc_filter_cache_bypass(bool on);      // the dense products below read operands from recycled scratch memory
-struct NoFilterCache { NoFilterCache() { eg_tc_filter_cache_bypass(true); } ~NoFilterCache() { eg_tc_filter_cache_bypass(false); } };
 int eg_tc_conv2d_fwd(const eg_conv_shape* s, const float* x, const float* w, const float* bias, float* y, int three_x, cudaStream_t st, const EgEpi* epi = nullptr);
 int eg_tc_conv2d_bwd_weight(const eg_conv_shape* s, const float* x, const float* dy, float* dw, int accumulate, int three_x, cudaStream_t st);
 
@@ -255,7 +253,6 @@ int eg_thin_conv2d_fwd(const eg_conv_shape* s, const float* x, const float* w, c
     thin_pad_rows_k<<<eg_ceil_div((long long)p.Kpad * s->Co, 256), 256, 0, st>>>(w, wp, p.K, p.Kpad, s->Co);
     EG_CHECK_LAUNCH();
     const eg_conv_shape g = gemm_shape(P, p.Kpad, s->Co);
-    NoFilterCache guard;
     return eg_tc_conv2d_fwd(&g, A, wp, bias, y, three_x, st);
 }
 
@@ -271,7 +268,6 @@ int eg_thin_conv2d_bwd_data(const eg_conv_shape* s, const float* dy, const float
     EG_CHECK_LAUNCH();
     const eg_conv_shape g = gemm_shape(P, s->Co, Npad);
     {
-        NoFilterCache guard;
         if (int r = eg_tc_conv2d_fwd(&g, dy, wt, nullptr, C, three_x, st)) return r;
     }
     const int threads = s->W >= 256 ? 256 : (s->W + 31) / 32 * 32;

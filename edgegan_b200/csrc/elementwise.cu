@@ -370,7 +370,6 @@ __global__ void rmsprop_k(float* __restrict__ var, const float* __restrict__ gra
 
 }  // namespace
 
-void eg_tc_filter_epoch_bump();
 #define ST ((cudaStream_t)stream)
 
 extern "C" {
@@ -520,7 +519,6 @@ int eg_onehot_concat(const float* z, int n, int zdim, int classes, float* out, v
 }
 int eg_rmsprop(float* var, const float* grad, float* ms, long long n, float lr, float decay, float eps, void* stream) {
     EG_REQUIRE(var && grad && ms && n > 0);
-    eg_tc_filter_epoch_bump();               // the weights change: prepared-filter copies are stale (eg_filter_cache)
     rmsprop_k<<<grid1d(n), TB, 0, ST>>>(var, grad, ms, n, lr, decay, eps);
     EG_CHECK_LAUNCH(); return 0;
 }

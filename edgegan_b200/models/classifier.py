@@ -72,7 +72,8 @@ class Classifier(object):
         self.name, self.ops, self.store = name, ops, store
         self.SPECTRAL_NORM_UPDATE_OPS = SPECTRAL_NORM_UPDATE_OPS
         self.num_classes, self.c_dim = num_classes, c_dim
-        self.aux = ParamStore(ops, classifier_aux_specs(name, num_classes, c_dim), rs or np.random.RandomState(0))
+        self.aux = ParamStore(ops, classifier_aux_specs(name, num_classes, c_dim), rs or np.random.RandomState(0),
+                              conv_filter_set=False)
         self.var_list = store.names() + [n for n in self.aux.names() if not n.endswith("/u")]
         self.layers = [s.name[:-len("/weights")] for s in store.specs if s.name.endswith("/weights")]
         self._wbar_valid = False
@@ -101,7 +102,6 @@ class Classifier(object):
         if self._wbar_valid:
             return
         ops = self.ops
-        ops.filter_cache_invalidate()         # the normalised copies below are rewritten in place
         self.wbar, self.ws = {}, {}
         for scope in self.layers:
             W = self.store.var[scope + "/weights"]
@@ -120,6 +120,16 @@ class Classifier(object):
                 ops.copy2d(wb, 0, cin * co, wa, 0, hd * co, k * k, hd * co)
                 ops.copy2d(wb, hd * co, cin * co, wi, 0, self.c_dim * co, k * k, self.c_dim * co)
                 self.wbar[scope + "#a"], self.wbar[scope + "#i"] = wa, wi
+        # prepared copies (tensor-core operand layouts) of the normalised filters: one kernel for the whole network
+        algo = getattr(ops, "default_algo", None)
+        tc = [w for w in self.wbar.values() if w.dim() == 4 and w.shape[2] % 32 == 0 and w.shape[3] % 32 == 0]
+        ids = tuple(w.data_ptr() for w in tc)
+        if getattr(self, "_fset_key", None) != (algo, ids):
+            if getattr(self, "_fset", None) is not None:
+                self._fset.close()
+            self._fset, self._fset_key = ops.filter_set(tc), (algo, ids)
+        if self._fset is not None:
+            self._fset.prepare()
         self._wbar_valid = True
 
     # ---- forward -------------------------------------------------------------------------------------

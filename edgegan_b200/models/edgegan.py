@@ -62,8 +62,8 @@ class EdgeGAN(object):
     def multiclass(self):
         return bool(self.config.multiclasses)
 
-    def _store(self, name, specs, rs):
-        st = ParamStore(self.ops, specs, rs)
+    def _store(self, name, specs, rs, conv_filter_set=True):
+        st = ParamStore(self.ops, specs, rs, conv_filter_set)
         self.stores[name] = st
         return st
 
@@ -96,16 +96,14 @@ class EdgeGAN(object):
             except ImportError as e:
                 raise NotImplementedError("the multi-class classifier run (d_optim2, BASELINE configs[2:]) is not "
                                           "built yet; use multiclasses=False") from e
-            st = self._store("D2", classifier_specs("D2", cfg.num_classes, self.c_dim), rs)
+            st = self._store("D2", classifier_specs("D2", cfg.num_classes, self.c_dim), rs, conv_filter_set=False)
             self.classifier = Classifier("D2", cfg.SPECTRAL_NORM_UPDATE_OPS, ops=ops, store=st, rs=rs,
                                          num_classes=cfg.num_classes)
             self.stores["D2/aux"] = self.classifier.aux      # unused disc head + frozen spectral-norm vectors
         self.losses = ops.zeros((16,))
         self._built = "train" if train else "test"
-        # filters are re-laid-out once per run instead of once per conv call; every place that writes weights outside
-        # rmsprop (loads, the classifier's normalised copies) invalidates, and so does the start of every run
-        ops.filter_cache(True)
-        ops.filter_cache_invalidate()        # the stores above may sit where an earlier model's filters were
+        # the tensor-core kernels' prepared filter copies are refreshed by ONE kernel per network right after each
+        # write to its weights (ParamStore.load / .rmsprop, Classifier._normalise_weights): ops.filter_set
 
     def build_train_model(self):
         self.build_networks(True)
@@ -115,7 +113,6 @@ class EdgeGAN(object):
 
     # ---- variables -------------------------------------------------------------------------------
     def load_variables(self, values, strict=True):
-        self.ops.filter_cache_invalidate()
         for st in self.stores.values():
             sub = {k: v for k, v in values.items() if k in st.offsets}
             st.load(sub, strict=strict)
@@ -501,7 +498,6 @@ class EdgeGAN(object):
             return G1.cache["h"][4], G2.cache["h"][4]
 
         for run in todo:
-            ops.filter_cache_invalidate()
             if run == "d_optim":
                 e, i = fakes()
                 D = self.joint_discriminator

@@ -27,6 +27,36 @@ def _p(t):
     return None if t is None else t.data_ptr()
 
 
+class FilterSet:
+    """Library-side prepared copies of all tensor-core conv filters of one network (include/edgegan_b200.h,
+    eg_filter_set_*): `prepare()` = one kernel on the current stream, to be enqueued after every write to the
+    filters.  The set is destroyed when any of its filter tensors is garbage collected (before its memory can be
+    reused), so a stale pointer can never be served."""
+
+    def __init__(self, ops, filters, algo):
+        import weakref
+        self.ops, self.algo = ops, algo
+        descs = (_lib.FilterDesc * len(filters))()
+        for d, w in zip(descs, filters):
+            kh, kw, ci, co = w.shape
+            if not w.is_contiguous():
+                raise ValueError("filters of a prepared-filter set must be contiguous")
+            d.w, d.taps, d.Ci, d.Co = w.data_ptr(), kh * kw, ci, co
+        h = C.c_longlong(-1)
+        _lib.check(ops.lib.eg_filter_set_create(descs, len(filters), ALGO[algo], C.byref(h)), "eg_filter_set_create")
+        self.handle = h.value
+        lib, handle = ops.lib, self.handle
+        self._fin = [weakref.finalize(w, lib.eg_filter_set_destroy, handle) for w in filters]
+
+    def prepare(self):
+        _lib.check(self.ops.lib.eg_filter_set_prepare(self.handle, self.ops._st), "eg_filter_set_prepare")
+
+    def close(self):
+        for f in self._fin:
+            f.detach()
+        self.ops.lib.eg_filter_set_destroy(self.handle)
+
+
 class DeviceOps:
     """CUDA implementation (the only one the product has)."""
 
@@ -53,7 +83,9 @@ class DeviceOps:
         return torch.empty(tuple(shape), dtype=torch.float32, device=self.device)
 
     def zeros(self, shape):
-        return torch.zeros(tuple(shape), dtype=torch.float32, device=self.device)
+        t = torch.empty(tuple(shape), dtype=torch.float32, device=self.device)
+        self.fill(t, 0.0)
+        return t
 
     def buf(self, key, shape):
         """Persistent named scratch buffer (allocated once -> the step is CUDA-graph capturable)."""
@@ -65,7 +97,6 @@ class DeviceOps:
         return t
 
     def from_numpy(self, a):
-        self.lib.eg_filter_cache(2)          # a new tensor may reuse the address of a freed filter (caching allocator)
         return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(self.device)
 
     def to_numpy(self, t):
@@ -76,7 +107,6 @@ class DeviceOps:
         if isinstance(src_host, np.ndarray):
             src_host = torch.from_numpy(np.ascontiguousarray(src_host, dtype=np.float32))
         dst.copy_(src_host.reshape(dst.shape), non_blocking=True)
-        self.lib.eg_filter_cache(2)          # the destination may be a filter
 
     def bytes_allocated(self):
         return sum(t.numel() * 4 for t in self._bufs.values())
@@ -87,6 +117,11 @@ class DeviceOps:
 
     def set_default_algo(self, algo):
         _lib.check(self.lib.eg_set_default_algo(ALGO[algo]), "eg_set_default_algo")
+
+    @property
+    def default_algo(self):
+        code = int(self.lib.eg_get_default_algo())
+        return {v: k for k, v in ALGO.items() if k}[code]
 
     # ---- convolution trio -------------------------------------------------------------------
     def _cs(self, xs, ws, ys, stride, pad):
@@ -213,16 +248,17 @@ class DeviceOps:
     def copy(self, src, dst):
         _lib.check(self.lib.eg_copy2d(_p(src), src.numel(), _p(dst), dst.numel(), 1, src.numel(), self._st), "copy2d")
 
-    def filter_cache(self, on=True):
-        """prepared-filter cache of the tensor-core convs (eg_filter_cache): the caller promises to call
-        filter_cache_invalidate() whenever filter memory changes other than through rmsprop()"""
-        self.lib.eg_filter_cache(1 if on else 0)
+    # ---- prepared-filter sets (eg_filter_set_*) -------------------------------------------------------
+    def filter_set(self, filters):
+        """-> FilterSet over the given 4-D HWIO filter tensors (or None when the default conv algorithm is the SIMT
+        path, which reads the filters as they are).  Call `.prepare()` after every write to those tensors."""
+        algo = self.default_algo
+        if algo not in ("tc", "tc3x") or not filters:
+            return None
+        return FilterSet(self, filters, algo)
 
-    def filter_cache_invalidate(self):
-        self.lib.eg_filter_cache(2)
-
-    def filter_cache_hits(self):
-        return int(self.lib.eg_filter_cache(3))
+    def filter_set_hits(self):
+        return int(self.lib.eg_filter_set_hits())
 
     def u8_lut(self, src_u8, lut, dst, stream=None):
         """dst[i] = lut[src[i]] (image bytes -> float with a 256-entry device table); `stream`: torch stream or None"""

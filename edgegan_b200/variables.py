@@ -99,8 +99,9 @@ def encoder_specs(name, image_size, z_dim=100, c_dim=3):
 class ParamStore:
     """Flat parameter / gradient / RMSProp-slot buffers of one network with named views."""
 
-    def __init__(self, ops, specs, rs=None):
+    def __init__(self, ops, specs, rs=None, conv_filter_set=True):
         self.ops = ops
+        self.conv_filter_set = conv_filter_set     # False: the convs never read these weights directly (classifier: Wbar)
         self.specs = list(specs)
         self.offsets = OrderedDict()
         off = 0
@@ -121,8 +122,29 @@ class ParamStore:
             n = int(np.prod(s.shape)) if len(s.shape) else 1
             self.var[s.name] = self.flat[o:o + n].view(s.shape)
             self.g[s.name] = self.grad[o:o + n].view(s.shape)
+        self._fset, self._fset_algo = None, None
         if rs is not None:
             self.load({s.name: s.sample(rs) for s in self.specs})
+
+    # ---- prepared copies of the conv filters (ops.filter_set) --------------------------------------------------
+    def conv_filters(self):
+        """the 4-D filters a tensor-core conv kernel can take in at least one direction (both channel counts
+        multiples of 32); the thin-channel image layers are read as they are"""
+        return [self.var[s.name] for s in self.specs
+                if len(s.shape) == 4 and s.shape[2] % 32 == 0 and s.shape[3] % 32 == 0 and s.shape[0] * s.shape[1] <= 25]
+
+    def prepare_filters(self):
+        """Refresh the library-side prepared copies of this network's conv filters: ONE kernel, enqueued after every
+        write to the flat buffer (load, RMSProp).  The set is (re)built lazily for the current default conv algorithm."""
+        if not self.conv_filter_set:
+            return
+        algo = getattr(self.ops, "default_algo", None)
+        if self._fset is None or self._fset_algo != algo:
+            if self._fset is not None:
+                self._fset.close()
+            self._fset, self._fset_algo = self.ops.filter_set(self.conv_filters()), algo
+        if self._fset is not None:
+            self._fset.prepare()
 
     def names(self):
         return list(self.offsets)
@@ -147,6 +169,8 @@ class ParamStore:
                     cur = self.ops.to_numpy(dst)
                 host[o:o + n] = cur[o:o + n]
         self.ops.upload(dst, host)
+        if what == "var":
+            self.prepare_filters()
 
     def export(self, what="var"):
         src = {"var": self.flat, "grad": self.grad, "ms": self.ms}[what]
@@ -163,3 +187,4 @@ class ParamStore:
 
     def rmsprop(self, lr):
         self.ops.rmsprop(self.flat, self.grad, self.ms, lr)
+        self.prepare_filters()

@@ -48,12 +48,21 @@ int eg_get_default_algo(void);
 /* development knob (kernel layout experiments from tools/tc_probe.py); not part of the stable surface */
 int eg_debug_set(int key, int value);
 
-/* Prepared-filter cache of the tensor-core conv path (off by default).  op 1 / 0: on / off; op 2: the filter memory
- * may have changed (eg_rmsprop calls this itself; call it after any other write to a filter, and whenever a filter
- * buffer is recycled for different weights); op 3: query only.  Returns the number of filter preparations skipped so
- * far.  With the cache on, a filter is re-laid-out once per (pointer, pass) between two invalidations instead of on
- * every launch; its buffers are allocated at first use, so run one step before capturing a CUDA graph. */
-long long eg_filter_cache(int op);
+/* Prepared-filter sets.  The tensor-core conv kernels read a re-laid-out copy of the filter (forward: [tap][Co][Ci],
+ * input gradient: [tap][Ci][Co]; in the 3xTF32 mode each with its low-order split next to it).  A set keeps those
+ * copies for ALL conv filters of one network in library-owned device memory and refreshes them with ONE kernel launch:
+ * the owner of the weights calls eg_filter_set_prepare on the stream right after every write to them (the reference's
+ * counterpart of that moment is the end of an RMSPropOptimizer.minimize run, edgegan/models/edgegan.py:105-124, or a
+ * Saver.restore, :641-657).  eg_conv2d_fwd / eg_conv2d_bwd_data look the filter pointer up and launch no preparation
+ * kernel; freshness follows from stream order, also when the launches are replayed from a CUDA graph.  Filters that
+ * are in no set are prepared per call.  `algo`: EG_ALGO_TC or EG_ALGO_TC3X (the copies are mode specific; a conv call
+ * in another mode ignores the set).  A pointer belongs to at most one set (the newest); destroy a set before the
+ * memory of its filters is released. */
+typedef struct { const float* w; int taps, Ci, Co; } eg_filter_desc;    /* filter [taps][Ci][Co] (HWIO, taps = KH*KW) */
+int eg_filter_set_create(const eg_filter_desc* descs, int n, int algo, long long* handle);
+int eg_filter_set_prepare(long long handle, cudaStream_t stream);
+int eg_filter_set_destroy(long long handle);
+long long eg_filter_set_hits(void);     /* conv calls served from a set so far */
 
 /* number of CUDA kernels the library has launched so far in this process (host-side counter, one host thread per
  * rank; launches recorded into a CUDA graph count once, at capture) -- bench.py's gpu_launches */

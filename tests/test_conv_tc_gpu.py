@@ -167,33 +167,49 @@ def test_fused_epilogues(dev, ref, case, algo):
         assert relerr(dev.to_numpy(out), want) < tol, ("dgrad*mask", act)
 
 
-def test_prepared_filter_cache(dev, ref):
-    """eg_filter_cache: a filter is prepared once per (pointer, pass) between invalidations; uploads and rmsprop
-    invalidate; results always reflect the current weights."""
+def test_prepared_filter_set(dev, ref):
+    """eg_filter_set_*: the filters of a set are prepared by ONE launch after each write; conv calls on them launch no
+    preparation kernel and always reflect the weights of the last prepare(); a freed set is never served."""
     rs = np.random.RandomState(5)
     N, H, W, Ci, Co, k, s, p = 2, 16, 16, 64, 128, 3, 1, 1
     x, w1, w2 = rnd(rs, N, H, W, Ci), rnd(rs, k, k, Ci, Co, scale=0.05), rnd(rs, k, k, Ci, Co, scale=0.05)
-    xd, wd, y = dev.from_numpy(x), dev.from_numpy(w1), dev.zeros((N, H, W, Co))
+    wb = rnd(rs, 1, 1, 128, 64, scale=0.05)                              # a second filter in the same set
+    xd, wd, wbd, y = dev.from_numpy(x), dev.from_numpy(w1), dev.from_numpy(wb), dev.zeros((N, H, W, Co))
     want1 = run(ref, "conv_fwd", [x, w1, None], (N, H, W, Co), s, p)
     want2 = run(ref, "conv_fwd", [x, w2, None], (N, H, W, Co), s, p)
-    dev.filter_cache(True)
-    try:
-        dev.filter_cache_invalidate()
-        h0 = dev.filter_cache_hits()
-        for _ in range(3):
-            dev.conv_fwd(xd, wd, None, y, s, p, "tc3x")
-        assert dev.filter_cache_hits() == h0 + 2                         # prepared once, reused twice
-        assert relerr(dev.to_numpy(y), want1) < 2e-5
-        dev.conv_bwd_data(y, wd, None, dev.zeros((N, H, W, Ci)), s, p, "tc3x")
-        assert dev.filter_cache_hits() == h0 + 2                         # the input gradient uses another layout
-        dev.upload(wd, w2)                                               # same pointer, new weights
+    dev.set_default_algo("tc3x")
+    fs = dev.filter_set([wd, wbd])
+    fs.prepare()
+    h0, l0 = dev.filter_set_hits(), dev.launches
+    for _ in range(3):
         dev.conv_fwd(xd, wd, None, y, s, p, "tc3x")
-        assert dev.filter_cache_hits() == h0 + 2
-        assert relerr(dev.to_numpy(y), want2) < 2e-5
-        g, ms = dev.from_numpy(np.ones_like(w2)), dev.from_numpy(np.ones_like(w2))
-        dev.rmsprop(wd, g, ms, 0.1)                                      # w -= 0.1 * 1 / sqrt(0.9 + 0.1 + 1e-10)
-        dev.conv_fwd(xd, wd, None, y, s, p, "tc3x")
-        want3 = run(ref, "conv_fwd", [x, w2 - np.float32(0.1), None], (N, H, W, Co), s, p)
-        assert relerr(dev.to_numpy(y), want3) < 2e-5
-    finally:
-        dev.filter_cache(False)
+    assert dev.filter_set_hits() == h0 + 3 and dev.launches == l0 + 3        # conv kernels only
+    assert relerr(dev.to_numpy(y), want1) < 2e-5
+    dx = dev.zeros((N, H, W, Ci))
+    dev.conv_bwd_data(y, wd, None, dx, s, p, "tc3x")                     # the other prepared layout, same set
+    assert dev.filter_set_hits() == h0 + 4
+    want_dx = run(ref, "conv_bwd_data", [dev.to_numpy(y), w1, None], (N, H, W, Ci), s, p)
+    assert relerr(dev.to_numpy(dx), want_dx) < 2e-5
+    y1 = dev.zeros((N, H, W, 64))
+    dev.conv_fwd(y, wbd, None, y1, 1, 0, "tc3x")                         # second member
+    assert relerr(dev.to_numpy(y1), run(ref, "conv_fwd", [dev.to_numpy(y), wb, None], (N, H, W, 64), 1, 0)) < 2e-5
+    dev.conv_fwd(xd, wd, None, y, s, p, "tc")                            # another mode ignores the 3x copies
+    assert relerr(dev.to_numpy(y), want1) < 4e-3
+    dev.upload(wd, w2)                                                   # same pointer, new weights ...
+    fs.prepare()                                                         # ... the writer refreshes the set
+    dev.conv_fwd(xd, wd, None, y, s, p, "tc3x")
+    assert relerr(dev.to_numpy(y), want2) < 2e-5
+    g, ms = dev.from_numpy(np.ones_like(w2)), dev.from_numpy(np.ones_like(w2))
+    dev.rmsprop(wd, g, ms, 0.1)                                          # w -= 0.1 * 1 / sqrt(0.9 + 0.1 + 1e-10)
+    fs.prepare()
+    dev.conv_fwd(xd, wd, None, y, s, p, "tc3x")
+    want3 = run(ref, "conv_fwd", [x, w2 - np.float32(0.1), None], (N, H, W, Co), s, p)
+    assert relerr(dev.to_numpy(y), want3) < 2e-5
+    # dropping a member destroys the set: the pointer is prepared per call again (and stays correct)
+    h1 = dev.filter_set_hits()
+    del wbd
+    import gc
+    gc.collect()
+    dev.upload(wd, w1)
+    dev.conv_fwd(xd, wd, None, y, s, p, "tc3x")
+    assert dev.filter_set_hits() == h1 and relerr(dev.to_numpy(y), want1) < 2e-5
