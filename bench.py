@@ -435,7 +435,8 @@ def conv_roofline(model, ops, step_fn, algo):
             e0.record()
             f(*a, **kw)
             e1.record()
-            recs.append((name, used, 2.0 * macs, e0, e1))
+            shape = f"N{s.N} {s.H}x{s.W}x{s.Ci}->{s.OH}x{s.OW}x{s.Co} k{s.KH} s{s.stride}"
+            recs.append((name, used, 2.0 * macs, e0, e1, shape))
         return g
 
     for pid, n in enumerate(("conv_fwd", "conv_bwd_data", "conv_bwd_weight")):
@@ -446,13 +447,15 @@ def conv_roofline(model, ops, step_fn, algo):
     finally:
         for n, f in orig.items():
             setattr(ops, n, f)
-    agg = {}
-    for name, used, fl, e0, e1 in recs:
+    agg, by_shape = {}, {}
+    for name, used, fl, e0, e1, shape in recs:
         key = (name, "tc" if used in (2, 3) else "simt")
-        a = agg.setdefault(key, [0.0, 0.0, 0])
-        a[0] += fl
-        a[1] += e0.elapsed_time(e1)
-        a[2] += 1
+        ms = e0.elapsed_time(e1)
+        for d, k in ((agg, key), (by_shape, key + (shape,))):
+            a = d.setdefault(k, [0.0, 0.0, 0])
+            a[0] += fl
+            a[1] += ms
+            a[2] += 1
     tc_fl = sum(v[0] for k, v in agg.items() if k[1] == "tc")
     tc_ms = sum(v[1] for k, v in agg.items() if k[1] == "tc")
     all_ms = sum(v[1] for v in agg.values())
@@ -470,6 +473,9 @@ def conv_roofline(model, ops, step_fn, algo):
     peak_kind = peak / 2.0
     detail = {f"{k[0]}/{k[1]}": {"launches": v[2], "ms": round(v[1], 3), "tflops": (v[0] / v[1] / 1e9 if v[1] > 0 else None)}
               for k, v in agg.items()}
+    top = sorted(by_shape.items(), key=lambda kv: -kv[1][1])[:24]
+    shapes = [{"pass": k[0], "path": k[1], "shape": k[2], "launches": v[2], "ms": round(v[1], 3),
+               "tflops": round(v[0] / v[1] / 1e9, 1) if v[1] > 0 else None} for k, v in top]
     if tc_ms > 0:
         ach = tc_fl / tc_ms / 1e9
         mult = 3.0 if algo == "tc3x" else 1.0
@@ -480,7 +486,7 @@ def conv_roofline(model, ops, step_fn, algo):
                 "tensor_pipe_work_frac": mult * ach / peak_kind,
                 "note": ("achieved counts ALGORITHMIC conv FLOPs; the 3xTF32 mode issues 3 tensor-core MMAs per algorithmic "
                          "MMA (hi*hi + lo*hi + hi*lo), so the tensor pipe is busy tensor_pipe_work_frac of its tf32 peak"),
-                "detail": detail}
+                "detail": detail, "by_shape": shapes}
     simt_fl = sum(v[0] for v in agg.values())
     ach = simt_fl / all_ms / 1e9 if all_ms > 0 else 0.0
     return {"bound": "tensor", "kernel": "fp32 FFMA implicit-GEMM conv (SIMT path; tensor cores not used)",

@@ -79,11 +79,16 @@ SIGNATURES = {
     "eg_zl1_loss_bwd": [vp, vp, f32, vp, vp, i32, i32, i32, f32, f32, vp, vp, vp, vp],
     "eg_prelu_fwd": [vp, vp, vp, i64, vp],
     "eg_prelu_bwd": [vp, vp, vp, vp, vp, i64, i32, vp],
+    "eg_prelu_fwd2": [vp, vp, vp, vp, vp, i64, vp],
+    "eg_prelu_bwd_ex": [vp, vp, vp, vp, vp, i64, i32, i32, vp],
+    "eg_mru_gate_fwd": [vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp],
+    "eg_mru_gate_bwd": [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp],
     "eg_minmax_fwd": [vp, vp, vp, i32, i32, i32, vp],
     "eg_minmax_bwd": [vp, vp, vp, vp, i32, i32, i32, vp],
     "eg_fma3": [vp, vp, vp, vp, i64, vp],
     "eg_mul": [vp, vp, vp, i64, vp],
     "eg_add_pool2_fwd": [vp, vp, vp, i32, i32, i32, i32, vp],
+    "eg_add_pool2_prelu_fwd": [vp, vp, vp, vp, vp, i32, i32, i32, i32, vp],
     "eg_pool2_bwd": [vp, vp, i32, i32, i32, i32, i32, vp],
     "eg_globalmean_fwd": [vp, vp, i32, i32, i32, vp],
     "eg_globalmean_bwd": [vp, vp, i32, i32, i32, vp],

@@ -151,37 +151,39 @@ class Classifier(object):
         c0 = B("c0", (n, S, S, 8))
         self._conv("Conv", x, c0, 7)
         ht = B("h0", c0.shape)
-        ops.prelu_fwd(c0, self._v("Conv/prelu/param"), ht)
+        # h0 = prelu(c0) and the first unit's a_in = prelu(h0) in one pass; later units get their a_in from the pooling
+        # kernel that produces their ht
+        a_in = B("u1/a_in", c0.shape)
+        ops.prelu_fwd2(c0, self._v("Conv/prelu/param"), ht, self._v("mru_conv_unit_t_1_layer_0/norm_activation_in/prelu/param"), a_in)
         units = []
         for t, (hd, fd) in enumerate(UNITS, start=1):
             p = f"mru_conv_unit_t_{t}_layer_0"
             inp = pyr[t - 1]
             H = inp.shape[1]
             U = lambda key, c: B(f"u{t}/{key}", (n, H, H, c))
-            a_in = U("a_in", hd)
-            ops.prelu_fwd(ht, self._v(f"{p}/norm_activation_in/prelu/param"), a_in)
-            cg, cg_i, rgl, rg = U("cg", hd), U("cg_i", hd), U("rgl", hd), U("rg", hd)
+            # update gate: conv(concat(a_in, inp)) as two convs; rgl = lrelu(sum) is written over cg by the fused kernel
+            rgl, cg_i = U("rgl", hd), U("cg_i", hd)
             gate = f"{nm}/{p}/update_gate"
-            ops.conv_fwd(a_in, self.wbar[gate + "#a"], self.store.var[gate + "/biases"].view(-1), cg, 1, 1)
+            ops.conv_fwd(a_in, self.wbar[gate + "#a"], self.store.var[gate + "/biases"].view(-1), rgl, 1, 1)
             ops.conv_fwd(inp, self.wbar[gate + "#i"], None, cg_i, 1, 1)
-            ops.axpby(cg_i, cg, 1.0, 1.0)
-            ops.act_fwd(cg, rgl, "lrelu2")
-            mm = B(f"u{t}/mm", (n, hd, 2))
-            ops.minmax_fwd(rgl, rg, mm)
             img = U("img", hd)
             self._conv(f"{p}/Conv", inp, img, 3)
+            mm = B(f"u{t}/mm", (n, hd, 4))
             plus, hin = U("plus", hd), U("hin", hd)
-            ops.fma3(ht, rg, img, plus)
-            ops.prelu_fwd(plus, self._v(f"{p}/norm_activation_merge_1/prelu/param"), hin)
+            ops.mru_gate_fwd(rgl, cg_i, ht, img, self._v(f"{p}/norm_activation_merge_1/prelu/param"), mm, plus, hin)
             c1, hn1, hn2, ho = U("c1", fd), U("hn1", fd), U("hn2", fd), U("ho", fd)
             self._conv(f"{p}/Conv_1", hin, c1, 3)
             ops.prelu_fwd(c1, self._v(f"{p}/Conv_1/prelu/param"), hn1)
             self._conv(f"{p}/Conv_2", hn1, hn2, 3)
             self._conv(f"{p}/Conv_3", ht, ho, 1)
             out = B(f"u{t}/out", (n, H // 2, H // 2, fd))
-            ops.add_pool2_fwd(ho, hn2, out)
-            units.append(dict(p=p, hd=hd, fd=fd, ht=ht, inp=inp, a_in=a_in, cg=cg, rgl=rgl, rg=rg, mm=mm,
-                              img=img, plus=plus, hin=hin, c1=c1, hn1=hn1))
+            units.append(dict(p=p, hd=hd, fd=fd, ht=ht, inp=inp, a_in=a_in, rgl=rgl, mm=mm, img=img, plus=plus, hin=hin,
+                              c1=c1, hn1=hn1))
+            if t < len(UNITS):
+                a_in = B(f"u{t + 1}/a_in", out.shape)
+                ops.add_pool2_fwd(ho, hn2, out, self._v(f"mru_conv_unit_t_{t + 1}_layer_0/norm_activation_in/prelu/param"), a_in)
+            else:
+                ops.add_pool2_fwd(ho, hn2, out)
             ht = out
         hl = B("hlast", ht.shape)
         ops.prelu_fwd(ht, self._v("mru_conv_unit_last_norm/prelu/param"), hl)
@@ -266,20 +268,14 @@ class Classifier(object):
                           self._g(f"{p}/Conv_1/prelu/param") if param_grads else None)
             if param_grads:
                 self._wgrad(f"{p}/Conv_1", u["hin"], g_c1, 3, tag)
-            g_hin, g_plus = U("g_hin", hd), U("g_plus", hd)
+            g_hin = U("g_hin", hd)
             ops.conv_bwd_data(g_c1, wb("Conv_1"), None, g_hin, 1, 1)
-            ops.prelu_bwd(u["plus"], self._v(f"{p}/norm_activation_merge_1/prelu/param"), g_hin, g_plus,
-                          self._g(f"{p}/norm_activation_merge_1/prelu/param") if param_grads else None)
-            # plus = ht + rg * img
-            ops.axpby(g_plus, g_ht, 1.0, 1.0)
-            g_rg, g_img = U("g_rg", hd), U("g_img", hd)
-            ops.mul(g_plus, u["img"], g_rg)
-            ops.mul(g_plus, u["rg"], g_img)
+            # plus = ht + rg * img, hin = prelu(plus), rg = minmax(rgl), rgl = lrelu(cg): one fused kernel
+            g_img, g_cg = U("g_img", hd), U("g_cg", hd)
+            ops.mru_gate_bwd(u["plus"], g_hin, u["img"], u["rgl"], u["mm"], self._v(f"{p}/norm_activation_merge_1/prelu/param"),
+                             g_ht, g_img, g_cg, self._g(f"{p}/norm_activation_merge_1/prelu/param") if param_grads else None)
             if param_grads:
                 self._wgrad(f"{p}/Conv", inp, g_img, 3, tag)
-            g_rgl, g_cg = U("g_rgl", hd), U("g_cg", hd)
-            ops.minmax_bwd(u["rgl"], u["mm"], g_rg, g_rgl)
-            ops.act_bwd(u["cg"], g_rgl, g_cg, "lrelu2")
             gate = f"{nm}/{p}/update_gate"
             if param_grads:
                 # dL/dWbar of the two filter parts, assembled into the [k, k, hd+3, hd] layout for the spectral-norm backward
@@ -293,11 +289,10 @@ class Classifier(object):
                 ops.copy2d(gi_w, 0, self.c_dim * co, gbar, hd * co, cin * co, 9, self.c_dim * co)
                 ops.spectral_norm_bwd(Wg, self.aux.var[gate + "/u"], self.ws[gate], gbar, self.store.g[gate + "/weights"])
                 ops.bias_grad(g_cg, self.store.g[gate + "/biases"].view(-1), False)
-            g_ain, g_ht2 = U("g_ain", hd), U("g_ht2", hd)
+            g_ain = U("g_ain", hd)
             ops.conv_bwd_data(g_cg, self.wbar[gate + "#a"], None, g_ain, 1, 1)
-            ops.prelu_bwd(htu, self._v(f"{p}/norm_activation_in/prelu/param"), g_ain, g_ht2,
-                          self._g(f"{p}/norm_activation_in/prelu/param") if param_grads else None)
-            ops.axpby(g_ht2, g_ht, 1.0, 1.0)
+            ops.prelu_bwd(htu, self._v(f"{p}/norm_activation_in/prelu/param"), g_ain, g_ht,
+                          self._g(f"{p}/norm_activation_in/prelu/param") if param_grads else None, accumulate_gx=True)
             if input_grad:
                 gi = B(f"g_pyr{t - 1}", inp.shape)
                 ops.conv_bwd_data(g_img, wb("Conv"), None, gi, 1, 1)

@@ -332,8 +332,25 @@ class DeviceOps:
     def prelu_fwd(self, x, leak, y):
         _lib.check(self.lib.eg_prelu_fwd(_p(x), _p(leak), _p(y), x.numel(), self._st), "prelu_fwd")
 
-    def prelu_bwd(self, x, leak, gy, gx, gleak, accumulate_leak=False):
-        _lib.check(self.lib.eg_prelu_bwd(_p(x), _p(leak), _p(gy), _p(gx), _p(gleak), x.numel(), int(accumulate_leak), self._st), "prelu_bwd")
+    def prelu_bwd(self, x, leak, gy, gx, gleak, accumulate_leak=False, accumulate_gx=False):
+        """gx (= or +=) gy * prelu'(x); gleak (= or +=) the leak gradient (either output may be None)"""
+        _lib.check(self.lib.eg_prelu_bwd_ex(_p(x), _p(leak), _p(gy), _p(gx), _p(gleak), x.numel(), int(accumulate_leak),
+                                            int(accumulate_gx), self._st), "prelu_bwd")
+
+    def prelu_fwd2(self, x, leak, y, leak2, y2):
+        """y = prelu(x; leak), y2 = prelu(y; leak2) in one pass"""
+        _lib.check(self.lib.eg_prelu_fwd2(_p(x), _p(leak), _p(y), _p(leak2), _p(y2), x.numel(), self._st), "prelu_fwd2")
+
+    def mru_gate_fwd(self, cg, cg_i, ht, img, leak, stats, plus, hin):
+        """fused middle of an MRU unit (eg_mru_gate_fwd): cg is overwritten with rgl = lrelu(cg + cg_i)"""
+        N, P, Cn = self._npc(cg)
+        _lib.check(self.lib.eg_mru_gate_fwd(_p(cg), _p(cg_i), _p(ht), _p(img), _p(leak), _p(stats), _p(plus), _p(hin),
+                                            N, P, Cn, self._st), "mru_gate_fwd")
+
+    def mru_gate_bwd(self, plus, g_hin, img, rgl, stats, leak, g_ht, g_img, g_cg, gleak, accumulate_leak=False):
+        N, P, Cn = self._npc(plus)
+        _lib.check(self.lib.eg_mru_gate_bwd(_p(plus), _p(g_hin), _p(img), _p(rgl), _p(stats), _p(leak), _p(g_ht), _p(g_img),
+                                            _p(g_cg), _p(gleak), int(accumulate_leak), N, P, Cn, self._st), "mru_gate_bwd")
 
     def minmax_fwd(self, x, y, stats):
         N, P, Cn = self._npc(x)
@@ -349,9 +366,10 @@ class DeviceOps:
     def mul(self, a, b, out):
         _lib.check(self.lib.eg_mul(_p(a), _p(b), _p(out), a.numel(), self._st), "mul")
 
-    def add_pool2_fwd(self, a, b, y):
+    def add_pool2_fwd(self, a, b, y, leak=None, y_act=None):
+        """y = mean_pool2x2(a + b); with leak / y_act also y_act = prelu(y; leak)"""
         N, H, W, Cn = a.shape
-        _lib.check(self.lib.eg_add_pool2_fwd(_p(a), _p(b), _p(y), N, H, W, Cn, self._st), "add_pool2_fwd")
+        _lib.check(self.lib.eg_add_pool2_prelu_fwd(_p(a), _p(b), _p(y), _p(leak), _p(y_act), N, H, W, Cn, self._st), "add_pool2_fwd")
 
     def pool2_bwd(self, gy, gx, accumulate=False):
         N, H, W, Cn = gx.shape

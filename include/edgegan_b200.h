@@ -204,6 +204,22 @@ int eg_zl1_loss_bwd(const float* mu, const float* ls, float eps, const float* ep
 int eg_prelu_fwd(const float* x, const float* leak, float* y, long long n, void* stream);
 int eg_prelu_bwd(const float* x, const float* leak, const float* gy, float* gx, float* gleak, long long n,
                  int accumulate_leak, void* stream);
+/* y = prelu(x; leak), y2 = prelu(y; leak2): classifier.py:43-45 (h0) followed by the first MRU unit's
+ * norm_activation_in (conv.py:160) in one pass.  _ex: gx (= or +=) ... when accumulate_gx (cotangents that meet at ht) */
+int eg_prelu_fwd2(const float* x, const float* leak, float* y, const float* leak2, float* y2, long long n, void* stream);
+int eg_prelu_bwd_ex(const float* x, const float* leak, const float* gy, float* gx, float* gleak, long long n,
+                    int accumulate_leak, int accumulate_gx, void* stream);
+/* The element-wise middle of one MRU unit (nn/modules/conv.py:189-209) as ONE kernel per direction, tensors [N,P,C]:
+ *   fwd:  rgl = lrelu(cg + cg_i) written over cg (cg = conv over prelu(ht) + bias, cg_i = conv over the image part of
+ *         the concat, conv.py:189-196);  rg = (rgl - min_P)/(max_P - min_P) (:197-198);  plus = ht + rg*img (:209);
+ *         hin = prelu(plus; leak) (:212).  stats[N,C,4] = (min, max, #argmin, #argmax).  rg is not stored.
+ *   bwd:  from g_hin: g_ht += g_plus, g_img = g_plus*rg, g_cg = lrelu'(rgl) * minmax_bwd(g_plus*img); gleak (may be
+ *         NULL) (= or +=) the prelu leak gradient.  C % 4 == 0. */
+int eg_mru_gate_fwd(float* cg_rgl, const float* cg_i, const float* ht, const float* img, const float* leak, float* stats,
+                    float* plus, float* hin, int N, int P, int C, void* stream);
+int eg_mru_gate_bwd(const float* plus, const float* g_hin, const float* img, const float* rgl, const float* stats,
+                    const float* leak, float* g_ht, float* g_img, float* g_cg, float* gleak, int accumulate_leak,
+                    int N, int P, int C, void* stream);
 /* update-gate normalisation (conv.py:197-198): y = (x - min)/(max - min) over H,W per (n,c); stats[N,C,2] =
  * (min, max); bwd sends the min / max terms to the arg-extrema, split evenly between ties */
 int eg_minmax_fwd(const float* x, float* y, float* stats, int N, int P, int C, void* stream);
@@ -214,6 +230,9 @@ int eg_mul(const float* a, const float* b, float* out, long long n, void* stream
 /* y = mean_pool2x2(a + b) (b may be NULL; pooling.py:4-8 after conv.py:236); gx (= or +=) pooled-gradient ;
  * y[n,c] = mean_p x[n,p,c] (classifier.py:111) and its gradient */
 int eg_add_pool2_fwd(const float* a, const float* b, float* y, int N, int H, int W, int C, void* stream);
+/* same, and y_act = prelu(y; leak) (the next unit's norm_activation_in, conv.py:160) when y_act != NULL */
+int eg_add_pool2_prelu_fwd(const float* a, const float* b, float* y, const float* leak, float* y_act, int N, int H, int W,
+                           int C, void* stream);
 int eg_pool2_bwd(const float* gy, float* gx, int N, int H, int W, int C, int accumulate, void* stream);
 int eg_globalmean_fwd(const float* x, float* y, int N, int P, int C, void* stream);
 int eg_globalmean_bwd(const float* gy, float* gx, int N, int P, int C, void* stream);

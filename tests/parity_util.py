@@ -26,35 +26,47 @@ def oracle_pair(ocfg, v, u, inp, runs=None):
     return out[torch.float64], out[torch.float32]
 
 
-def oracle_sensitivity(ocfg, v, u, inp, col64, rel=1e-5, seed=0, runs=None, samples=2):
+def oracle_sensitivity(ocfg, v, u, inp, col64, rel=1e-5, seed=0, runs=None, samples=2, rms=None):
     """max over `samples` random perturbations of _oracle_sensitivity_once (the response is heavy-tailed: a
     single lrelu-mask or arg-max flip moves a whole filter gradient by a finite amount)."""
     out = None
     for k in range(samples):
-        cur = _oracle_sensitivity_once(ocfg, v, u, inp, col64, rel, seed + k, runs)
+        cur = _oracle_sensitivity_once(ocfg, v, u, inp, col64, rel, seed + k, runs, rms)
+        w = cur.pop("__weights__")
         if out is None:
             out = cur
+            out["__weights__"] = [w]
         else:
-            for run in out:
+            for run in cur:
                 for n in out[run]:
                     out[run][n] = max(out[run][n], cur[run][n])
+            out["__weights__"].append(w)
     return out
 
 
-def _oracle_sensitivity_once(ocfg, v, u, inp, col64, rel, seed, runs):
-    """How far the fp64 oracle's own gradients move when the images are perturbed by `rel` (relative): the
+def _oracle_sensitivity_once(ocfg, v, u, inp, col64, rel, seed, runs, rms=None):
+    """How far the fp64 oracle's own gradients move when the images and z are perturbed by `rel` (relative): the
     critics' penalty gradient is discontinuous in the lrelu masks of low-variance instance-norm channels, so
     near such a point ANY two fp32 implementations disagree by a finite amount.  run -> name -> rel. change."""
     rs = np.random.RandomState(seed)
     img = (inp.images.astype(np.float64) * (1 + rel * rs.standard_normal(inp.images.shape))).astype(np.float32)
-    inp2 = O.StepInputs(img, inp.z, inp.alpha, inp.eps)
+    # the latent too (runs 5-7 do not read the images at all); the class-id column stays exact
+    z = inp.z.astype(np.float64).copy()
+    z[:, :ocfg.z_dim] *= 1 + rel * rs.standard_normal((z.shape[0], ocfg.z_dim))
+    inp2 = O.StepInputs(img, z.astype(np.float32), inp.alpha, inp.eps)
     st = O.OracleState(ocfg, v, u, dtype=torch.float64)
+    if rms is not None:
+        for n in st.rms:
+            st.rms[n] = torch.tensor(np.asarray(rms[n], np.float64).reshape(tuple(st.rms[n].shape)), dtype=torch.float64)
     col = {}
     O.update_model(st, inp2, runs=runs, collect=col)
     out = {}
     for run, rec in col64.items():
         out[run] = {n: maxabs(col[run]["grads"][n] - g) / (maxabs(g) + 1e-30) for n, g in rec["grads"].items()}
         out[run] = dict(out[run])
+    # the perturbed run's end weights (torch tensors): RMSProp normalises the step, so where |g| >> 1 a small relative
+    # change of a gradient element moves its weight by O(lr) -- the weight check needs this response too
+    out["__weights__"] = {n: t.detach().numpy().astype(np.float64) for n, t in st.v.items()}
     return out
 
 
@@ -69,6 +81,8 @@ def check_grads(mine, truth, ref32, tol, noise_factor=10.0, sens=None, stats=Non
     tensors passed on the plain tolerance and how many only through the noise clause."""
     fails, report = [], {}
     for run, rec in truth.items():
+        if run.startswith("__"):
+            continue
         worst = 0.0
         for name, g64 in rec["grads"].items():
             if cancelled(name):
@@ -92,15 +106,19 @@ def check_grads(mine, truth, ref32, tol, noise_factor=10.0, sens=None, stats=Non
     return report, fails
 
 
-def check_weights(new, st64, st32, lr, tol, noise_factor=4.0, only=None, stats=None):
+def check_weights(new, st64, st32, lr, tol, noise_factor=4.0, only=None, stats=None, sens=None):
     """updated weights in lr-units (one RMSProp step moves a weight by at most ~lr / sqrt(0.1) ~ 3.2 lr): error vs the
-    fp64 oracle <= tol, or <= noise_factor x the fp32 oracle's own distance to it.  `only`: name-prefix filter."""
+    fp64 oracle <= tol, or <= noise_factor x max(the fp32 oracle's own distance to it, the fp64 oracle's response to
+    the input perturbation of oracle_sensitivity -- `sens`).  `only`: name-prefix filter."""
     fails = []
     for name, t in st64.v.items():
         if cancelled(name) or (only is not None and not name.startswith(only)):
             continue
         e = maxabs(np.asarray(new[name], np.float64).reshape(t.shape) - t.numpy()) / lr
         noise = maxabs(st32.v[name].numpy().astype(np.float64) - t.numpy()) / lr
+        if sens is not None:
+            for w in sens.get("__weights__", []):
+                noise = max(noise, maxabs(w[name] - t.numpy()) / lr)
         if stats is not None:
             stats["tensors"] = stats.get("tensors", 0) + 1
             stats["strict" if e <= tol else "noise_clause"] = stats.get("strict" if e <= tol else "noise_clause", 0) + 1
@@ -157,7 +175,7 @@ def teacher_forced_step(m, ops, ocfg, v, u, inp, grad_tol, weight_tol=0.05, sens
             if maxabs(col64[run]["grads"][name]) < 1e-9:
                 for c in (col64, col32):
                     c[run]["grads"].pop(name)
-        sens = oracle_sensitivity(ocfg, var, u, inp, col64, runs=[run], samples=sens_samples) if sens_samples else None
+        sens = oracle_sensitivity(ocfg, var, u, inp, col64, runs=[run], samples=sens_samples, rms=ms) if sens_samples else None
         mine = {run: {n: np.asarray(g).reshape(col64[run]["grads"][n].shape) for n, g in grad.items() if n in col64[run]["grads"]}}
         gstats = {}
         tol = grad_tol(run) if callable(grad_tol) else grad_tol
@@ -165,7 +183,7 @@ def teacher_forced_step(m, ops, ocfg, v, u, inp, grad_tol, weight_tol=0.05, sens
         wstats = {}
         wfails = []
         for scope in RUN_SCOPES[run]:
-            wfails += check_weights(after, st64, st32, lr, weight_tol, only=scope, stats=wstats)
+            wfails += check_weights(after, st64, st32, lr, weight_tol, only=scope, stats=wstats, sens=sens)
         rec = dict(gstats.get(run, {}))
         loss_dev, loss_ref = sum(dev_losses[n] for n in loss_of[run]), st64.losses.get(run)
         rec.update(grad_tol=tol, loss_dev=loss_dev, loss_ref=loss_ref, weights=wstats)

@@ -352,10 +352,40 @@ class RefOps:
         a = leak.reshape(()) * x
         y.copy_(torch.where(a >= x, a, x))
 
-    def prelu_bwd(self, x, leak, gy, gx, gleak, accumulate_leak=False):
+    def prelu_fwd2(self, x, leak, y, leak2, y2):
+        self.prelu_fwd(x, leak, y)
+        self.prelu_fwd(y, leak2, y2)
+
+    def mru_gate_fwd(self, cg, cg_i, ht, img, leak, stats, plus, hin):
+        """composition of the separate reference ops (axpby, lrelu2, minmax, fma3, prelu)"""
+        rgl = act_fwd("lrelu2", cg + cg_i)
+        cg.copy_(rgl)
+        rg = torch.empty_like(rgl)
+        mm = torch.empty(stats.shape[:-1] + (2,), dtype=self.dtype)
+        self.minmax_fwd(rgl, rg, mm)
+        x3 = rgl.reshape(rgl.shape[0], -1, rgl.shape[-1])
+        cnt_min = (x3 == mm[:, None, :, 0]).to(self.dtype).sum(1)
+        cnt_max = (x3 == mm[:, None, :, 1]).to(self.dtype).sum(1)
+        stats.copy_(torch.stack([mm[..., 0], mm[..., 1], cnt_min, cnt_max], dim=-1))
+        self.fma3(ht, rg, img, plus)
+        self.prelu_fwd(plus, leak, hin)
+
+    def mru_gate_bwd(self, plus, g_hin, img, rgl, stats, leak, g_ht, g_img, g_cg, gleak, accumulate_leak=False):
+        g_plus = torch.empty_like(plus)
+        self.prelu_bwd(plus, leak, g_hin, g_plus, gleak, accumulate_leak)
+        g_ht.add_(g_plus)
+        rg = torch.empty_like(rgl)
+        self.minmax_fwd(rgl, rg, torch.empty(stats.shape[:-1] + (2,), dtype=self.dtype))
+        g_img.copy_(g_plus * rg)
+        g_rgl = torch.empty_like(rgl)
+        self.minmax_bwd(rgl, stats[..., :2], g_plus * img, g_rgl)
+        g_cg.copy_(g_rgl * act_grad("lrelu2", rgl))
+
+    def prelu_bwd(self, x, leak, gy, gx, gleak, accumulate_leak=False, accumulate_gx=False):
         first = (leak.reshape(()) * x >= x)
         if gx is not None:
-            gx.copy_(torch.where(first, gy * leak.reshape(()), gy))
+            o = torch.where(first, gy * leak.reshape(()), gy)
+            gx.add_(o) if accumulate_gx else gx.copy_(o)
         if gleak is not None:
             v = (gy * x * first.to(self.dtype)).sum().reshape(gleak.shape)
             gleak.add_(v) if accumulate_leak else gleak.copy_(v)
@@ -385,9 +415,11 @@ class RefOps:
     def mul(self, a, b, out):
         out.copy_(a * b)
 
-    def add_pool2_fwd(self, a, b, y):
+    def add_pool2_fwd(self, a, b, y, leak=None, y_act=None):
         v = a + b if b is not None else a
         y.copy_(_nhwc(TF.avg_pool2d(_nchw(v), 2, 2)))
+        if y_act is not None:
+            self.prelu_fwd(y, leak, y_act)
 
     def pool2_bwd(self, gy, gx, accumulate=False):
         up = gy.repeat_interleave(2, dim=1).repeat_interleave(2, dim=2) * 0.25

@@ -60,6 +60,8 @@ CONV_CASES = [
     (5, 1, 1, 100, 512, 1, 1, 0, 1, 1),        # linear as a 1x1 conv
     (2, 9, 7, 8, 20, 3, 1, 1, 9, 7),           # SAME 3x3 stride 1, odd sizes, ragged channels
     (1, 12, 12, 16, 8, 7, 1, 3, 12, 12),       # 7x7 SAME (classifier h0 style)
+    (4, 6, 6, 512, 512, 3, 1, 0, 4, 4),        # encoder last block (few pixels, long K)
+    (4, 4, 4, 512, 512, 1, 1, 0, 4, 4),        # its 1x1 shortcut
 ]
 
 
@@ -263,6 +265,59 @@ def test_minmax(dev, ref, shape):
     both(dev, ref, "minmax_bwd", [x, st, gy], [shape], tol=5e-5)
 
 
+@pytest.mark.parametrize("shape", [(2, 8, 8, 40), (3, 16, 16, 8), (2, 32, 32, 128), (2, 4, 4, 12)])
+def test_mru_gate_fused(dev, ref, shape):
+    """eg_mru_gate_fwd / _bwd (the fused element-wise middle of an MRU unit) against the composition of the separate
+    reference ops, with tied extrema and zeros in the gate pre-activation."""
+    rs = np.random.RandomState(23)
+    N, C = shape[0], shape[-1]
+    cg, cgi, ht, img, g_hin, g_ht0 = (rnd(rs, *shape) for _ in range(6))
+    s = cg + cgi
+    flat = s.reshape(N, -1, C)
+    cg[0, 0, 0, :] += flat[0].max(0) + 0.5 - s[0, 0, 0, :]                 # two tied maxima in sample 0 ...
+    cg[0, 1, 1, :] += (cg[0, 0, 0, :] + cgi[0, 0, 0, :]) - s[0, 1, 1, :]
+    cg[1, 2, 2, :] = -cgi[1, 2, 2, :]                                      # ... and exact zeros (lrelu tie) in sample 1
+    leak = np.array([0.2], np.float32)
+    res = []
+    for o in (dev, ref):
+        CG, CGI, HT, IMG, L = (o.from_numpy(a) for a in (cg, cgi, ht, img, leak))
+        st, plus, hin = o.zeros((N, C, 4)), o.zeros(shape), o.zeros(shape)
+        o.mru_gate_fwd(CG, CGI, HT, IMG, L, st, plus, hin)
+        g_ht, g_img, g_cg, gl = o.from_numpy(g_ht0), o.zeros(shape), o.zeros(shape), o.zeros((1,))
+        o.mru_gate_bwd(plus, o.from_numpy(g_hin), IMG, CG, st, L, g_ht, g_img, g_cg, gl, False)
+        gl2 = o.from_numpy(np.array([2.0], np.float32))
+        g_ht2, g_img2, g_cg2 = o.from_numpy(g_ht0), o.zeros(shape), o.zeros(shape)
+        o.mru_gate_bwd(plus, o.from_numpy(g_hin), IMG, CG, st, L, g_ht2, g_img2, g_cg2, gl2, True)
+        res.append([o.to_numpy(t) for t in (CG, st, plus, hin, g_ht, g_img, g_cg, gl, gl2, g_cg2)])
+    for k, (g_, w_) in enumerate(zip(*res)):
+        close(g_, w_, 5e-5, f"mru_gate[{k}]")
+    assert (res[0][1][0, :, 3] == 2).all()                                  # both tied maxima counted
+
+
+def test_prelu_fused_variants(dev, ref):
+    rs = np.random.RandomState(24)
+    for shape in ((3, 8, 8, 16), (1, 3, 5, 7)):                             # vector body and scalar tail
+        x, gy, g0 = rnd(rs, *shape), rnd(rs, *shape), rnd(rs, *shape)
+        l1, l2 = np.array([0.2], np.float32), np.array([-0.3], np.float32)
+        res = []
+        for o in (dev, ref):
+            X, GY = o.from_numpy(x), o.from_numpy(gy)
+            y, y2, gx, gl = o.zeros(shape), o.zeros(shape), o.from_numpy(g0), o.zeros((1,))
+            o.prelu_fwd2(X, o.from_numpy(l1), y, o.from_numpy(l2), y2)
+            o.prelu_bwd(X, o.from_numpy(l1), GY, gx, gl, False, accumulate_gx=True)
+            res.append([o.to_numpy(t) for t in (y, y2, gx, gl)])
+        for g_, w_ in zip(*res):
+            close(g_, w_, 2e-5)
+    a, b = rnd(rs, 2, 6, 8, 8), rnd(rs, 2, 6, 8, 8)
+    res = []
+    for o in (dev, ref):
+        y, ya = o.zeros((2, 3, 4, 8)), o.zeros((2, 3, 4, 8))
+        o.add_pool2_fwd(o.from_numpy(a), o.from_numpy(b), y, o.from_numpy(np.array([0.25], np.float32)), ya)
+        res.append([o.to_numpy(y), o.to_numpy(ya)])
+    for g_, w_ in zip(*res):
+        close(g_, w_, 2e-5)
+
+
 def test_fma_mul_pool_mean_cslice(dev, ref):
     rs = np.random.RandomState(22)
     shape = (2, 6, 8, 5)
@@ -274,6 +329,12 @@ def test_fma_mul_pool_mean_cslice(dev, ref):
     gy = rnd(rs, 2, 3, 4, 5)
     both(dev, ref, "pool2_bwd", [gy], [shape], False)
     both(dev, ref, "pool2_bwd", [gy], [rnd(rs, *shape)], True)
+    a8, b8, gy8 = rnd(rs, 2, 6, 8, 8), rnd(rs, 2, 6, 8, 8), rnd(rs, 2, 3, 4, 8)      # float4 path
+    both(dev, ref, "fma3", [a8, b8, a8], [a8.shape])
+    both(dev, ref, "mul", [a8, b8], [a8.shape])
+    both(dev, ref, "add_pool2_fwd", [a8, b8], [(2, 3, 4, 8)])
+    both(dev, ref, "pool2_bwd", [gy8], [a8.shape], False)
+    both(dev, ref, "pool2_bwd", [gy8], [rnd(rs, *a8.shape)], True)
     both(dev, ref, "globalmean_fwd", [a], [(2, 5)])
     both(dev, ref, "globalmean_bwd", [rnd(rs, 2, 5)], [shape])
     res = []
