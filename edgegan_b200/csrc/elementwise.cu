@@ -13,15 +13,36 @@ inline unsigned grid1d(long long n, int per_block = TB) {
     long long g = (n + per_block - 1) / per_block;
     return (unsigned)(g < 1 ? 1 : g);
 }
-
-__global__ void act_fwd_k(const float* __restrict__ x, float* __restrict__ y, long long n, int act) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) y[i] = act_fwd(act, x[i]);
+// float4 streaming for the flat element-wise kernels: 16 bytes per access, grid-stride, scalar tail
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+__host__ __device__ __forceinline__ bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+inline unsigned grid4(long long n) {
+    long long g = (n / 4 + TB * 4 - 1) / (TB * 4);
+    if (g < 1) g = 1;
+    if (g > 148 * 16) g = 148 * 16;
+    return (unsigned)g;
 }
-__global__ void act_bwd_k(const float* __restrict__ x, const float* __restrict__ gy, float* __restrict__ gx,
-                          long long n, int act) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) gx[i] = gy[i] * act_grad(act, x[i]);
+#define EG_FLAT_LOOP(n, vec)                                                                                       \
+    const long long tid_ = (long long)blockIdx.x * blockDim.x + threadIdx.x, nt_ = (long long)gridDim.x * blockDim.x; \
+    const long long n4_ = (vec) ? (n) / 4 : 0
+
+__global__ void __launch_bounds__(TB) act_fwd_k(const float* __restrict__ x, float* __restrict__ y, long long n, int act, int vec) {
+    EG_FLAT_LOOP(n, vec);
+    for (long long i = tid_; i < n4_; i += nt_) {
+        const float4 v = ld4(x + 4 * i);
+        st4(y + 4 * i, make_float4(act_fwd(act, v.x), act_fwd(act, v.y), act_fwd(act, v.z), act_fwd(act, v.w)));
+    }
+    for (long long i = 4 * n4_ + tid_; i < n; i += nt_) y[i] = act_fwd(act, x[i]);
+}
+__global__ void __launch_bounds__(TB) act_bwd_k(const float* __restrict__ x, const float* __restrict__ gy, float* __restrict__ gx,
+                                                long long n, int act, int vec) {
+    EG_FLAT_LOOP(n, vec);
+    for (long long i = tid_; i < n4_; i += nt_) {
+        const float4 v = ld4(x + 4 * i), g = ld4(gy + 4 * i);
+        st4(gx + 4 * i, make_float4(g.x * act_grad(act, v.x), g.y * act_grad(act, v.y), g.z * act_grad(act, v.z), g.w * act_grad(act, v.w)));
+    }
+    for (long long i = 4 * n4_ + tid_; i < n; i += nt_) gx[i] = gy[i] * act_grad(act, x[i]);
 }
 
 // ---- legacy bicubic 2x (A = -0.75, no half-pixel offset, clamped borders) ---------------
@@ -102,9 +123,10 @@ __global__ void copy2d_k(const float* __restrict__ src, long long ss, float* __r
     const long long r = i / cols, c = i % cols;
     dst[r * ds + c] = src[r * ss + c];
 }
-__global__ void fill_k(float* dst, long long n, float v) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) dst[i] = v;
+__global__ void __launch_bounds__(TB) fill_k(float* dst, long long n, float v, int vec) {
+    EG_FLAT_LOOP(n, vec);
+    for (long long i = tid_; i < n4_; i += nt_) st4(dst + 4 * i, make_float4(v, v, v, v));
+    for (long long i = 4 * n4_ + tid_; i < n; i += nt_) dst[i] = v;
 }
 // dst[i] = lut[src[i]]: the loader uploads image bytes and the byte -> [-1, 1] table of utils.transform
 // (edgegan/utils/utils.py:160: x / 127.5 - 1); 16 bytes in, 64 bytes out per thread, table in shared memory
@@ -125,9 +147,15 @@ __global__ void u8_lut_f32_k(const uint8_t* __restrict__ src, const float* __res
         for (long long i = i0; i < n && i < i0 + 16; ++i) dst[i] = tab[src[i]];
     }
 }
-__global__ void axpby_k(const float* __restrict__ x, float* __restrict__ y, long long n, float a, float b) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) y[i] = a * x[i] + (b == 0.f ? 0.f : b * y[i]);
+__global__ void __launch_bounds__(TB) axpby_k(const float* __restrict__ x, float* __restrict__ y, long long n, float a, float b, int vec) {
+    EG_FLAT_LOOP(n, vec);
+    for (long long i = tid_; i < n4_; i += nt_) {
+        const float4 u = ld4(x + 4 * i);
+        float4 o = make_float4(a * u.x, a * u.y, a * u.z, a * u.w);
+        if (b != 0.f) { const float4 w = ld4(y + 4 * i); o.x += b * w.x; o.y += b * w.y; o.z += b * w.z; o.w += b * w.w; }
+        st4(y + 4 * i, o);
+    }
+    for (long long i = 4 * n4_ + tid_; i < n; i += nt_) y[i] = a * x[i] + (b == 0.f ? 0.f : b * y[i]);
 }
 
 // ---- WGAN-GP ---------------------------------------------------------------------------------------
@@ -358,14 +386,21 @@ __global__ void onehot_concat_k(const float* __restrict__ z, int zdim, int class
     else out[i] = ((int)z[(size_t)b * (zdim + 1) + zdim] == j - zdim) ? 1.f : 0.f;   // tf.cast(float->int32) truncates
 }
 
-__global__ void rmsprop_k(float* __restrict__ var, const float* __restrict__ grad, float* __restrict__ ms, long long n,
-                          float lr, float decay, float eps) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const float g = grad[i];
-    const float m = decay * ms[i] + (1.f - decay) * g * g;
-    ms[i] = m;
-    var[i] -= lr * g / sqrtf(m + eps);
+__device__ __forceinline__ void rmsprop1(float& v, float g, float& m, float lr, float decay, float eps) {
+    m = decay * m + (1.f - decay) * g * g;
+    v -= lr * g / sqrtf(m + eps);
+}
+__global__ void __launch_bounds__(TB) rmsprop_k(float* __restrict__ var, const float* __restrict__ grad, float* __restrict__ ms, long long n,
+                                                float lr, float decay, float eps, int vec) {
+    EG_FLAT_LOOP(n, vec);
+    for (long long i = tid_; i < n4_; i += nt_) {
+        const float4 g = ld4(grad + 4 * i);
+        float4 m = ld4(ms + 4 * i), v = ld4(var + 4 * i);
+        rmsprop1(v.x, g.x, m.x, lr, decay, eps); rmsprop1(v.y, g.y, m.y, lr, decay, eps);
+        rmsprop1(v.z, g.z, m.z, lr, decay, eps); rmsprop1(v.w, g.w, m.w, lr, decay, eps);
+        st4(ms + 4 * i, m); st4(var + 4 * i, v);
+    }
+    for (long long i = 4 * n4_ + tid_; i < n; i += nt_) rmsprop1(var[i], grad[i], ms[i], lr, decay, eps);
 }
 
 }  // namespace
@@ -376,12 +411,12 @@ extern "C" {
 
 int eg_act_fwd(const float* x, float* y, long long n, int act, void* stream) {
     EG_REQUIRE(x && y && n > 0);
-    act_fwd_k<<<grid1d(n), TB, 0, ST>>>(x, y, n, act);
+    act_fwd_k<<<grid4(n), TB, 0, ST>>>(x, y, n, act, al16(x) && al16(y));
     EG_CHECK_LAUNCH(); return 0;
 }
 int eg_act_bwd(const float* x_pre, const float* gy, float* gx, long long n, int act, void* stream) {
     EG_REQUIRE(x_pre && gy && gx && n > 0);
-    act_bwd_k<<<grid1d(n), TB, 0, ST>>>(x_pre, gy, gx, n, act);
+    act_bwd_k<<<grid4(n), TB, 0, ST>>>(x_pre, gy, gx, n, act, al16(x_pre) && al16(gy) && al16(gx));
     EG_CHECK_LAUNCH(); return 0;
 }
 int eg_bicubic_up2_fwd(const float* x, float* y, int N, int H, int W, int C, void* stream) {
@@ -402,7 +437,7 @@ int eg_copy2d(const float* src, long long src_stride, float* dst, long long dst_
 }
 int eg_fill(float* dst, long long n, float value, void* stream) {
     EG_REQUIRE(dst && n > 0);
-    fill_k<<<grid1d(n), TB, 0, ST>>>(dst, n, value);
+    fill_k<<<grid4(n), TB, 0, ST>>>(dst, n, value, al16(dst));
     EG_CHECK_LAUNCH(); return 0;
 }
 int eg_u8_lut_f32(const void* src, const float* lut, float* dst, long long n, void* stream) {
@@ -412,7 +447,7 @@ int eg_u8_lut_f32(const void* src, const float* lut, float* dst, long long n, vo
 }
 int eg_axpby(const float* x, float* y, long long n, float a, float b, void* stream) {
     EG_REQUIRE(x && y && n > 0);
-    axpby_k<<<grid1d(n), TB, 0, ST>>>(x, y, n, a, b);
+    axpby_k<<<grid4(n), TB, 0, ST>>>(x, y, n, a, b, al16(x) && al16(y));
     EG_CHECK_LAUNCH(); return 0;
 }
 int eg_gp_interpolate(const float* real, const float* fake, const float* alpha, float* xhat, int B, long long per,
@@ -519,7 +554,7 @@ int eg_onehot_concat(const float* z, int n, int zdim, int classes, float* out, v
 }
 int eg_rmsprop(float* var, const float* grad, float* ms, long long n, float lr, float decay, float eps, void* stream) {
     EG_REQUIRE(var && grad && ms && n > 0);
-    rmsprop_k<<<grid1d(n), TB, 0, ST>>>(var, grad, ms, n, lr, decay, eps);
+    rmsprop_k<<<grid4(n), TB, 0, ST>>>(var, grad, ms, n, lr, decay, eps, al16(var) && al16(grad) && al16(ms));
     EG_CHECK_LAUNCH(); return 0;
 }
 
