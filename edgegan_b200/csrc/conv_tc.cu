@@ -235,8 +235,22 @@ struct TcPhase {          // one GEMM problem (a dgrad parity phase, or the whol
                                       // (sn, sh, sw are the same in every phase; only out_off differs)
 };
 
+// Thin-channel forward (Ci <= 8: the image-side layers): one filter tap is 12-32 bytes of K, below a TMA box, so the
+// conditioning warps GATHER their accumulator row's im2col slice straight from the NHWC input instead (K = the whole
+// receptive field KH*KW*Ci, padded to a multiple of 32) -- no patch matrix is ever written.  Rows are consecutive
+// output pixels q = (n*OH + oh)*OW + ow; column j = (kh*KW + kw)*Ci + ci.
+constexpr int kGatherMaxK = 160;
+struct TcGather {
+    const float* x;
+    int on;
+    int H, W, C, OH, OW, KH, KW, stride, pad_t, pad_l, K;
+    long long P;                      // output pixels
+    FastDiv fow, foh;
+};
+
 struct TcParams {
     TcPhase ph[4];
+    TcGather g;
     int nphases;
     int bw, bh, bn;       // pixel box: bw*bh*bn == 128
     int BN;               // channel tile (UMMA N)
@@ -308,7 +322,7 @@ conv_tc_kmajor(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
     // stage: [A landing tile][B][B_lo (3x)]
     const uint32_t b_off = a_bytes, b_lo_off = b_off + b_bytes;
     const uint32_t stage_bytes = a_bytes + (mode == 3 ? 2 : 1) * b_bytes;
-    const uint32_t tx_bytes = stage_bytes;
+    const uint32_t tx_bytes = P.g.on ? stage_bytes - a_bytes : stage_bytes;      // gather mode: only the filter arrives by TMA
     const uint32_t stg_base = smem_base + kStages * stage_bytes;   // 4 x 4 KB output staging tiles (one per epilogue warp)
 
     __shared__ __align__(8) uint64_t full_bar[kStages];      // TMA bytes landed
@@ -317,8 +331,19 @@ conv_tc_kmajor(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
     __shared__ __align__(8) uint64_t acc_full_bar[2];        // chunk accumulator complete (tcgen05.commit)
     __shared__ __align__(8) uint64_t acc_empty_bar[2];       // chunk accumulator drained (4 warp arrivals)
     __shared__ uint32_t tmem_base_slot;
+    __shared__ int gtab[kGatherMaxK];                        // gather mode: column j -> kh << 24 | kw << 16 | element offset
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (P.g.on) {
+        for (int j = threadIdx.x; j < kGatherMaxK; j += blockDim.x) {
+            int tv = 31 << 24;                               // row 31 never exists: padding columns read as zero
+            if (j < P.g.K) {
+                const int tap = j / P.g.C, ci = j - tap * P.g.C, kh = tap / P.g.KW, kw = tap - kh * P.g.KW;
+                tv = (kh << 24) | (kw << 16) | ((kh * P.g.W + kw) * P.g.C + ci);
+            }
+            gtab[j] = tv;
+        }
+    }
     // TMEM columns: [0, 2*BN) two chunk accumulators, then kStages x (32 hi + 32 lo) A columns
     const uint32_t a_col0 = (uint32_t)(2 * BN);
     const int need_cols = 2 * BN + kStages * 64;
@@ -358,7 +383,7 @@ conv_tc_kmajor(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
                     const uint32_t sa = smem_base + stage * stage_bytes;
                     const uint32_t fb = smem_u32(&full_bar[stage]);
                     mbar_expect_tx(fb, tx_bytes);
-                    tma_load_4d(sa, &maps.a[tp.amap], fb, kc * 32, t.w0 + tp.ax, t.h0 + tp.ay, t.n0);
+                    if (!P.g.on) tma_load_4d(sa, &maps.a[tp.amap], fb, kc * 32, t.w0 + tp.ax, t.h0 + tp.ay, t.n0);
                     tma_load_3d(sa + b_off, &maps.b[0], fb, kc * 32, t.col0, tp.bsel);
                     if (mode == 3) tma_load_3d(sa + b_lo_off, &maps.b[0], fb, kc * 32, t.col0, tp.bsel + P.b_lo_tap_off);
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -420,16 +445,43 @@ conv_tc_kmajor(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
         for (int id = blockIdx.x; id < total_ids; id += gridDim.x) {
             if (!get_item(P, id, t)) continue;
             const int niter = t.niter;
+            // gather mode: this thread's output pixel and the validity masks of its KH x KW window
+            const float* gbase = nullptr;
+            uint32_t hmask = 0, wmask = 0;
+            if (P.g.on) {
+                const long long pix = (long long)t.n0 + arow;
+                if (pix < P.g.P) {
+                    const uint32_t r1 = fd_div((uint32_t)pix, P.g.fow), ow = (uint32_t)pix - r1 * (uint32_t)P.g.OW;
+                    const uint32_t n = fd_div(r1, P.g.foh), oh = r1 - n * (uint32_t)P.g.OH;
+                    const int h0 = (int)oh * P.g.stride - P.g.pad_t, w0 = (int)ow * P.g.stride - P.g.pad_l;
+                    for (int k = 0; k < P.g.KH; ++k) hmask |= (uint32_t)(h0 + k >= 0 && h0 + k < P.g.H) << k;
+                    for (int k = 0; k < P.g.KW; ++k) wmask |= (uint32_t)(w0 + k >= 0 && w0 + k < P.g.W) << k;
+                    gbase = P.g.x + (((long long)n * P.g.H + h0) * P.g.W + w0) * P.g.C;
+                }
+            }
             for (int it = 0; it < niter; ++it) {
                 if ((stage & 1) != grp) { if (++stage == kStages) { stage = 0; phase ^= 1; } continue; }
-                mbar_wait(smem_u32(&full_bar[stage]), phase);
                 const uint32_t sa = smem_base + stage * stage_bytes;
                 const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + a_col0 + (uint32_t)(stage * 64);
                 uint32_t hi[32];
+                if (P.g.on) {
+                    // the loads are issued before the wait: the filter stage (and the TMEM slot it guards) is usually
+                    // not free yet, so the global-memory latency hides behind it
+                    const int j0 = (t.it0 + it) * 32;
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {                    // 8 x 16 B at the swizzled positions of row arow
-                    const uint4 v = lds128(sa + (uint32_t)arow * 128u + (uint32_t)((j ^ (arow & 7)) << 4));
-                    hi[4 * j] = v.x; hi[4 * j + 1] = v.y; hi[4 * j + 2] = v.z; hi[4 * j + 3] = v.w;
+                    for (int e = 0; e < 32; ++e) {
+                        const int tv = gtab[j0 + e];
+                        const bool ok = ((hmask >> (tv >> 24)) & (wmask >> ((tv >> 16) & 255)) & 1u) != 0;
+                        hi[e] = ok ? __float_as_uint(__ldg(gbase + (tv & 0xffff))) : 0u;
+                    }
+                    mbar_wait(smem_u32(&full_bar[stage]), phase);
+                } else {
+                    mbar_wait(smem_u32(&full_bar[stage]), phase);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {                    // 8 x 16 B at the swizzled positions of row arow
+                        const uint4 v = lds128(sa + (uint32_t)arow * 128u + (uint32_t)((j ^ (arow & 7)) << 4));
+                        hi[4 * j] = v.x; hi[4 * j + 1] = v.y; hi[4 * j + 2] = v.z; hi[4 * j + 3] = v.w;
+                    }
                 }
                 if (P.dbg & 2) {
                     // timing experiment: operands left unwritten
@@ -837,6 +889,18 @@ __global__ void prep_filter_k(const float* __restrict__ w, float* __restrict__ h
     }
 }
 
+// gather-mode filter: w [K][Co] (HWIO flattened) -> K-major [Co][Kpad] hi copy followed by the lo copy, zero padded
+__global__ void prep_filter_gather_k(const float* __restrict__ w, float* __restrict__ hi, float* __restrict__ lo, int K,
+                                     int Kpad, int Co, int mode) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= Co * Kpad) return;
+    const int co = i / Kpad, j = i - co * Kpad;
+    const float v = j < K ? __ldg(w + (size_t)j * Co + co) : 0.f;
+    const uint32_t u = __float_as_uint(v);
+    if (mode == 3) { hi[i] = v; lo[i] = __uint_as_float(tf32_lo(u)); }
+    else hi[i] = __uint_as_float(tf32_rna(u));
+}
+
 // ---------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------
@@ -1112,7 +1176,18 @@ static bool thin_fwd(const eg_conv_shape* s) { return (g_dbg[5] & 1) && eg_thin_
 static bool thin_bwd_data(const eg_conv_shape* s) { return (g_dbg[5] & 2) && eg_thin_supported_bwd_data(s); }
 static bool thin_bwd_weight(const eg_conv_shape* s) { return (g_dbg[5] & 4) && eg_thin_supported_bwd_weight(s); }
 
+// g_dbg[5] bit 3 turns the gather route off (tests compare the routes)
+static bool gather_fwd(const eg_conv_shape* s) {
+    if (g_dbg[5] & 8) return false;
+    if (s->Ci < 1 || s->Ci > 8 || s->Co % 64) return false;
+    if (s->KH > 8 || s->KW > 8 || s->KH * s->KW * s->Ci > kGatherMaxK) return false;
+    if (((s->KH - 1) * s->W + s->KW) * s->Ci >= 65536) return false;              // table offsets are 16 bits
+    if ((long long)s->N * s->OH * s->OW >= (1ll << 31)) return false;
+    return s->stride >= 1;
+}
+
 int eg_tc_supported_fwd(const eg_conv_shape* s) {
+    if (gather_fwd(s)) return 1;
     if (thin_fwd(s)) return 1;
     if (s->Ci % 32 || s->Co % 64) return 0;
     if (s->stride != 1 && s->stride != 2) return 0;
@@ -1204,8 +1279,53 @@ static int launch_kmajor(const TcMaps& maps, TcParams& P, int gx, int gy, int mo
 }
 
 // `epi` (may be NULL): fused epilogue; returns 1 instead of 0 when it was NOT applied (thin route): the caller runs it
+// thin-channel forward, A gathered by the conditioning warps (TcGather): y[P, Co] = im2col(x)[P, Kpad] . w[Kpad, Co]
+static int tc_conv2d_fwd_gather(const eg_conv_shape* s, const float* x, const float* w, const float* bias, float* y,
+                                int three_x, cudaStream_t st, const EgEpi* epi) {
+    if (int r = get_encode()) return r;
+    if (int r = set_attrs()) return r;
+    const int mode = three_x ? 3 : 1;
+    const int K = s->KH * s->KW * s->Ci, Kpad = (K + 31) / 32 * 32;
+    const long long Ppix = (long long)s->N * s->OH * s->OW;
+    float* wt = nullptr;
+    if (int r = get_scratch(st, sizeof(float) * (size_t)2 * s->Co * Kpad, &wt, 3)) return r;
+    prep_filter_gather_k<<<eg_ceil_div((long long)s->Co * Kpad, 256), 256, 0, st>>>(w, wt, wt + (size_t)s->Co * Kpad, K, Kpad, s->Co, mode);
+    EG_CHECK_LAUNCH();
+    TcMaps maps;
+    TcParams P{};
+    P.bw = 1; P.bh = 1; P.bn = 128;
+    P.BN = pick_bn(s->Co);
+    P.mode = mode; P.b_lo_tap_off = 1; P.dbg = g_dbg[3];
+    if (int r = make_filter_map(&maps.b[0], wt, Kpad, s->Co, 2, P.BN)) return r;
+    for (int i = 1; i < 4; ++i) maps.b[i] = maps.b[0];
+    for (int i = 0; i < 4; ++i) maps.a[i] = maps.b[0];       // never used for loads in gather mode (prefetch only)
+    P.nphases = 1; P.ldn = s->Co; P.bias = bias; P.out = y;
+    TcPhase& ph = P.ph[0];
+    ph.ntaps = 1; ph.kchunks = Kpad / 32;
+    TcTap t0; t0.amap = 0; t0.ax = 0; t0.ay = 0; t0.bsel = 0;
+    ph.taps[0] = t0;
+    ph.ext_w = 1; ph.ext_h = 1; ph.ext_n = (int)Ppix;
+    ph.tiles_w = 1; ph.tiles_h = 1; ph.tiles_n = eg_ceil_div(Ppix, 128);
+    ph.out_off = 0; ph.sw = s->Co; ph.sh = s->Co; ph.sn = s->Co;
+    P.ksplit = 1;
+    TcGather& g = P.g;
+    g.x = x; g.on = 1; g.H = s->H; g.W = s->W; g.C = s->Ci; g.OH = s->OH; g.OW = s->OW; g.KH = s->KH; g.KW = s->KW;
+    g.stride = s->stride; g.pad_t = s->pad_t; g.pad_l = s->pad_l; g.K = K; g.P = Ppix;
+    auto fd = [&](int d, long long nmax) {
+        FastDiv f; f.d = (uint32_t)d;
+        f.m = (d > 1 && nmax * d < (1ll << 32)) ? (uint32_t)(((1ull << 32) + (uint32_t)d - 1) / (uint32_t)d) : 0u;
+        return f;
+    };
+    g.fow = fd(s->OW, Ppix); g.foh = fd(s->OH, Ppix);
+    const int unfused = set_epilogue(P, epi);
+    launch_kmajor(maps, P, ph.tiles_n, s->Co / P.BN, mode, st);
+    EG_CHECK_LAUNCH();
+    return unfused;
+}
+
 int eg_tc_conv2d_fwd(const eg_conv_shape* s, const float* x, const float* w, const float* bias, float* y, int three_x,
                      cudaStream_t st, const EgEpi* epi) {
+    if (gather_fwd(s)) return tc_conv2d_fwd_gather(s, x, w, bias, y, three_x, st, epi);
     if (thin_fwd(s)) {
         if (int r = eg_thin_conv2d_fwd(s, x, w, bias, y, three_x, st)) return r;
         return (epi && epi->mode != EG_EPI_NONE) ? 1 : 0;

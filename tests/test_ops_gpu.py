@@ -272,11 +272,10 @@ def test_mru_gate_fused(dev, ref, shape):
     rs = np.random.RandomState(23)
     N, C = shape[0], shape[-1]
     cg, cgi, ht, img, g_hin, g_ht0 = (rnd(rs, *shape) for _ in range(6))
-    s = cg + cgi
-    flat = s.reshape(N, -1, C)
-    cg[0, 0, 0, :] += flat[0].max(0) + 0.5 - s[0, 0, 0, :]                 # two tied maxima in sample 0 ...
-    cg[0, 1, 1, :] += (cg[0, 0, 0, :] + cgi[0, 0, 0, :]) - s[0, 1, 1, :]
-    cg[1, 2, 2, :] = -cgi[1, 2, 2, :]                                      # ... and exact zeros (lrelu tie) in sample 1
+    top = (cg + cgi).reshape(N, -1, C)[0].max(0) + 0.5
+    cgi[0, 0, 0, :] = cgi[0, 1, 1, :] = 0.0                                # two tied maxima in sample 0 (exact in fp32
+    cg[0, 0, 0, :] = cg[0, 1, 1, :] = top                                  # and in fp64: the other summand is zero) ...
+    cg[1, 2, 2, :] = cgi[1, 2, 2, :] = 0.0                                 # ... and exact zeros (lrelu tie) in sample 1
     leak = np.array([0.2], np.float32)
     res = []
     for o in (dev, ref):

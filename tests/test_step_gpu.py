@@ -130,7 +130,7 @@ def test_full_14class_step_batch8_on_example_images():
     B = 8
     ocfg, v, u, m, ops = make(B, True, "tc3x", seed=5)
     inp = example_inputs(ocfg, seed=41)
-    stats, fails = teacher_forced_step(m, ops, ocfg, v, u, inp, grad_tol, sens_samples=1)
+    stats, fails = teacher_forced_step(m, ops, ocfg, v, u, inp, grad_tol, sens_samples=3, run_level=True)
     assert len(stats) == 7
     nets, bad = drift_check(m, ocfg, v, u, inp)
     report("14-class batch 8 whole step on the reference's example images [tc3x]", stats, nets)
@@ -145,7 +145,7 @@ def test_config2_whole_step_at_batch_64():
     B = 64
     ocfg, v, u, m, ops = make(B, False, "tc3x", seed=13)
     inp = O.make_inputs(ocfg, seed=17)
-    stats, fails = teacher_forced_step(m, ops, ocfg, v, u, inp, grad_tol, sens_samples=1)
+    stats, fails = teacher_forced_step(m, ops, ocfg, v, u, inp, grad_tol, sens_samples=2, run_level=True)
     report("single-class batch 64 (BASELINE configs[1]) whole step [tc3x]", stats)
     assert not fails, fails[:5]
 
