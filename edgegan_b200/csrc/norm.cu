@@ -6,6 +6,8 @@
 // Reference: nn/modules/normalization.py:10-29.
 #include "common.cuh"
 
+#include <initializer_list>
+
 namespace {
 
 constexpr int CG = 32;   // channels per block (one 128-byte line of an NHWC row)
@@ -232,6 +234,196 @@ instnorm_bwd_v4(const float* __restrict__ x, const float* __restrict__ stats, co
 }
 
 // ---------------------------------------------------------------------------------------------------
+// Shared-memory-resident variants: the (sample, channel-group) slab is read from HBM exactly ONCE, parked in shared
+// memory (as the centred value / masked cotangent the later passes need), and every further pass runs out of shared
+// memory.  The multi-pass kernels above re-read the slab from L2 two to three times per tensor, which made the norms
+// run at ~22 % of the HBM roofline (r01 launch list); here the traffic is the algorithmic minimum: fwd 4 + 4 B/element,
+// bwd 8 + 4 (+4 addend), bwd2 12 + 8.  Block = COLS float4 columns x (512 / COLS) rows; the channel-group width
+// (32 / 16 / 8 channels = 128 / 64 / 32-byte rows) is chosen so that the slab(s) fit in 200 KB.
+constexpr int kSmThreads = 512;
+constexpr size_t kSmCap = 200 * 1024;
+
+__device__ __forceinline__ float4 f4z() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+__device__ __forceinline__ float4 shfl_xor4(float4 v, int o) {
+    return make_float4(__shfl_xor_sync(0xffffffffu, v.x, o), __shfl_xor_sync(0xffffffffu, v.y, o),
+                       __shfl_xor_sync(0xffffffffu, v.z, o), __shfl_xor_sync(0xffffffffu, v.w, o));
+}
+// sum of v over all rows of the block, per float4 column; result in every thread.  red: [16 warps][8] float4
+__device__ __forceinline__ float4 colsum4(float4 v, float4 (*red)[8], int cols, int tx) {
+    for (int o = cols; o < 32; o <<= 1) { const float4 t = shfl_xor4(v, o); v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w; }
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    __syncthreads();
+    if (lane < cols) red[warp][lane] = v;
+    __syncthreads();
+    float4 s = f4z();
+#pragma unroll
+    for (int w = 0; w < kSmThreads / 32; ++w) { const float4 t = red[w][tx]; s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w; }
+    return s;
+}
+
+__global__ void __launch_bounds__(kSmThreads)
+instnorm_fwd_sm(const float* __restrict__ x, float* __restrict__ y, float* __restrict__ stats, int P, int C, float eps,
+                int act, int cols) {
+    extern __shared__ float4 slab[];                         // [P][cols]
+    __shared__ float4 red[kSmThreads / 32][8];
+    const int rows = kSmThreads / cols, tx = threadIdx.x % cols, ty = threadIdx.x / cols;
+    const int n = blockIdx.y, c = (blockIdx.x * cols + tx) * 4;
+    const size_t pitch = C / 4;
+    const float4* xp = reinterpret_cast<const float4*>(x + (size_t)n * P * C + c);
+    float4 a = f4z();
+    for (int p = ty; p < P; p += rows) {
+        const float4 t = __ldg(xp + p * pitch);
+        slab[p * cols + tx] = t;
+        a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w;
+    }
+    a = colsum4(a, red, cols, tx);
+    const float4 mean = make_float4(a.x / P, a.y / P, a.z / P, a.w / P);
+    a = f4z();
+    for (int p = ty; p < P; p += rows) {
+        const float4 t = slab[p * cols + tx];
+        float d;
+        d = t.x - mean.x; a.x = fmaf(d, d, a.x); d = t.y - mean.y; a.y = fmaf(d, d, a.y);
+        d = t.z - mean.z; a.z = fmaf(d, d, a.z); d = t.w - mean.w; a.w = fmaf(d, d, a.w);
+    }
+    a = colsum4(a, red, cols, tx);
+    const float4 sd = make_float4(sqrtf(a.x / P), sqrtf(a.y / P), sqrtf(a.z / P), sqrtf(a.w / P));
+    const float4 r = make_float4(1.f / (sd.x + eps), 1.f / (sd.y + eps), 1.f / (sd.z + eps), 1.f / (sd.w + eps));
+    if (ty == 0) {
+        float* st = stats + ((size_t)n * C + c) * 2;
+        *reinterpret_cast<float4*>(st) = make_float4(mean.x, sd.x, mean.y, sd.y);
+        *reinterpret_cast<float4*>(st + 4) = make_float4(mean.z, sd.z, mean.w, sd.w);
+    }
+    float4* yp = reinterpret_cast<float4*>(y + (size_t)n * P * C + c);
+    for (int p = ty; p < P; p += rows) {
+        const float4 t = slab[p * cols + tx];
+        yp[p * pitch] = make_float4(act_fwd(act, (t.x - mean.x) * r.x), act_fwd(act, (t.y - mean.y) * r.y),
+                                    act_fwd(act, (t.z - mean.z) * r.z), act_fwd(act, (t.w - mean.w) * r.w));
+    }
+}
+
+__global__ void __launch_bounds__(kSmThreads)
+instnorm_bwd_sm(const float* __restrict__ x, const float* __restrict__ stats, const float* __restrict__ gy,
+                const float* __restrict__ addend, float* __restrict__ gx, int P, int C, float eps, int act, int cols) {
+    extern __shared__ float4 slab[];                         // [2][P][cols]: centred x, masked cotangent
+    __shared__ float4 red[kSmThreads / 32][8];
+    const int rows = kSmThreads / cols, tx = threadIdx.x % cols, ty = threadIdx.x / cols;
+    const int n = blockIdx.y, c = (blockIdx.x * cols + tx) * 4;
+    const size_t base = (size_t)n * P * C + c, pitch = C / 4;
+    const float4* xp = reinterpret_cast<const float4*>(x + base);
+    const float4* gp = reinterpret_cast<const float4*>(gy + base);
+    float4* scc = slab;
+    float4* sgn = slab + (size_t)P * cols;
+    const Stat4 s = load_stats4(stats, (size_t)n * C + c, eps);
+    float4 v0 = f4z(), v1 = f4z();
+    for (int p = ty; p < P; p += rows) {
+        const float4 t = __ldg(xp + p * pitch), g = __ldg(gp + p * pitch);
+        float4 cc, gn;
+        cc.x = t.x - s.mean.x; gn.x = g.x * act_grad(act, cc.x * s.r.x); v0.x += gn.x; v1.x = fmaf(gn.x, cc.x, v1.x);
+        cc.y = t.y - s.mean.y; gn.y = g.y * act_grad(act, cc.y * s.r.y); v0.y += gn.y; v1.y = fmaf(gn.y, cc.y, v1.y);
+        cc.z = t.z - s.mean.z; gn.z = g.z * act_grad(act, cc.z * s.r.z); v0.z += gn.z; v1.z = fmaf(gn.z, cc.z, v1.z);
+        cc.w = t.w - s.mean.w; gn.w = g.w * act_grad(act, cc.w * s.r.w); v0.w += gn.w; v1.w = fmaf(gn.w, cc.w, v1.w);
+        scc[p * cols + tx] = cc; sgn[p * cols + tx] = gn;
+    }
+    v0 = colsum4(v0, red, cols, tx);
+    v1 = colsum4(v1, red, cols, tx);
+    const float4 mg = make_float4(v0.x / P, v0.y / P, v0.z / P, v0.w / P);
+    const float4 kq = make_float4(s.r.x * s.r.x / s.sd.x * (v1.x / P), s.r.y * s.r.y / s.sd.y * (v1.y / P),
+                                  s.r.z * s.r.z / s.sd.z * (v1.z / P), s.r.w * s.r.w / s.sd.w * (v1.w / P));
+    const float4* ap = addend ? reinterpret_cast<const float4*>(addend + base) : nullptr;
+    float4* op = reinterpret_cast<float4*>(gx + base);
+    for (int p = ty; p < P; p += rows) {
+        const float4 cc = scc[p * cols + tx], gn = sgn[p * cols + tx];
+        float4 o = make_float4(s.r.x * (gn.x - mg.x) - kq.x * cc.x, s.r.y * (gn.y - mg.y) - kq.y * cc.y,
+                               s.r.z * (gn.z - mg.z) - kq.z * cc.z, s.r.w * (gn.w - mg.w) - kq.w * cc.w);
+        if (ap) { const float4 a = __ldg(ap + p * pitch); o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w; }
+        op[p * pitch] = o;
+    }
+}
+
+// second-order term of the gradient penalty (same formulas as instnorm_bwd2_k: centred second moments)
+__global__ void __launch_bounds__(kSmThreads)
+instnorm_bwd2_sm(const float* __restrict__ x, const float* __restrict__ stats, const float* __restrict__ gy,
+                 const float* __restrict__ t, float* __restrict__ out_gy, float* __restrict__ out_x, int P, int C,
+                 float eps, int act, int cols) {
+    extern __shared__ float4 slab[];                         // [3][P][cols]: centred x, masked cotangent, tangent
+    __shared__ float4 red[kSmThreads / 32][8];
+    const int rows = kSmThreads / cols, tx = threadIdx.x % cols, ty = threadIdx.x / cols;
+    const int n = blockIdx.y, c = (blockIdx.x * cols + tx) * 4;
+    const size_t base = (size_t)n * P * C + c, pitch = C / 4;
+    const float4* xp = reinterpret_cast<const float4*>(x + base);
+    const float4* gp = reinterpret_cast<const float4*>(gy + base);
+    const float4* tp = reinterpret_cast<const float4*>(t + base);
+    float4* scc = slab;
+    float4* sgn = slab + (size_t)P * cols;
+    float4* stt = slab + (size_t)2 * P * cols;
+    const Stat4 s = load_stats4(stats, (size_t)n * C + c, eps);
+    float4 a0 = f4z(), a1 = f4z();
+    for (int p = ty; p < P; p += rows) {
+        const float4 xv = __ldg(xp + p * pitch), g = __ldg(gp + p * pitch), tt = __ldg(tp + p * pitch);
+        float4 cc, gn;
+        cc.x = xv.x - s.mean.x; gn.x = g.x * act_grad(act, cc.x * s.r.x);
+        cc.y = xv.y - s.mean.y; gn.y = g.y * act_grad(act, cc.y * s.r.y);
+        cc.z = xv.z - s.mean.z; gn.z = g.z * act_grad(act, cc.z * s.r.z);
+        cc.w = xv.w - s.mean.w; gn.w = g.w * act_grad(act, cc.w * s.r.w);
+        a0.x += gn.x; a0.y += gn.y; a0.z += gn.z; a0.w += gn.w;
+        a1.x += tt.x; a1.y += tt.y; a1.z += tt.z; a1.w += tt.w;
+        scc[p * cols + tx] = cc; sgn[p * cols + tx] = gn; stt[p * cols + tx] = tt;
+    }
+    a0 = colsum4(a0, red, cols, tx);
+    a1 = colsum4(a1, red, cols, tx);
+    const float4 mg = make_float4(a0.x / P, a0.y / P, a0.z / P, a0.w / P), mt = make_float4(a1.x / P, a1.y / P, a1.z / P, a1.w / P);
+    float4 b0 = f4z(), b1 = f4z(), b2 = f4z();                // sum gn*c, sum t*c, sum (t-mt)*(gn-mg)
+    for (int p = ty; p < P; p += rows) {
+        const float4 cc = scc[p * cols + tx], gn = sgn[p * cols + tx], tt = stt[p * cols + tx];
+        b0.x = fmaf(gn.x, cc.x, b0.x); b1.x = fmaf(tt.x, cc.x, b1.x); b2.x = fmaf(tt.x - mt.x, gn.x - mg.x, b2.x);
+        b0.y = fmaf(gn.y, cc.y, b0.y); b1.y = fmaf(tt.y, cc.y, b1.y); b2.y = fmaf(tt.y - mt.y, gn.y - mg.y, b2.y);
+        b0.z = fmaf(gn.z, cc.z, b0.z); b1.z = fmaf(tt.z, cc.z, b1.z); b2.z = fmaf(tt.z - mt.z, gn.z - mg.z, b2.z);
+        b0.w = fmaf(gn.w, cc.w, b0.w); b1.w = fmaf(tt.w, cc.w, b1.w); b2.w = fmaf(tt.w - mt.w, gn.w - mg.w, b2.w);
+    }
+    b0 = colsum4(b0, red, cols, tx);
+    b1 = colsum4(b1, red, cols, tx);
+    b2 = colsum4(b2, red, cols, tx);
+    float4 kap, ku, kqv, coef;
+#define EG_B2C(f) { const float q = b0.f / P, u = b1.f / P, w = b2.f / P, r = s.r.f, sd = s.sd.f; kap.f = r * r / sd; ku.f = kap.f * u; \
+                    kqv.f = kap.f * q; coef.f = -kap.f * w + (2.f * r * r * r / (sd * sd) + r * r / (sd * sd * sd)) * q * u; }
+    EG_B2C(x) EG_B2C(y) EG_B2C(z) EG_B2C(w)
+#undef EG_B2C
+    float4* og = reinterpret_cast<float4*>(out_gy + base);
+    float4* ox = reinterpret_cast<float4*>(out_x + base);
+    for (int p = ty; p < P; p += rows) {
+        const float4 cc = scc[p * cols + tx], gn = sgn[p * cols + tx], tt = stt[p * cols + tx];
+        float4 o1, o2;
+#define EG_B2O(f) { const float ag = act_grad(act, cc.f * s.r.f); o1.f = ag * (s.r.f * (tt.f - mt.f) - ku.f * cc.f); \
+                    o2.f = cc.f * coef.f - ku.f * (gn.f - mg.f) - kqv.f * (tt.f - mt.f); }
+        EG_B2O(x) EG_B2O(y) EG_B2O(z) EG_B2O(w)
+#undef EG_B2O
+        og[p * pitch] = o1; ox[p * pitch] = o2;
+    }
+}
+
+// channel-group width (in float4 columns) such that `tensors` slabs of P rows fit in shared memory; 0: use the
+// multi-pass kernels
+int sm_cols(int P, int C, int tensors) {
+    for (int cols = 8; cols >= 2; cols >>= 1)
+        if (C % (cols * 4) == 0 && (size_t)P * cols * 16 * tensors <= kSmCap) return cols;
+    return 0;
+}
+bool g_sm_attr = false;
+int sm_attrs() {
+    if (g_sm_attr) return 0;
+    cudaError_t e = cudaFuncSetAttribute(instnorm_fwd_sm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmCap);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(instnorm_bwd_sm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmCap);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(instnorm_bwd2_sm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmCap);
+    if (e != cudaSuccess) return eg_fail(e, __FILE__, __LINE__);
+    g_sm_attr = true;
+    return 0;
+}
+bool al16all(std::initializer_list<const void*> ps) {
+    for (const void* p : ps) if (reinterpret_cast<uintptr_t>(p) & 15) return false;
+    return true;
+}
+
+// ---------------------------------------------------------------------------------------------------
 // batch norm over rows of x[R, C]
 
 __global__ void __launch_bounds__(CG * RY)
@@ -301,6 +493,12 @@ extern "C" {
 
 int eg_instnorm_fwd(const float* x, float* y, float* stats, int N, int P, int C, float eps, int act, void* stream) {
     EG_REQUIRE(x && y && stats && N > 0 && P > 0 && C > 0 && N <= 65535);
+    if (const int cols = al16all({x, y, stats}) ? sm_cols(P, C, 1) : 0) {
+        if (int r = sm_attrs()) return r;
+        instnorm_fwd_sm<<<dim3(C / (cols * 4), N), kSmThreads, (size_t)P * cols * 16, (cudaStream_t)stream>>>(x, y, stats, P, C, eps, act, cols);
+        EG_CHECK_LAUNCH();
+        return 0;
+    }
     if (C % 4 == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(stats)) & 15) == 0) {
         dim3 grid(eg_ceil_div(C, VQ * 4), N), block(VQ, VR);
         instnorm_fwd_v4<<<grid, block, 0, (cudaStream_t)stream>>>(x, y, stats, P, C, eps, act);
@@ -316,6 +514,12 @@ int eg_instnorm_fwd(const float* x, float* y, float* stats, int N, int P, int C,
 int eg_instnorm_bwd(const float* x, const float* stats, const float* gy, const float* addend, float* gx, int N,
                     int P, int C, float eps, int act, void* stream) {
     EG_REQUIRE(x && stats && gy && gx && N > 0 && P > 0 && C > 0 && N <= 65535);
+    if (const int cols = al16all({x, stats, gy, addend, gx}) ? sm_cols(P, C, 2) : 0) {
+        if (int r = sm_attrs()) return r;
+        instnorm_bwd_sm<<<dim3(C / (cols * 4), N), kSmThreads, (size_t)P * cols * 32, (cudaStream_t)stream>>>(x, stats, gy, addend, gx, P, C, eps, act, cols);
+        EG_CHECK_LAUNCH();
+        return 0;
+    }
     if (C % 4 == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(gy) | reinterpret_cast<uintptr_t>(gx) |
                         reinterpret_cast<uintptr_t>(stats) | reinterpret_cast<uintptr_t>(addend)) & 15) == 0) {
         dim3 grid(eg_ceil_div(C, VQ * 4), N), block(VQ, VR);
@@ -333,6 +537,12 @@ int eg_instnorm_bwd2(const float* x, const float* stats, const float* gy, const 
                      float* out_x, int N, int P, int C, float eps, int act, void* stream) {
     EG_REQUIRE(x && stats && gy && t && out_gy && out_x && N > 0 && P > 0 && C > 0 && N <= 65535);
     EG_REQUIRE(act != EG_ACT_TANH);   // second derivative of the activation is taken as zero
+    if (const int cols = al16all({x, stats, gy, t, out_gy, out_x}) ? sm_cols(P, C, 3) : 0) {
+        if (int r = sm_attrs()) return r;
+        instnorm_bwd2_sm<<<dim3(C / (cols * 4), N), kSmThreads, (size_t)P * cols * 48, (cudaStream_t)stream>>>(x, stats, gy, t, out_gy, out_x, P, C, eps, act, cols);
+        EG_CHECK_LAUNCH();
+        return 0;
+    }
     dim3 grid(eg_ceil_div(C, CG), N), block(CG, RY);
     instnorm_bwd2_k<<<grid, block, 0, (cudaStream_t)stream>>>(x, stats, gy, t, out_gy, out_x, P, C, eps, act);
     EG_CHECK_LAUNCH();

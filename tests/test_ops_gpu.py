@@ -90,7 +90,10 @@ def test_conv_large_splitk(dev, ref):
     both(dev, ref, "conv_bwd_weight", [x, dy], [(4, 4, Ci, Co)], 2, 1, False, "simt", tol=5e-5)
 
 
-@pytest.mark.parametrize("shape", [(3, 8, 8, 64), (2, 16, 32, 128), (2, 4, 4, 40), (1, 2, 2, 512)])
+# (2, 32, 32, 128): 1024-pixel slabs -> the shared-memory kernels narrow the channel group to fit two / three slabs;
+# (1, 96, 96, 8): 9216 pixels do not fit at any width -> multi-pass kernels; (2, 4, 4, 40), (2, 5, 3, 6): odd channel counts
+@pytest.mark.parametrize("shape", [(3, 8, 8, 64), (2, 16, 32, 128), (2, 4, 4, 40), (1, 2, 2, 512), (2, 32, 32, 128),
+                                   (1, 96, 96, 8), (2, 5, 3, 6)])
 @pytest.mark.parametrize("act", ["none", "relu", "lrelu"])
 def test_instnorm(dev, ref, shape, act):
     rs = np.random.RandomState(1)

@@ -1,0 +1,36 @@
+"""Timing experiments on the gather-mode (thin-channel) forward of conv_tc_kmajor: which role bounds a short-K item.
+dbg bits (eg_debug_set(3, .)): 1 skip the filter lo load, 2 skip the A writes to TMEM, 4 skip the output stores."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+from edgegan_b200.ops import DeviceOps
+dev = DeviceOps()
+rs = np.random.RandomState(0)
+rnd = lambda *s: dev.from_numpy(rs.standard_normal(s).astype(np.float32))
+N = int(os.environ.get("N", "128"))
+CASES = [("critic l0 128x128x3->64", N, 128, 128, 3, 64, 4, 2, 1), ("cls conv_1 64x64x8->128", N, 64, 64, 8, 128, 3, 1, 1),
+         ("cls img 32x32x3->128", N, 32, 32, 3, 128, 3, 1, 1), ("dense 1x1 64x64x64->64 (TMA path)", N, 64, 64, 64, 64, 1, 1, 0),
+         ("dense 1x1 64x64x64->128 (TMA path)", N, 64, 64, 64, 128, 1, 1, 0)]
+def timeit(f, n=5):
+    f(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n): f()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / n
+for name, N, H, W, Ci, Co, k, s, p in CASES:
+    OH, OW = (H + 2 * p - k) // s + 1, (W + 2 * p - k) // s + 1
+    x, w = rnd(N, H, W, Ci), rnd(k, k, Ci, Co)
+    y = dev.zeros((N, OH, OW, Co))
+    mb = (x.numel() + y.numel()) * 4 / 1e6
+    row = []
+    for d in (0, 2, 4, 6, 1):
+        dev.lib.eg_debug_set(3, d)
+        t = timeit(lambda: dev.conv_fwd(x, w, None, y, s, p, "tc3x"))
+        row.append(f"dbg={d}: {t*1e3:6.1f} us")
+    dev.lib.eg_debug_set(3, 0)
+    t = timeit(lambda: dev.conv_fwd(x, w, None, y, s, p, "tc3x", act="lrelu"))
+    row.append(f"act epi: {t*1e3:6.1f} us")
+    t = timeit(lambda: dev.conv_fwd(x, w, None, y, s, p, "simt"))
+    row.append(f"simt: {t*1e3:6.1f} us")
+    print(f"{name:36s} {mb:6.0f} MB (HBM floor {mb/6.5e3*1e3:5.1f} us) | " + " | ".join(row), flush=True)
