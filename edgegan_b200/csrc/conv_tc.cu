@@ -662,6 +662,8 @@ struct WgParams {
     int layout_type, sbo;             // UMMA smem descriptor layout type / stride-byte-offset
     int mode;                         // 1 = TF32 rounded, 3 = 3xTF32
     float* out;
+    TcGather g;                       // thin-channel filter gradient: the row operand (im2col columns of x) is gathered
+    int gN;                           //   from the NHWC input by the row-operand warps (kTS kernel only); gN = batch
 };
 
 // kTS (3xTF32 mode): the row operand goes through tensor memory like in the K-major kernel.  Thread r of warps 2-5
@@ -691,8 +693,13 @@ conv_tc_wgrad(const __grid_constant__ TcMaps maps, const __grid_constant__ WgPar
     __shared__ __align__(8) uint64_t empty_bar[kStages];
     __shared__ __align__(8) uint64_t tmem_full_bar;
     __shared__ uint32_t tmem_base_slot;
+    __shared__ int ptab[32];                                 // gather mode: pixel p of the box -> wl | hl << 8 | nl << 16
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x < 32) {
+        const int p = threadIdx.x;
+        ptab[p] = (p % P.bw) | (((p / P.bw) % P.bh) << 8) | ((p / (P.bw * P.bh)) << 16);
+    }
     const int G = P.tap_group, ngroups = (P.ntaps + G - 1) / G;
     const int tap = (blockIdx.z % ngroups) * G, split = blockIdx.z / ngroups;     // first tap of this CTA's group
     const TcTap tp = P.taps[tap];
@@ -740,9 +747,9 @@ conv_tc_wgrad(const __grid_constant__ TcMaps maps, const __grid_constant__ WgPar
                 mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
                 const uint32_t sa = smem_base + stage * stage_bytes, sb = sa + a_bytes;
                 const uint32_t fb = smem_u32(&full_bar[stage]);
-                mbar_expect_tx(fb, ab_bytes);
+                mbar_expect_tx(fb, P.g.on ? b_bytes : ab_bytes);
                 // rows operand: 4 slabs of 32 channels; cols operand: BN/32 slabs
-                for (int i = 0; i < 4; ++i) {
+                for (int i = 0; i < 4 && !P.g.on; ++i) {
                     if (P.x_is_a) tma_load_4d(sa + i * sub_bytes, &maps.a[tp.amap], fb, row0 + i * 32, w0 + tp.ax, h0 + tp.ay, n0);
                     else          tma_load_4d(sa + i * sub_bytes, &maps.b[0], fb, row0 + i * 32, w0, h0, n0);
                 }
@@ -807,7 +814,40 @@ conv_tc_wgrad(const __grid_constant__ TcMaps maps, const __grid_constant__ WgPar
     } else {
         const int ctid = threadIdx.x - 64;
         const int q = warp & 3;
-        {
+        if (kTS && P.g.on) {
+            // thin-channel filter gradient: row r of the tile is im2col column j = (kh*KW + kw)*C + ci; its 32 values of a
+            // stage are that tap of the 32 output pixels of the stage's pixel box, read straight from the NHWC input
+            const int j = row0 + q * 32 + lane;
+            const bool jv = j < P.g.K;
+            int kh = 0, kw = 0, ci = 0;
+            if (jv) { const int tp_ = j / P.g.C; ci = j - tp_ * P.g.C; kh = tp_ / P.g.KW; kw = tp_ - kh * P.g.KW; }
+            const int dh = kh - P.g.pad_t, dw_ = kw - P.g.pad_l;
+            int stage = 0; uint32_t phase = 0;
+            int tw = t_beg % P.tiles_w, th = (t_beg / P.tiles_w) % P.tiles_h, tn = t_beg / (P.tiles_w * P.tiles_h);
+            for (int it = 0; it < niter; ++it) {
+                const int w0 = tw * P.bw, h0 = th * P.bh, n0 = tn * P.bn;
+                if (++tw == P.tiles_w) { tw = 0; if (++th == P.tiles_h) { th = 0; ++tn; } }
+                uint32_t hi[32], lo[32];
+#pragma unroll
+                for (int p = 0; p < 32; ++p) {
+                    const int pt = ptab[p];                  // wl | hl << 8 | nl << 16
+                    const int n = n0 + (pt >> 16), h = (h0 + ((pt >> 8) & 255)) * P.g.stride + dh, w = (w0 + (pt & 255)) * P.g.stride + dw_;
+                    const bool ok = jv && n < P.gN && h >= 0 && h < P.g.H && w >= 0 && w < P.g.W;
+                    hi[p] = ok ? __float_as_uint(__ldg(P.g.x + (((long long)n * P.g.H + h) * P.g.W + w) * P.g.C + ci)) : 0u;
+                }
+                mbar_wait(smem_u32(&full_bar[stage]), phase);  // the TMEM slot is free once the stage has been refilled
+#pragma unroll
+                for (int p = 0; p < 32; ++p) { lo[p] = tf32_lo(hi[p]); hi[p] &= 0xFFFFE000u; }
+                const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + a_col0 + (uint32_t)(stage * 64);
+                tmem_st32(ta, hi);
+                tmem_st32(ta + 32, lo);
+                tmem_st_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(&ready_bar[stage]));
+                if (++stage == kStages) { stage = 0; phase ^= 1; }
+            }
+        } else {
             int stage = 0; uint32_t phase = 0;
             for (int it = 0; it < niter; ++it) {
                 mbar_wait(smem_u32(&full_bar[stage]), phase);
@@ -1202,7 +1242,18 @@ int eg_tc_supported_bwd_data(const eg_conv_shape* s) {
     if (s->H % s->stride || s->W % s->stride) return 0;
     return 1;
 }
+// thin-channel filter gradient with the im2col rows gathered by the row-operand warps (3xTF32 kernel only; the plain
+// TF32 mode of these layers runs on the FFMA kernel).  g_dbg[5] bit 4 turns the route off.
+static bool gather_wgrad(const eg_conv_shape* s) {
+    if (g_dbg[5] & 16) return false;
+    if (s->Ci < 1 || s->Ci > 8 || s->Co % 32) return false;
+    if (s->KH > 16 || s->KW > 16 || s->KH * s->KW * s->Ci > 256) return false;
+    if (s->OW > 255 * 32 || s->OH > 255 * 32) return false;
+    return s->stride >= 1;
+}
+
 int eg_tc_supported_bwd_weight(const eg_conv_shape* s) {
+    if (gather_wgrad(s)) return 1;
     if (thin_bwd_weight(s)) return 1;
     if (s->Ci % 32 || s->Co % 32) return 0;        // (a row side below 128 channels is zero-filled by TMA)
     if (s->stride != 1 && s->stride != 2) return 0;
@@ -1426,8 +1477,63 @@ int eg_tc_conv2d_bwd_data(const eg_conv_shape* s, const float* dy, const float* 
     return unfused;
 }
 
+int eg_simt_conv2d_bwd_weight(const eg_conv_shape* s, const float* x, const float* dy, float* dw, int accumulate, int sms,
+                              cudaStream_t st);
+
+// dw[K, Co] (+)= im2col(x)^T[K, P] . dy[P, Co]: rows = im2col columns (gathered), columns = dy channels (TMA pixel boxes)
+static int tc_conv2d_bwd_weight_gather(const eg_conv_shape* s, const float* x, const float* dy, float* dw, int accumulate,
+                                       cudaStream_t st) {
+    if (int r = get_encode()) return r;
+    if (int r = set_attrs()) return r;
+    TcMaps maps;
+    WgParams P{};
+    P.mode = 3; P.pix = 32;
+    pick_box(s->OW, s->OH, P.pix, P.bw, P.bh, P.bn);
+    const CUtensorMapSwizzle swz = (CUtensorMapSwizzle)g_dbg[0];
+    P.layout_type = g_dbg[1]; P.sbo = g_dbg[2];
+    if (int r = make_act_map(&maps.b[0], dy, s->Co, s->OW, s->OH, s->N, s->Co, (long long)s->OW * s->Co,
+                             (long long)s->OH * s->OW * s->Co, P.bw, P.bh, P.bn, swz)) return r;
+    for (int i = 1; i < 4; ++i) maps.b[i] = maps.b[0];
+    for (int i = 0; i < 4; ++i) maps.a[i] = maps.b[0];       // never used for loads
+    const int K = s->KH * s->KW * s->Ci;
+    P.ntaps = 1;
+    TcTap t0; t0.amap = 0; t0.ax = 0; t0.ay = 0; t0.bsel = 0;
+    P.taps[0] = t0;
+    P.x_is_a = 1;
+    P.BN = s->Co % 128 == 0 ? 128 : (s->Co % 64 == 0 ? 64 : 32);
+    P.rows_total = K; P.cols_total = s->Co;
+    P.tap_group = 1; P.tap_stride = 0; P.sm = s->Co; P.sn = 1;
+    P.tiles_w = s->OW / P.bw; P.tiles_h = s->OH / P.bh; P.tiles_n = eg_ceil_div(s->N, P.bn);
+    const int ntiles = P.tiles_w * P.tiles_h * P.tiles_n;
+    const int row_tiles = eg_ceil_div(K, 128), col_tiles = s->Co / P.BN;
+    int splits = eg_ceil_div(2 * 148, row_tiles * col_tiles);
+    if (splits > ntiles) splits = ntiles;
+    if (splits < 1) splits = 1;
+    P.chunks_per_split = eg_ceil_div(ntiles, splits);
+    if (P.chunks_per_split > g_dbg[4]) P.chunks_per_split = g_dbg[4];
+    splits = eg_ceil_div(ntiles, P.chunks_per_split);
+    P.out = dw;
+    TcGather& g = P.g;
+    g.x = x; g.on = 1; g.H = s->H; g.W = s->W; g.C = s->Ci; g.OH = s->OH; g.OW = s->OW; g.KH = s->KH; g.KW = s->KW;
+    g.stride = s->stride; g.pad_t = s->pad_t; g.pad_l = s->pad_l; g.K = K; g.P = (long long)s->N * s->OH * s->OW;
+    P.gN = s->N;
+    if (!accumulate) {
+        cudaError_t e = cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)K * s->Co, st);
+        if (e != cudaSuccess) return eg_fail(e, __FILE__, __LINE__);
+    }
+    dim3 grid(row_tiles, col_tiles, splits);
+    const size_t smem = (size_t)kStagesW3 * ((4 + 2 * (P.BN / 32)) * P.pix * 128) + 1024;
+    conv_tc_wgrad<kStagesW3, true><<<grid, kThreadsW3, smem, st>>>(maps, P);
+    EG_CHECK_LAUNCH();
+    return 0;
+}
+
 int eg_tc_conv2d_bwd_weight(const eg_conv_shape* s, const float* x, const float* dy, float* dw, int accumulate,
                             int three_x, cudaStream_t st) {
+    if (gather_wgrad(s)) {
+        if (three_x) return tc_conv2d_bwd_weight_gather(s, x, dy, dw, accumulate, st);
+        if (!thin_bwd_weight(s)) return eg_simt_conv2d_bwd_weight(s, x, dy, dw, accumulate, g_sms, st);
+    }
     if (thin_bwd_weight(s)) return eg_thin_conv2d_bwd_weight(s, x, dy, dw, accumulate, three_x, st);
     if (int r = get_encode()) return r;
     if (int r = set_attrs()) return r;

@@ -556,7 +556,11 @@ class EdgeGAN(object):
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g, stream=s):
+        # data parallel: the NCCL all-reduces (gradients, sync-BN sums) are captured with the kernels -- the communicator
+        # exists by now (the warm-up steps above ran them eagerly).  NCCL's watchdog thread polls CUDA events while we
+        # capture, which the default "global" capture mode would turn into a capture error.
+        mode = "thread_local" if self.comm.world_size > 1 else "global"
+        with torch.cuda.graph(g, stream=s, capture_error_mode=mode):
             self.update_model(images, z, alpha, eps)
         return g
 
