@@ -508,8 +508,6 @@ conv_tc_kmajor(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
         asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
         const int q = warp & 3;                                  // this thread's accumulator row = TMEM lane q * 32 + lane
         float acc[128];
-#pragma unroll
-        for (int j = 0; j < 128; ++j) acc[j] = 0.f;
         // the 8 tile rows this lane stores (pass i: row q*32 + i*4 + lane/8): local pixel coordinates and output offset
         const int sub = lane >> 3, cj = lane & 7;                // row within a group of 4, 16-byte chunk within the row
         uint32_t loc[8];
@@ -532,14 +530,29 @@ conv_tc_kmajor(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
                 const int buf = cg & 1;
                 mbar_wait(smem_u32(&acc_full_bar[buf]), (uint32_t)((cg >> 1) & 1));
                 tc_fence_after();
+                // the first chunk of an item ASSIGNS (no zeroing of 128 registers per item, no add): short-K items are
+                // bound by the instruction count of these four warps (tools/gather_time.py)
+                if (c == 0) {
 #pragma unroll
-                for (int g = 0; g < 4; ++g) {
-                    if (g * 32 < BN) {
-                        uint32_t r[32];
-                        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + g * 32), r);
-                        tmem_ld_wait();
+                    for (int g = 0; g < 4; ++g) {
+                        if (g * 32 < BN) {
+                            uint32_t r[32];
+                            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + g * 32), r);
+                            tmem_ld_wait();
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) acc[g * 32 + j] += __uint_as_float(r[j]);
+                            for (int j = 0; j < 32; ++j) acc[g * 32 + j] = __uint_as_float(r[j]);
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        if (g * 32 < BN) {
+                            uint32_t r[32];
+                            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + g * 32), r);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) acc[g * 32 + j] += __uint_as_float(r[j]);
+                        }
                     }
                 }
                 tc_fence_before();
@@ -562,7 +575,8 @@ conv_tc_kmajor(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
             if (P.dbg & 4) vmask = 0;
             float* obase = P.out + ph.out_off + (long long)t.n0 * ph.sn + (long long)t.h0 * ph.sh + (long long)t.w0 * ph.sw + t.col0;
             const float* brow = (P.bias != nullptr && t.split == 0) ? P.bias + t.col0 + cj * 4 : nullptr;
-            const bool plain = vmask == 0xffu && brow == nullptr && P.ksplit == 1 && P.epi == EG_EPI_NONE;
+            // full tile, no mask / split: the transposed copy with the bias add and the sign-type activation folded in
+            const bool plain = vmask == 0xffu && P.ksplit == 1 && P.epi != EG_EPI_MASK;
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
                 const int c = g * 32;
@@ -572,17 +586,33 @@ conv_tc_kmajor(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
                         sts128(stg + (uint32_t)lane * 128u + (uint32_t)((j ^ (lane & 7)) << 4),
                                make_uint4(__float_as_uint(acc[c + 4 * j]), __float_as_uint(acc[c + 4 * j + 1]),
                                           __float_as_uint(acc[c + 4 * j + 2]), __float_as_uint(acc[c + 4 * j + 3])));
-                        acc[c + 4 * j] = 0.f; acc[c + 4 * j + 1] = 0.f; acc[c + 4 * j + 2] = 0.f; acc[c + 4 * j + 3] = 0.f;
                     }
                     __syncwarp();
                     if (plain) {
-                        // full tile, no bias / epilogue / split: nothing but the transposed copy (short-K tiles are
-                        // bound by the instruction count of these four warps)
+                        float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (brow != nullptr) bb = __ldg(reinterpret_cast<const float4*>(brow + c));
+                        // (the two tie rules of the sign-type activations give the same VALUE at zero: +-0)
+                        const float thr = 0.f;
+                        if (P.epi == EG_EPI_ACT) {
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            const int rr = i * 4 + sub;
-                            const uint4 u = lds128(stg + (uint32_t)rr * 128u + (uint32_t)((cj ^ (rr & 7)) << 4));
-                            *reinterpret_cast<uint4*>(obase + loff[i] + c) = u;
+                            for (int i = 0; i < 8; ++i) {
+                                const int rr = i * 4 + sub;
+                                const uint4 u = lds128(stg + (uint32_t)rr * 128u + (uint32_t)((cj ^ (rr & 7)) << 4));
+                                float4 v = make_float4(__uint_as_float(u.x) + bb.x, __uint_as_float(u.y) + bb.y,
+                                                       __uint_as_float(u.z) + bb.z, __uint_as_float(u.w) + bb.w);
+                                v.x = v.x > thr ? v.x : P.epi_neg * v.x; v.y = v.y > thr ? v.y : P.epi_neg * v.y;
+                                v.z = v.z > thr ? v.z : P.epi_neg * v.z; v.w = v.w > thr ? v.w : P.epi_neg * v.w;
+                                *reinterpret_cast<float4*>(obase + loff[i] + c) = v;
+                            }
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                const int rr = i * 4 + sub;
+                                const uint4 u = lds128(stg + (uint32_t)rr * 128u + (uint32_t)((cj ^ (rr & 7)) << 4));
+                                *reinterpret_cast<float4*>(obase + loff[i] + c) =
+                                    make_float4(__uint_as_float(u.x) + bb.x, __uint_as_float(u.y) + bb.y,
+                                                __uint_as_float(u.z) + bb.z, __uint_as_float(u.w) + bb.w);
+                            }
                         }
                     } else {
                         float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
