@@ -1273,9 +1273,12 @@ int eg_tc_supported_bwd_data(const eg_conv_shape* s) {
     return 1;
 }
 // thin-channel filter gradient with the im2col rows gathered by the row-operand warps (3xTF32 kernel only; the plain
-// TF32 mode of these layers runs on the FFMA kernel).  g_dbg[5] bit 4 turns the route off.
+// TF32 mode of these layers runs on the FFMA kernel).  OFF by default (g_dbg[5] bit 4 turns it on): measured on B200
+// (bench.py by_shape, critic first layer at 3 x 128 samples) 735 us against 445 us for the FFMA kernel -- only the two
+// warps whose TMEM lanes hold valid im2col columns (48 of 128 rows) gather, 32 dependent-latency scalar loads per stage,
+// one stage at a time; the forward's gather (8 warps, rows = pixels) does not have that problem.  Kept for the tests.
 static bool gather_wgrad(const eg_conv_shape* s) {
-    if (g_dbg[5] & 16) return false;
+    if (!(g_dbg[5] & 16)) return false;
     if (s->Ci < 1 || s->Ci > 8 || s->Co % 32) return false;
     if (s->KH > 16 || s->KW > 16 || s->KH * s->KW * s->Ci > 256) return false;
     if (s->OW > 255 * 32 || s->OH > 255 * 32) return false;

@@ -76,12 +76,22 @@ def test_tc_conv_trio(dev, ref, case, algo, request):
     x, w, b = rnd(rs, N, H, W, Ci), rnd(rs, k, k, Ci, Co, scale=0.05), rnd(rs, Co)
     dy, bi = rnd(rs, N, OH, OW, Co), rnd(rs, Ci)
     cs = dev._cs(x.shape, w.shape, dy.shape, s, p)
-    # thin layers: route all three passes through conv_thin.cu (by default only the input gradient goes there)
-    dev.lib.eg_debug_set(5, 7 if Ci <= 8 else 2)
     request.addfinalizer(lambda: dev.lib.eg_debug_set(5, 2))
-    used = [dev.lib.eg_conv2d_algo_for(C.byref(cs), i, 2) for i in range(3)]
-    # these shapes are the ones the tensor-core path must cover
-    assert used == [2, 2, 2], used
+    # eg_debug_set(5, mask): bit 0 / 1 / 2 = forward / input gradient / filter gradient through the patch-matrix route of
+    # conv_thin.cu, bit 3 = forward gather route OFF, bit 4 = filter-gradient gather route ON.  Thin layers run twice:
+    # (a) forward gathered by the conditioning warps (the default) + gathered filter gradient, (b) everything through
+    # the patch matrix; the default for the filter gradient of these layers is the FFMA kernel (test_ops_gpu.py).
+    routes = [2 | 16, 7 | 8] if Ci <= 8 else [2]
+    for route in routes:
+        dev.lib.eg_debug_set(5, route)
+        used = [dev.lib.eg_conv2d_algo_for(C.byref(cs), i, 2) for i in range(3)]
+        # these shapes are the ones the tensor-core path must cover
+        assert used == [2, 2, 2], (route, used)
+        _trio(dev, ref, rs, x, w, b, dy, bi, case, algo, TOL)
+
+
+def _trio(dev, ref, rs, x, w, b, dy, bi, case, algo, TOL):
+    N, H, W, Ci, Co, k, s, p, OH, OW = case
     want = run(ref, "conv_fwd", [x, w, b], (N, OH, OW, Co), s, p)
     got = run(dev, "conv_fwd", [x, w, b], (N, OH, OW, Co), s, p, algo)
     assert relerr(got, want) < TOL, ("fwd", relerr(got, want))

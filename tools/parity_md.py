@@ -16,10 +16,10 @@ def main(src, dst):
                 "Each run of `update_model` on the device is replayed by the fp64 oracle (truth) and the fp32 oracle (the\n"
                 "reference's precision) from the device's own pre-run weights.  `tol` = plain bar on max|g_dev - g_fp64| / max|g_fp64|\n"
                 "per tensor; a tensor above it passes only if it is within 10x max(fp32-oracle distance to fp64, fp64 response to a\n"
-                "1e-5 relative input perturbation) -- the column `via noise clause` counts those; in the large / realistic-input tests a
-tensor may also pass within 10x the largest such instability of its RUN (`via run-level clause`: activation-mask flips, see
-tests/parity_util.check_grads), and a gradient whose absolute error cannot move its weight by more than 0.005 lr through
-RMSProp counts as `below absolute bar` (the scalar prelu leaks: heavily cancelling sums).  Weight errors are in units of\n"
+                "1e-5 relative input perturbation) -- the column `via noise clause` counts those; in the large / realistic-input tests a\n"
+                "tensor may also pass within 10x the largest such instability of its RUN (`via run-level clause`: activation-mask flips, see\n"
+                "tests/parity_util.check_grads), and a gradient whose absolute error cannot move its weight by more than 0.005 lr through\n"
+                "RMSProp counts as `below absolute bar` (the scalar prelu leaks: heavily cancelling sums).  Weight errors are in units of\n"
                 "the learning rate (one RMSProp step moves a weight by <= ~3.2 lr).\n\n")
         for name, r in latest.items():
             f.write(f"## {name}\n\n| run | tol | grad tensors | within tol | via noise clause | via run-level clause | below absolute bar | worst rel. error (tensor; fp32-oracle noise) | "
