@@ -401,7 +401,17 @@ def main():
         }
         print(json.dumps(line), flush=True)
     if world > 1:
-        torch.distributed.destroy_process_group()
+        # Tear down in a fixed order: the captured graph (it references NCCL kernels) first, then a last rendezvous so
+        # that no rank leaves while another still needs it.  destroy_process_group() has been seen to hang after a graph
+        # with captured collectives (the bench line was out, the launcher then waited for its timeout), so the
+        # communicator is left to process exit.
+        leg.release()
+        torch.cuda.synchronize()
+        comm.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def conv_roofline(model, ops, step_fn, algo):
