@@ -446,7 +446,9 @@ def conv_roofline(model, ops, step_fn, algo):
             f(*a, **kw)
             e1.record()
             shape = f"N{s.N} {s.H}x{s.W}x{s.Ci}->{s.OH}x{s.OW}x{s.Co} k{s.KH} s{s.stride}"
-            recs.append((name, used, 2.0 * macs, e0, e1, shape))
+            thin = min(s.Ci, s.Co) <= 8
+            nbytes = 4.0 * (s.N * s.H * s.W * s.Ci + s.N * s.OH * s.OW * s.Co)      # algorithmic: input + output once
+            recs.append((name, used, 2.0 * macs, e0, e1, shape, thin, nbytes))
         return g
 
     for pid, n in enumerate(("conv_fwd", "conv_bwd_data", "conv_bwd_weight")):
@@ -457,17 +459,24 @@ def conv_roofline(model, ops, step_fn, algo):
     finally:
         for n, f in orig.items():
             setattr(ops, n, f)
+    # Three classes of conv launches: "tc" = tensor-bound tcgen05 layers; "thin" = the image-side layers (<= 8 channels
+    # on one side): tensor cores or FFMA, but HBM-bound by arithmetic intensity (d_conv_0 AI 20, g_dconv_4
+    # 31, classifier h0 / unit-1 34-53 flop/B) -> reported in GB/s against the HBM roofline; "simt" = the rest on FFMA.
     agg, by_shape = {}, {}
-    for name, used, fl, e0, e1, shape in recs:
-        key = (name, "tc" if used in (2, 3) else "simt")
+    for name, used, fl, e0, e1, shape, thin, nbytes in recs:
+        path = "thin" if thin else ("tc" if used in (2, 3) else "simt")
+        key = (name, path)
         ms = e0.elapsed_time(e1)
         for d, k in ((agg, key), (by_shape, key + (shape,))):
-            a = d.setdefault(k, [0.0, 0.0, 0])
+            a = d.setdefault(k, [0.0, 0.0, 0, 0.0])
             a[0] += fl
             a[1] += ms
             a[2] += 1
+            a[3] += nbytes
     tc_fl = sum(v[0] for k, v in agg.items() if k[1] == "tc")
     tc_ms = sum(v[1] for k, v in agg.items() if k[1] == "tc")
+    thin_b = sum(v[3] for k, v in agg.items() if k[1] == "thin")
+    thin_ms = sum(v[1] for k, v in agg.items() if k[1] == "thin")
     all_ms = sum(v[1] for v in agg.values())
     def num(v):                      # plain number, or an object carrying it under "value"
         if isinstance(v, dict):
@@ -481,11 +490,14 @@ def conv_roofline(model, ops, step_fn, algo):
         peak /= 1e3
     # kind::tf32 runs at half the bf16 rate: the peak of the MMA kind actually used
     peak_kind = peak / 2.0
-    detail = {f"{k[0]}/{k[1]}": {"launches": v[2], "ms": round(v[1], 3), "tflops": (v[0] / v[1] / 1e9 if v[1] > 0 else None)}
+    hbm = num(pk.get("hbm_gbs")) or FALLBACK_PEAKS["hbm_gbs"]
+    detail = {f"{k[0]}/{k[1]}": {"launches": v[2], "ms": round(v[1], 3), "tflops": (v[0] / v[1] / 1e9 if v[1] > 0 else None),
+                                 **({"gbs": v[3] / v[1] / 1e6, "hbm_frac": v[3] / v[1] / 1e6 / hbm} if k[1] == "thin" and v[1] > 0 else {})}
               for k, v in agg.items()}
     top = sorted(by_shape.items(), key=lambda kv: -kv[1][1])[:24]
     shapes = [{"pass": k[0], "path": k[1], "shape": k[2], "launches": v[2], "ms": round(v[1], 3),
-               "tflops": round(v[0] / v[1] / 1e9, 1) if v[1] > 0 else None} for k, v in top]
+               "tflops": round(v[0] / v[1] / 1e9, 1) if v[1] > 0 else None,
+               "gbs": round(v[3] / v[1] / 1e6, 0) if v[1] > 0 else None} for k, v in top]
     if tc_ms > 0:
         ach = tc_fl / tc_ms / 1e9
         mult = 3.0 if algo == "tc3x" else 1.0
@@ -496,6 +508,9 @@ def conv_roofline(model, ops, step_fn, algo):
                 "tensor_pipe_work_frac": mult * ach / peak_kind,
                 "note": ("achieved counts ALGORITHMIC conv FLOPs; the 3xTF32 mode issues 3 tensor-core MMAs per algorithmic "
                          "MMA (hi*hi + lo*hi + hi*lo), so the tensor pipe is busy tensor_pipe_work_frac of its tf32 peak"),
+                "thin_layers": {"bound": "hbm", "achieved": thin_b / thin_ms / 1e6 if thin_ms > 0 else None, "peak": hbm, "unit": "GB/s",
+                                "frac": thin_b / thin_ms / 1e6 / hbm if thin_ms > 0 else None, "ms_per_step": thin_ms,
+                                "note": "image-side layers (<= 8 channels on one side): algorithmic bytes = 4*(input + output) per launch"},
                 "detail": detail, "by_shape": shapes}
     simt_fl = sum(v[0] for v in agg.values())
     ach = simt_fl / all_ms / 1e9 if all_ms > 0 else 0.0

@@ -920,10 +920,19 @@ conv_tc_wgrad(const __grid_constant__ TcMaps maps, const __grid_constant__ WgPar
                 const int cbase = G > 1 ? c % P.cols_total : col0 + c;
                 float* ob = obase + (long long)tj * P.tap_stride;
                 if (tj < P.ntaps) {
+                    if (P.sn == 1 && cbase + 32 <= P.cols_total && ((P.sm | P.tap_stride) & 3) == 0) {
+                        // columns are contiguous in dw: 8 x 16-byte reductions per thread instead of 32 scalar ones (the
+                        // 32 rows of a warp lie sm floats apart, so every lane is its own L2 transaction either way)
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const int col = cbase + j;
-                        if (col < P.cols_total) atomicAdd(ob + (long long)col * P.sn, __uint_as_float(r[j]));
+                        for (int j = 0; j < 8; ++j)
+                            red_add_v4(ob + cbase + 4 * j, make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                                                                       __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3])));
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const int col = cbase + j;
+                            if (col < P.cols_total) atomicAdd(ob + (long long)col * P.sn, __uint_as_float(r[j]));
+                        }
                     }
                 }
             }
