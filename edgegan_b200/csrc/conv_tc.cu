@@ -706,7 +706,7 @@ struct WgParams {
 constexpr int kThreadsW3 = 320;
 
 template <int kStages, bool kTS>
-__global__ void __launch_bounds__(kTS ? kThreadsW3 : kThreads, 1)
+__global__ void __launch_bounds__(kTS ? kThreadsW3 : kThreads, (kTS && kStages == 2) ? 2 : 1)
 conv_tc_wgrad(const __grid_constant__ TcMaps maps, const __grid_constant__ WgParams P) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -1067,6 +1067,8 @@ int set_attrs() {
     e = cudaFuncSetAttribute(conv_tc_wgrad<kStagesW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return eg_fail(e, __FILE__, __LINE__);
     e = cudaFuncSetAttribute(conv_tc_wgrad<kStagesW3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return eg_fail(e, __FILE__, __LINE__);
+    e = cudaFuncSetAttribute(conv_tc_wgrad<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     if (e != cudaSuccess) return eg_fail(e, __FILE__, __LINE__);
     g_attr_set = true;
     return 0;
@@ -1625,8 +1627,15 @@ int eg_tc_conv2d_bwd_weight(const eg_conv_shape* s, const float* x, const float*
     }
     dim3 grid(row_tiles, col_tiles, tap_groups * splits);
     if (P.mode == 3) {
-        const size_t smem = (size_t)kStagesW3 * ((4 + 2 * (P.BN / 32)) * P.pix * 128) + 1024;
-        conv_tc_wgrad<kStagesW3, true><<<grid, kThreadsW3, smem, st>>>(maps, P);
+        // g_dbg[6] bit 1: two CTAs per SM with a 2-stage ring each (one CTA's prologue / atomic epilogue overlaps the
+        // other's main loop) instead of one CTA with 4 stages
+        if (g_dbg[6] & 2) {
+            const size_t smem = (size_t)2 * ((4 + 2 * (P.BN / 32)) * P.pix * 128) + 1024;
+            conv_tc_wgrad<2, true><<<grid, kThreadsW3, smem, st>>>(maps, P);
+        } else {
+            const size_t smem = (size_t)kStagesW3 * ((4 + 2 * (P.BN / 32)) * P.pix * 128) + 1024;
+            conv_tc_wgrad<kStagesW3, true><<<grid, kThreadsW3, smem, st>>>(maps, P);
+        }
     } else {
         const size_t smem = (size_t)kStagesW * ((4 + P.BN / 32) * P.pix * 128) + 1024;
         conv_tc_wgrad<kStagesW, false><<<grid, kThreads, smem, st>>>(maps, P);

@@ -40,6 +40,58 @@ class LocalComm:
         return t
 
 
+class _GraphStep:
+    """update_model as a CUDA-graph replay for the training loop (see EdgeGAN.train)."""
+
+    def __init__(self, model, eager_steps=2):
+        self.m, self.eager_steps, self.n, self.graph, self.shape = model, eager_steps, 0, None, None
+        self.stream = None
+
+    def __call__(self, images, z):
+        """runs on a dedicated stream (the one the graph is captured on, so that the library's per-stream scratch exists
+        before the capture), ordered after / before the caller's current stream"""
+        import torch
+        if self.stream is None:
+            self.stream = torch.cuda.Stream()
+        cur = torch.cuda.current_stream()
+        self.stream.wait_stream(cur)
+        with torch.cuda.stream(self.stream):
+            self._step(images, z)
+        cur.wait_stream(self.stream)
+
+    def _step(self, images, z):
+        import torch
+        m, ops = self.m, self.m.ops
+        rs = getattr(m, "_rs", None) or np.random.RandomState(m.seed + 1)
+        m._rs = rs
+        nb = images.shape[0]
+        alpha = rs.uniform(0, 1, (3, nb)).astype(np.float32)
+        eps = float(rs.normal())
+        shape = (tuple(images.shape), tuple(z.shape))
+        if self.shape is not None and shape != self.shape:      # e.g. another batch size: back to eager launches
+            self.graph, self.n, self.shape = None, 0, None
+        self.n += 1
+        if self.graph is None and self.n <= self.eager_steps:
+            m.update_model(images, z, ops.from_numpy(alpha), eps)
+            return
+        if self.graph is None:
+            self.shape = shape
+            self.s_img, self.s_z = torch.empty_like(images), torch.empty_like(z)
+            self.s_alpha = ops.empty((3, nb))
+            self.s_eps = ops.empty((1,))
+            self.h_alpha = torch.empty((3, nb), dtype=torch.float32).pin_memory()
+            self.h_eps = torch.empty((1,), dtype=torch.float32).pin_memory()
+            self.graph = m.capture_step(self.s_img, self.s_z, self.s_alpha, self.s_eps, warmup=0, stream=self.stream)
+        self.s_img.copy_(images, non_blocking=True)
+        self.s_z.copy_(z, non_blocking=True)
+        self.h_alpha.numpy()[...] = alpha
+        self.h_eps[0] = eps
+        self.s_alpha.copy_(self.h_alpha, non_blocking=True)
+        self.s_eps.copy_(self.h_eps, non_blocking=True)
+        self.graph.replay()
+        torch.cuda.current_stream().synchronize()               # the pinned alpha / eps staging is reused next iteration
+
+
 class EdgeGAN(object):
     def __init__(self, sess=None, config: Flags = None, dataset=None, z_dim=100, gf_dim=64, df_dim=64,
                  gfc_dim=1024, dfc_dim=1024, c_dim=3, *, ops=None, comm=None, seed=0):
@@ -126,14 +178,18 @@ class EdgeGAN(object):
         return out
 
     # ---- train / test loops (edgegan.py:425-489, 551-633) ----------------------------------------------------------
-    def train(self, max_steps=None, prefetch_workers=None, log=print):
+    def train(self, max_steps=None, prefetch_workers=None, log=print, use_graph=None):
         """edgegan.py:425-489.  Restores the latest checkpoint if there is one, then per epoch: shuffle, and per batch
         one `update_model` and the loss line of the reference.  The reference re-evaluates five loss tensors with three
         extra graph runs after every step (:461-477); here the line is printed from the scalars the step itself
         produced (`read_losses`, one 64-byte read-back), i.e. each loss is the value its own run minimised.
         Scalar summaries go to <logdir>/events.out.tfevents.* under the reference's tags (edgegan_b200/summary.py; image
         and histogram summaries are not written).  `max_steps` bounds the run (tests); `prefetch_workers` > 0 feeds the
-        device through DevicePrefetcher (default: 8 on a GPU operator set, 0 otherwise)."""
+        device through DevicePrefetcher (default: 8 on a GPU operator set, 0 otherwise).
+        `use_graph` (default: on for a CUDA operator set): the first two iterations launch eagerly (they allocate every
+        buffer of the step), the third is captured into a CUDA graph over static input buffers and from then on each
+        iteration is a refill of those buffers plus one replay -- ~1 200 kernel launches per step without host work.
+        alpha ~ U[0,1) and the encoder noise are drawn on the host per iteration exactly as in the eager path."""
         import time
         from ..utils.data import DevicePrefetcher
         cfg, ops = self.config, self.ops
@@ -154,6 +210,9 @@ class EdgeGAN(object):
             from ..summary import SummaryWriter
             writer = SummaryWriter(cfg.logdir)
         steps = 0
+        if use_graph is None:
+            use_graph = getattr(getattr(ops, "device", None), "type", "cpu") == "cuda"
+        replay = _GraphStep(self) if use_graph else None
         for epoch in range(cfg.epoch):
             if self.comm.world_size > 1:
                 # one global permutation per epoch (seed drawn on rank 0), disjoint shards per rank
@@ -168,7 +227,10 @@ class EdgeGAN(object):
                 batches = ((ops.from_numpy(im), ops.from_numpy(z.astype(np.float32)), f)
                            for im, z, f in (self.dataset[i] for i in range(len(self.dataset))))
             for idx, (batch_images, batch_z, _files) in enumerate(batches):
-                self.update_model(batch_images, batch_z)
+                if replay is not None:
+                    replay(batch_images, batch_z)
+                else:
+                    self.update_model(batch_images, batch_z)
                 L = self.read_losses()
                 discriminator_err = L["joint_dis_dloss"] + L["image_dis_dloss"] + L["edge_dis_dloss"]
                 generator_err = L["edge_gloss"] + L["image_gloss"]
@@ -542,13 +604,14 @@ class EdgeGAN(object):
                 self._generator_run(run, zin, z, fresh_forward=True)
                 fakes_fresh = False
 
-    def capture_step(self, images, z, alpha, eps, warmup=2):
+    def capture_step(self, images, z, alpha, eps, warmup=2, stream=None):
         """Capture one update_model into a CUDA graph over STATIC device buffers (images, z, alpha and a 1-element
         device tensor eps): refill the buffers, then `graph.replay()`.  The step allocates nothing after its first
         call and takes every scalar input from device memory, so the ~650 launches replay without host work.
-        Runs `warmup` real steps first (they update the weights like any other step)."""
+        Runs `warmup` real steps first (they update the weights like any other step); they also let the library size its
+        per-stream scratch memory on the capture stream, so with warmup=0 pass the `stream` earlier steps already ran on."""
         import torch
-        s = torch.cuda.Stream()
+        s = stream or torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
             for _ in range(warmup):

@@ -120,8 +120,11 @@ class DeviceOps:
 
     @property
     def default_algo(self):
+        """what the library's EG_ALGO_AUTO currently resolves to for tensor-core-capable layers ('tc3x' unless
+        set_default_algo chose otherwise)"""
         code = int(self.lib.eg_get_default_algo())
-        return {v: k for k, v in ALGO.items() if k}[code]
+        name = {v: k for k, v in ALGO.items() if k}[code]
+        return "tc3x" if name == "auto" else name
 
     # ---- convolution trio -------------------------------------------------------------------
     def _cs(self, xs, ws, ys, stride, pad):

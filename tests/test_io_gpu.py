@@ -91,3 +91,39 @@ def test_train_checkpoint_resume_test_cli_on_the_device(dev, tmp_path):
     assert written == 12
     im = np.array(Image.open(os.path.join(root, "outputs", "t", "test_output", "toy", "1", "13.png")))
     assert im.shape == (64, 128 + 64 + 64, 3) and im.min() == 0 and im.max() == 255
+
+
+def test_train_loop_graph_replay_equals_eager(dev, tmp_path):
+    """EdgeGAN.train(use_graph=True): iterations 1-2 launch eagerly, iteration 3 is captured into a CUDA graph and
+    iterations 3-5 are replays over static input buffers.  Same data order, same host random draws (z, alpha, eps) ->
+    the weights after 5 iterations must equal the all-eager loop's up to the reordering of fp32 atomics."""
+    from edgegan_b200.config import parse_flags, update_flags
+    from edgegan_b200.models.edgegan import EdgeGAN
+    from edgegan_b200.utils.data import Dataset
+    root = str(tmp_path)
+    _tree(root)
+    args = ["--dataroot", os.path.join(root, "data"), "--dataset", "toy", "--outputsroot", os.path.join(root, "outputs"),
+            "--name", "g", "--num_classes", "2", "--batch_size", "2", "--epoch", "3"]
+    out = []
+    for use_graph in (False, True):
+        flags = update_flags(parse_flags(args))
+        flags.logdir = None
+        flags.checkpoint_dir = os.path.join(root, "ck_%d" % use_graph)
+        cfg = {"input_height": flags.input_height, "input_width": flags.input_width, "output_height": flags.output_height,
+               "output_width": flags.output_width, "crop": flags.crop, "grayscale": False, "z_dim": flags.z_dim}
+        np.random.seed(7)
+        ds = Dataset(flags.dataroot, flags.dataset, flags.train_size, flags.batch_size, cfg, flags.num_classes, "train")
+        m = EdgeGAN(None, flags, ds, ops=dev, seed=3)
+        m.build_train_model()
+        logs = []
+        m.train(max_steps=5, prefetch_workers=0, log=logs.append, use_graph=use_graph)
+        torch.cuda.synchronize()
+        out.append((m.export_variables("var"), m.read_losses(), [l for l in logs if l.startswith("Epoch")]))
+    (v0, l0, log0), (v1, l1, log1) = out
+    assert len(log0) == len(log1) == 5
+    for k in v0:
+        assert np.isfinite(v1[k]).all(), k
+        d = np.abs(v0[k] - v1[k]).max()
+        assert d <= 1e-4 * 5, (k, d)           # 5 RMSProp steps of lr = 2e-4 move a weight by at most ~3e-3
+    for k in l0:
+        assert abs(l0[k] - l1[k]) <= 2e-3 * max(1.0, abs(l0[k])), (k, l0[k], l1[k])
