@@ -116,8 +116,8 @@ def _train_worker(rank, world, port, root, out_dir):
     ds = Dataset(flags.dataroot, flags.dataset, flags.train_size, flags.batch_size, cfg, None, "train")
     m = EdgeGAN(None, flags, ds, ops=RefOps(torch.float64), comm=TorchDistComm("gloo"), seed=5)
     np.random.seed(100 + rank)                                   # ranks do NOT share numpy's generator state
-    m.train(max_steps=1, prefetch_workers=0, log=lambda *a: None)
-    np.savez(os.path.join(out_dir, f"rank{rank}.npz"), files=np.array(ds.data),
+    counter = m.train(max_steps=None, prefetch_workers=0, log=lambda *a: None)      # the WHOLE epoch: no rank may run an extra batch
+    np.savez(os.path.join(out_dir, f"rank{rank}.npz"), files=np.array(ds.data), counter=counter,
              w=m.export_variables("var")["D/d_conv_3/conv2d/w"])
     dist.barrier()
     dist.destroy_process_group()
@@ -128,14 +128,17 @@ def test_two_rank_train_loop_shards_the_epoch_and_keeps_weights_in_sync(tmp_path
     from PIL import Image
     root = str(tmp_path)
     rs = np.random.RandomState(0)
-    for i in range(8):
+    # 7 files, 2 ranks, batch 2: ceil(7 / 2) = 4 = two batches for rank 0 but 3 files = one batch for rank 1 if the shards
+    # were files[rank::world] of the full list -- rank 0 would then wait forever in a second gradient all-reduce
+    for i in range(7):
         p = os.path.join(root, "data", "toy", "train", f"{i}.png")
         os.makedirs(os.path.dirname(p), exist_ok=True)
         Image.fromarray(rs.randint(0, 256, (32, 64, 3)).astype(np.uint8)).save(p)
     port = _free_port()
     mp.spawn(_train_worker, args=(2, port, root, root), nprocs=2, join=True)
     r0, r1 = np.load(os.path.join(root, "rank0.npz")), np.load(os.path.join(root, "rank1.npz"))
-    assert len(r0["files"]) == len(r1["files"]) == 4
+    assert len(r0["files"]) == len(r1["files"]) == 3
+    assert int(r0["counter"]) == int(r1["counter"]) == 2         # one batch each (counter starts at 1)
     assert not set(r0["files"]) & set(r1["files"])               # disjoint shards of one global permutation
     assert np.array_equal(r0["w"], r1["w"])                      # same all-reduced gradients -> identical weights
     # rank 0 wrote the checkpoint (counter 2 with frequency 3)
