@@ -1627,9 +1627,10 @@ int eg_tc_conv2d_bwd_weight(const eg_conv_shape* s, const float* x, const float*
     }
     dim3 grid(row_tiles, col_tiles, tap_groups * splits);
     if (P.mode == 3) {
-        // g_dbg[6] bit 1: two CTAs per SM with a 2-stage ring each (one CTA's prologue / atomic epilogue overlaps the
-        // other's main loop) instead of one CTA with 4 stages
-        if (g_dbg[6] & 2) {
+        // Two CTAs per SM with a 2-stage ring each (one CTA's prologue / atomic epilogue overlaps the other's main loop)
+        // instead of one CTA with 4 stages: +2 ... +10 % on the single-tap-per-CTA layouts, -2 % with tap pairs
+        // (tools/wgrad_time.py).  g_dbg[6] bit 1 forces the 4-stage kernel.
+        if (!(g_dbg[6] & 2) && P.tap_group == 1) {
             const size_t smem = (size_t)2 * ((4 + 2 * (P.BN / 32)) * P.pix * 128) + 1024;
             conv_tc_wgrad<2, true><<<grid, kThreadsW3, smem, st>>>(maps, P);
         } else {

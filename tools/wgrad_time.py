@@ -25,10 +25,9 @@ for name, N, H, W, Ci, Co, k, s, p in CASES:
     x, dy = rnd(N, H, W, Ci), rnd(N, OH, OW, Co)
     ref, dw = dev.zeros((k, k, Ci, Co)), dev.zeros((k, k, Ci, Co))
     fl = 2.0 * N * OH * OW * k * k * Ci * Co
-    dev.lib.eg_debug_set(6, 0)
+    dev.lib.eg_debug_set(6, 2)           # bit 1: force the 4-stage, one-CTA-per-SM kernel
     t4 = timeit(lambda: dev.conv_bwd_weight(x, dy, ref, s, p, False, "tc3x"))
-    dev.lib.eg_debug_set(6, 2)
+    dev.lib.eg_debug_set(6, 0)           # default: two CTAs per SM, 2 stages each (single-tap layouts)
     t2 = timeit(lambda: dev.conv_bwd_weight(x, dy, dw, s, p, False, "tc3x"))
-    dev.lib.eg_debug_set(6, 0)
     err = float((dw - ref).abs().max() / ref.abs().max())
     print(f"{name:30s} 4 stages x 1 CTA {t4*1e3:7.1f} us {fl/t4/1e9:6.1f} TF/s | 2 stages x 2 CTAs {t2*1e3:7.1f} us {fl/t2/1e9:6.1f} TF/s | rel diff {err:.1e}", flush=True)
