@@ -1,5 +1,5 @@
 """Timing experiments on the gather-mode (thin-channel) forward of conv_tc_kmajor: which role bounds a short-K item.
-dbg bits (eg_debug_set(3, .)): 1 skip the filter lo load, 2 skip the A writes to TMEM, 4 skip the output stores."""
+dbg bits (eg_debug_set(3, .)): 1 skip the filter lo load, 2 skip the A writes to TMEM, 4 skip the output stores, 16 no L2 prefetch of the items ahead."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
@@ -24,7 +24,7 @@ for name, N, H, W, Ci, Co, k, s, p in CASES:
     y = dev.zeros((N, OH, OW, Co))
     mb = (x.numel() + y.numel()) * 4 / 1e6
     row = []
-    for d in (0, 2, 4, 6, 1):
+    for d in (0, 16, 2, 4, 1):
         dev.lib.eg_debug_set(3, d)
         t = timeit(lambda: dev.conv_fwd(x, w, None, y, s, p, "tc3x"))
         row.append(f"dbg={d}: {t*1e3:6.1f} us")
