@@ -119,9 +119,15 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const void* map, uint3
         "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
         ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
-// (An L2 prefetch of the operand boxes of the work item two rounds ahead -- cp.async.bulk.prefetch.tensor / .L2 issued by
-// the producer thread -- was measured and made the short-K layers 20 % SLOWER: they are instruction-issue-bound, not
-// latency-bound, and the single producer thread is on the critical path; tools/gather_time.py)
+// L2 prefetches (no shared-memory destination, no barrier) of the operand boxes of the work item two rounds ahead,
+// issued by the producer thread for short-K items (P.dbg bit 4; see launch_kmajor for when it is on)
+__device__ __forceinline__ void tma_prefetch_4d(const void* map, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];"
+                 ::"l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void l2_prefetch_bulk(const void* p, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void prefetch_tmap(const void* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -489,6 +495,33 @@ conv_tc_kmajor(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
             if (P.dbg & 8) __nanosleep((blockIdx.x & 15) * 500);
             for (int id = blockIdx.x; id < total_ids; id += gridDim.x) {
                 if (!get_item(P, id, t)) continue;
+                if (P.dbg & 16) {   // L2 prefetch of the A operand of the item two rounds ahead
+                    WorkItem tn;
+                    const int idn = id + 2 * (int)gridDim.x;
+                    if (idn < total_ids && get_item(P, idn, tn) && tn.niter <= 6) {
+                        if (P.g.on == 1) {
+                            // gather mode: the input rows the 128 output pixels of that item read are one contiguous range
+                            const long long p0 = tn.n0, p1 = min((long long)tn.n0 + 127, P.g.P - 1);
+                            const long long r0 = p0 / P.g.OW, r1 = p1 / P.g.OW;           // global output rows n*OH + oh
+                            const long long n0i = r0 / P.g.OH, n1i = r1 / P.g.OH;
+                            long long h0 = (r0 - n0i * P.g.OH) * P.g.stride - P.g.pad_t, h1 = (r1 - n1i * P.g.OH) * P.g.stride - P.g.pad_t + P.g.KH;
+                            if (h0 < 0) h0 = 0;
+                            if (h1 > P.g.H) h1 = P.g.H;
+                            const long long e0 = (n0i * P.g.H + h0) * P.g.W * P.g.C, e1 = (n1i * P.g.H + h1) * P.g.W * P.g.C;
+                            const uintptr_t a0 = reinterpret_cast<uintptr_t>(P.g.x + e0) & ~(uintptr_t)15;
+                            const uintptr_t a1 = (reinterpret_cast<uintptr_t>(P.g.x + e1)) & ~(uintptr_t)15;
+                            if (a1 > a0) l2_prefetch_bulk(reinterpret_cast<const void*>(a0), (uint32_t)min((uintptr_t)(256 * 1024), a1 - a0));
+                        } else {
+                            const TcPhase& phn = P.ph[tn.pz];
+                            int tapn = tn.it0 / phn.kchunks, kcn = tn.it0 - tapn * phn.kchunks;
+                            for (int it = 0; it < tn.niter; ++it) {
+                                const TcTap tq = phn.taps[tapn];
+                                tma_prefetch_4d(&maps.a[tq.amap], kcn * 32, tn.w0 + tq.ax, tn.h0 + tq.ay, tn.n0);
+                                if (++kcn == phn.kchunks) { kcn = 0; ++tapn; }
+                            }
+                        }
+                    }
+                }
                 const TcPhase& ph = P.ph[t.pz];
                 int tap = t.it0 / ph.kchunks, kc = t.it0 - tap * ph.kchunks;      // advanced incrementally: the single
                 TcTap tp = ph.taps[tap];                                           // producer thread is latency-critical
