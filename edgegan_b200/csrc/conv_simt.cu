@@ -449,8 +449,15 @@ int eg_simt_conv2d_bwd_data(const eg_conv_shape* s, const float* dy, const float
     return unfused;
 }
 
+int eg_thin_wgrad_ffma(const eg_conv_shape* s, const float* x, const float* dy, float* dw, int accumulate, int sms, cudaStream_t st);
+extern int g_eg_thin_wgrad_off;      // eg_debug_set(7, 1): generic implicit GEMM for the thin layers too (tests compare both)
+
 int eg_simt_conv2d_bwd_weight(const eg_conv_shape* s, const float* x, const float* dy, float* dw, int accumulate,
                               int sm_count, cudaStream_t st) {
+    if (s->Ci <= 8 && !g_eg_thin_wgrad_off) {
+        const int r = eg_thin_wgrad_ffma(s, x, dy, dw, accumulate, sm_count, st);
+        if (r != -100) return r;
+    }
     ConvP p = to_p(s);
     Phase f{};
     f.M = p.KH * p.KW * p.Ci; f.N = p.Co; f.K = p.N * p.OH * p.OW;

@@ -1350,9 +1350,12 @@ extern "C" int eg_filter_set_destroy(long long handle) {
 // conv calls served from a prepared-filter set so far (no preparation launch)
 extern "C" long long eg_filter_set_hits(void) { return (long long)g_managed_hits; }
 
+int g_eg_thin_wgrad_off = 0;
+
 extern "C" int eg_debug_set(int key, int value) {
     if (key < 0 || key >= 8) return -2;
     g_dbg[key] = value;
+    if (key == 7) g_eg_thin_wgrad_off = value;
     return 0;
 }
 

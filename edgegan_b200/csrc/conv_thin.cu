@@ -229,6 +229,91 @@ int launch_im2col(const float* x, float* A, const ThinP& p, long long P, cudaStr
     return 0;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Filter gradient of the thin layers on the CUDA cores: dw[K, Co] += patch(x)[P, K]^T . dy[P, Co], K = KH*KW*Ci <= 160.
+// The tensor-core formulations of this product either pay a patch-matrix round trip or leave most TMEM lanes empty
+// (conv_tc.cu, gather_wgrad), and the generic FFMA implicit GEMM reaches 21 TFLOP/s on it.  Here one block owns ALL K rows
+// of a 64-channel column slab: 32 pixels of dy (8 KB) and of the patch matrix (<= 20 KB) are staged in shared memory,
+// and every thread keeps a 4-channel x KC-row register tile (rows tk, tk + 16, ...): per pixel 1 + KC shared-memory
+// reads (conflict-free: 16 distinct float4 of dy, 2 distinct patch words per warp) feed 4 * KC FMAs.  Pixels are split
+// across blocks; red.global.add.v4 epilogue.
+constexpr int kWgPix = 32;
+
+template <int KC>
+__global__ void __launch_bounds__(256)
+thin_wgrad_ffma_k(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dw, ThinP p, int Co,
+                  long long P, int chunks_per_block) {
+    constexpr int KP = KC * 16;                              // padded K
+    __shared__ __align__(16) float sdy[kWgPix][64];
+    __shared__ float spatch[kWgPix][KP + 1];
+    __shared__ int tab[KP];                                  // k -> kh << 24 | kw << 16 | (kh * W + kw) * Ci + ci ; -1 beyond K
+    const int tid = threadIdx.x, tk = tid >> 4, tc = tid & 15;
+    const int co0 = blockIdx.x * 64;
+    for (int j = tid; j < KP; j += 256) {
+        int t = -1;
+        if (j < p.K) {
+            const int tap = j / p.Ci, ci = j - tap * p.Ci, kh = tap / p.KW, kw = tap - kh * p.KW;
+            t = (kh << 24) | (kw << 16) | ((kh * p.W + kw) * p.Ci + ci);
+        }
+        tab[j] = t;
+    }
+    float acc[KC][4];
+#pragma unroll
+    for (int i = 0; i < KC; ++i) { acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f; }
+    const long long chunk0 = (long long)blockIdx.y * chunks_per_block;
+    for (int ch = 0; ch < chunks_per_block; ++ch) {
+        const long long q0 = (chunk0 + ch) * kWgPix;
+        if (q0 >= P) break;
+        __syncthreads();
+        // dy rows: 32 pixels x 64 channels, 16 bytes per thread x 2
+        for (int i = tid; i < kWgPix * 16; i += 256) {
+            const int pp = i >> 4, c4 = (i & 15) * 4;
+            const long long q = q0 + pp;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (q < P) v = __ldg(reinterpret_cast<const float4*>(dy + q * Co + co0 + c4));
+            *reinterpret_cast<float4*>(&sdy[pp][c4]) = v;
+        }
+        // patch rows: thread -> (pixel = tid / 8, columns tid % 8, +8, ...)
+        {
+            const int pp = tid >> 3;
+            const long long q = q0 + pp;
+            const bool pv = q < P;
+            int ow = 0, oh = 0; long long n = 0;
+            if (pv) { ow = (int)(q % p.OW); const long long t2 = q / p.OW; oh = (int)(t2 % p.OH); n = t2 / p.OH; }
+            const int h0 = oh * p.stride - p.pad_t, w0 = ow * p.stride - p.pad_l;
+            const float* base = x + ((n * p.H + h0) * p.W + w0) * p.Ci;
+            for (int j = tid & 7; j < KP; j += 8) {
+                const int t = tab[j];
+                float v = 0.f;
+                if (pv && t >= 0) {
+                    const int h = h0 + (t >> 24), w = w0 + ((t >> 16) & 255);
+                    if (h >= 0 && h < p.H && w >= 0 && w < p.W) v = __ldg(base + (t & 0xffff));
+                }
+                spatch[pp][j] = v;
+            }
+        }
+        __syncthreads();
+#pragma unroll 4
+        for (int pp = 0; pp < kWgPix; ++pp) {
+            const float4 d = *reinterpret_cast<const float4*>(&sdy[pp][tc * 4]);
+#pragma unroll
+            for (int i = 0; i < KC; ++i) {
+                const float a = spatch[pp][tk + 16 * i];
+                acc[i][0] = fmaf(a, d.x, acc[i][0]); acc[i][1] = fmaf(a, d.y, acc[i][1]);
+                acc[i][2] = fmaf(a, d.z, acc[i][2]); acc[i][3] = fmaf(a, d.w, acc[i][3]);
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < KC; ++i) {
+        const int k = tk + 16 * i;
+        if (k < p.K) {
+            float* o = dw + (size_t)k * Co + co0 + tc * 4;
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o), "f"(acc[i][0]), "f"(acc[i][1]), "f"(acc[i][2]), "f"(acc[i][3]) : "memory");
+        }
+    }
+}
+
 bool thin_common(const eg_conv_shape* s) {
     if (s->Ci < 1 || s->Ci > kThinMaxCi) return false;
     if (s->KH * s->KW * s->Ci > kThinMaxK) return false;
@@ -294,6 +379,42 @@ int eg_thin_conv2d_bwd_weight(const eg_conv_shape* s, const float* x, const floa
     if (int r = eg_tc_conv2d_bwd_weight(&g, A, dy, dW, 0, three_x, st)) return r;
     const int n = p.K * s->Co;
     thin_dw_out_k<<<eg_ceil_div(n, 256), 256, 0, st>>>(dW, dw, n, accumulate);
+    EG_CHECK_LAUNCH();
+    return 0;
+}
+
+// FFMA filter gradient of a thin layer (see thin_wgrad_ffma_k); returns -100 when the shape is not covered
+int eg_thin_wgrad_ffma(const eg_conv_shape* s, const float* x, const float* dy, float* dw, int accumulate, int sms,
+                       cudaStream_t st) {
+    const ThinP p = make_p(s);
+    if (s->Ci > 8 || p.K > 160 || s->Co % 64 || s->KW > 255 || ((s->KH - 1) * s->W + s->KW) * s->Ci >= 65536) return -100;
+    if ((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(dw)) & 15) return -100;
+    const long long P = (long long)s->N * s->OH * s->OW;
+    const long long chunks = (P + kWgPix - 1) / kWgPix;
+    const int slabs = s->Co / 64;
+    long long blocks_y = (8ll * sms + slabs - 1) / slabs;                 // ~8 blocks per SM in flight (30 KB smem, 256 threads)
+    if (blocks_y > chunks) blocks_y = chunks;
+    if (blocks_y > 65535) blocks_y = 65535;
+    const int cpb = (int)((chunks + blocks_y - 1) / blocks_y);
+    blocks_y = (chunks + cpb - 1) / cpb;
+    if (!accumulate) {
+        cudaError_t e = cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)p.K * s->Co, st);
+        if (e != cudaSuccess) return eg_fail(e, __FILE__, __LINE__);
+    }
+    const dim3 grid(slabs, (unsigned)blocks_y);
+    const int KC = (p.K + 15) / 16;
+#define EG_TW(kc) thin_wgrad_ffma_k<kc><<<grid, 256, 0, st>>>(x, dy, dw, p, s->Co, P, cpb)
+    switch (KC) {
+        case 1: EG_TW(1); break;
+        case 2: EG_TW(2); break;
+        case 3: EG_TW(3); break;
+        case 4: EG_TW(4); break;
+        case 5: EG_TW(5); break;
+        case 6: case 7: EG_TW(7); break;
+        case 8: case 9: case 10: EG_TW(10); break;
+        default: return -100;
+    }
+#undef EG_TW
     EG_CHECK_LAUNCH();
     return 0;
 }

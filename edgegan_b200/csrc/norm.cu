@@ -256,8 +256,8 @@ __device__ __forceinline__ float4 colsum4(float4 v, float4 (*red)[8], int cols, 
     if (lane < cols) red[warp][lane] = v;
     __syncthreads();
     float4 s = f4z();
-#pragma unroll
-    for (int w = 0; w < kSmThreads / 32; ++w) { const float4 t = red[w][tx]; s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w; }
+    const int nwarps = blockDim.x >> 5;
+    for (int w = 0; w < nwarps; ++w) { const float4 t = red[w][tx]; s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w; }
     return s;
 }
 
@@ -266,7 +266,7 @@ instnorm_fwd_sm(const float* __restrict__ x, float* __restrict__ y, float* __res
                 int act, int cols) {
     extern __shared__ float4 slab[];                         // [P][cols]
     __shared__ float4 red[kSmThreads / 32][8];
-    const int rows = kSmThreads / cols, tx = threadIdx.x % cols, ty = threadIdx.x / cols;
+    const int rows = blockDim.x / cols, tx = threadIdx.x % cols, ty = threadIdx.x / cols;
     const int n = blockIdx.y, c = (blockIdx.x * cols + tx) * 4;
     const size_t pitch = C / 4;
     const float4* xp = reinterpret_cast<const float4*>(x + (size_t)n * P * C + c);
@@ -306,7 +306,7 @@ instnorm_bwd_sm(const float* __restrict__ x, const float* __restrict__ stats, co
                 const float* __restrict__ addend, float* __restrict__ gx, int P, int C, float eps, int act, int cols) {
     extern __shared__ float4 slab[];                         // [2][P][cols]: centred x, masked cotangent
     __shared__ float4 red[kSmThreads / 32][8];
-    const int rows = kSmThreads / cols, tx = threadIdx.x % cols, ty = threadIdx.x / cols;
+    const int rows = blockDim.x / cols, tx = threadIdx.x % cols, ty = threadIdx.x / cols;
     const int n = blockIdx.y, c = (blockIdx.x * cols + tx) * 4;
     const size_t base = (size_t)n * P * C + c, pitch = C / 4;
     const float4* xp = reinterpret_cast<const float4*>(x + base);
@@ -347,7 +347,7 @@ instnorm_bwd2_sm(const float* __restrict__ x, const float* __restrict__ stats, c
                  float eps, int act, int cols) {
     extern __shared__ float4 slab[];                         // [3][P][cols]: centred x, masked cotangent, tangent
     __shared__ float4 red[kSmThreads / 32][8];
-    const int rows = kSmThreads / cols, tx = threadIdx.x % cols, ty = threadIdx.x / cols;
+    const int rows = blockDim.x / cols, tx = threadIdx.x % cols, ty = threadIdx.x / cols;
     const int n = blockIdx.y, c = (blockIdx.x * cols + tx) * 4;
     const size_t base = (size_t)n * P * C + c, pitch = C / 4;
     const float4* xp = reinterpret_cast<const float4*>(x + base);
@@ -403,10 +403,24 @@ instnorm_bwd2_sm(const float* __restrict__ x, const float* __restrict__ stats, c
 
 // channel-group width (in float4 columns) such that `tensors` slabs of P rows fit in shared memory; 0: use the
 // multi-pass kernels
+// Preference: the widest group whose slabs stay below 64 KB (>= 3 blocks per SM, so that one block's load phase overlaps
+// another's reduction / store phases -- with one 128 KB block per SM the r02 capture showed 25 % of the HBM roofline);
+// 64-byte rows (cols = 4) before 32-byte rows; above that whatever still fits in 200 KB.
 int sm_cols(int P, int C, int tensors) {
+    for (int cols = 8; cols >= 4; cols >>= 1)
+        if (C % (cols * 4) == 0 && (size_t)P * cols * 16 * tensors <= 64 * 1024) return cols;
     for (int cols = 8; cols >= 2; cols >>= 1)
         if (C % (cols * 4) == 0 && (size_t)P * cols * 16 * tensors <= kSmCap) return cols;
     return 0;
+}
+// threads per block: about four rows per thread (small slabs are bound by the block-wide reductions, not by bytes)
+int sm_threads(int P, int cols) {
+    int rows = 4;
+    while (rows < 64 && rows * 4 < P) rows <<= 1;
+    int t = rows * cols;
+    if (t < 64) t = 64;
+    if (t > kSmThreads) t = kSmThreads;
+    return t;
 }
 bool g_sm_attr = false;
 int sm_attrs() {
@@ -495,7 +509,7 @@ int eg_instnorm_fwd(const float* x, float* y, float* stats, int N, int P, int C,
     EG_REQUIRE(x && y && stats && N > 0 && P > 0 && C > 0 && N <= 65535);
     if (const int cols = al16all({x, y, stats}) ? sm_cols(P, C, 1) : 0) {
         if (int r = sm_attrs()) return r;
-        instnorm_fwd_sm<<<dim3(C / (cols * 4), N), kSmThreads, (size_t)P * cols * 16, (cudaStream_t)stream>>>(x, y, stats, P, C, eps, act, cols);
+        instnorm_fwd_sm<<<dim3(C / (cols * 4), N), sm_threads(P, cols), (size_t)P * cols * 16, (cudaStream_t)stream>>>(x, y, stats, P, C, eps, act, cols);
         EG_CHECK_LAUNCH();
         return 0;
     }
@@ -516,7 +530,7 @@ int eg_instnorm_bwd(const float* x, const float* stats, const float* gy, const f
     EG_REQUIRE(x && stats && gy && gx && N > 0 && P > 0 && C > 0 && N <= 65535);
     if (const int cols = al16all({x, stats, gy, addend, gx}) ? sm_cols(P, C, 2) : 0) {
         if (int r = sm_attrs()) return r;
-        instnorm_bwd_sm<<<dim3(C / (cols * 4), N), kSmThreads, (size_t)P * cols * 32, (cudaStream_t)stream>>>(x, stats, gy, addend, gx, P, C, eps, act, cols);
+        instnorm_bwd_sm<<<dim3(C / (cols * 4), N), sm_threads(P, cols), (size_t)P * cols * 32, (cudaStream_t)stream>>>(x, stats, gy, addend, gx, P, C, eps, act, cols);
         EG_CHECK_LAUNCH();
         return 0;
     }
@@ -539,7 +553,7 @@ int eg_instnorm_bwd2(const float* x, const float* stats, const float* gy, const 
     EG_REQUIRE(act != EG_ACT_TANH);   // second derivative of the activation is taken as zero
     if (const int cols = al16all({x, stats, gy, t, out_gy, out_x}) ? sm_cols(P, C, 3) : 0) {
         if (int r = sm_attrs()) return r;
-        instnorm_bwd2_sm<<<dim3(C / (cols * 4), N), kSmThreads, (size_t)P * cols * 48, (cudaStream_t)stream>>>(x, stats, gy, t, out_gy, out_x, P, C, eps, act, cols);
+        instnorm_bwd2_sm<<<dim3(C / (cols * 4), N), sm_threads(P, cols), (size_t)P * cols * 48, (cudaStream_t)stream>>>(x, stats, gy, t, out_gy, out_x, P, C, eps, act, cols);
         EG_CHECK_LAUNCH();
         return 0;
     }
