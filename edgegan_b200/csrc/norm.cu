@@ -326,16 +326,23 @@ instnorm_bwd_sm(const float* __restrict__ x, const float* __restrict__ stats, co
     float4* sgn = slab + (size_t)P * cols;
     const Stat4 s = load_stats4(stats, (size_t)n * C + c, eps);
     float4 v0 = f4z(), v1 = f4z();
-#pragma unroll 4
-    for (int p = ty; p < P; p += rows) {
-        const float4 t = __ldg(xp + p * pitch), g = __ldg(gp + p * pitch);
+    auto row = [&](int p, const float4 t, const float4 g) {
         float4 cc, gn;
         cc.x = t.x - s.mean.x; gn.x = g.x * act_grad(act, cc.x * s.r.x); v0.x += gn.x; v1.x = fmaf(gn.x, cc.x, v1.x);
         cc.y = t.y - s.mean.y; gn.y = g.y * act_grad(act, cc.y * s.r.y); v0.y += gn.y; v1.y = fmaf(gn.y, cc.y, v1.y);
         cc.z = t.z - s.mean.z; gn.z = g.z * act_grad(act, cc.z * s.r.z); v0.z += gn.z; v1.z = fmaf(gn.z, cc.z, v1.z);
         cc.w = t.w - s.mean.w; gn.w = g.w * act_grad(act, cc.w * s.r.w); v0.w += gn.w; v1.w = fmaf(gn.w, cc.w, v1.w);
         scc[p * cols + tx] = cc; sgn[p * cols + tx] = gn;
+    };
+    int p = ty;
+    for (; p + 3 * rows < P; p += 4 * rows) {                // eight independent 16-byte loads in flight per thread
+        const float4 t0 = __ldg(xp + (size_t)p * pitch), g0 = __ldg(gp + (size_t)p * pitch);
+        const float4 t1 = __ldg(xp + (size_t)(p + rows) * pitch), g1 = __ldg(gp + (size_t)(p + rows) * pitch);
+        const float4 t2 = __ldg(xp + (size_t)(p + 2 * rows) * pitch), g2 = __ldg(gp + (size_t)(p + 2 * rows) * pitch);
+        const float4 t3 = __ldg(xp + (size_t)(p + 3 * rows) * pitch), g3 = __ldg(gp + (size_t)(p + 3 * rows) * pitch);
+        row(p, t0, g0); row(p + rows, t1, g1); row(p + 2 * rows, t2, g2); row(p + 3 * rows, t3, g3);
     }
+    for (; p < P; p += rows) row(p, __ldg(xp + (size_t)p * pitch), __ldg(gp + (size_t)p * pitch));
     v0 = colsum4(v0, red, cols, tx);
     v1 = colsum4(v1, red, cols, tx);
     const float4 mg = make_float4(v0.x / P, v0.y / P, v0.z / P, v0.w / P);
@@ -371,9 +378,7 @@ instnorm_bwd2_sm(const float* __restrict__ x, const float* __restrict__ stats, c
     float4* stt = slab + (size_t)2 * P * cols;
     const Stat4 s = load_stats4(stats, (size_t)n * C + c, eps);
     float4 a0 = f4z(), a1 = f4z();
-#pragma unroll 2
-    for (int p = ty; p < P; p += rows) {
-        const float4 xv = __ldg(xp + p * pitch), g = __ldg(gp + p * pitch), tt = __ldg(tp + p * pitch);
+    auto row = [&](int p, const float4 xv, const float4 g, const float4 tt) {
         float4 cc, gn;
         cc.x = xv.x - s.mean.x; gn.x = g.x * act_grad(act, cc.x * s.r.x);
         cc.y = xv.y - s.mean.y; gn.y = g.y * act_grad(act, cc.y * s.r.y);
@@ -382,7 +387,15 @@ instnorm_bwd2_sm(const float* __restrict__ x, const float* __restrict__ stats, c
         a0.x += gn.x; a0.y += gn.y; a0.z += gn.z; a0.w += gn.w;
         a1.x += tt.x; a1.y += tt.y; a1.z += tt.z; a1.w += tt.w;
         scc[p * cols + tx] = cc; sgn[p * cols + tx] = gn; stt[p * cols + tx] = tt;
+    };
+    int p = ty;
+    for (; p + 2 * rows < P; p += 3 * rows) {                // nine independent 16-byte loads in flight per thread
+        const float4 x0 = __ldg(xp + (size_t)p * pitch), g0 = __ldg(gp + (size_t)p * pitch), t0 = __ldg(tp + (size_t)p * pitch);
+        const float4 x1 = __ldg(xp + (size_t)(p + rows) * pitch), g1 = __ldg(gp + (size_t)(p + rows) * pitch), t1 = __ldg(tp + (size_t)(p + rows) * pitch);
+        const float4 x2 = __ldg(xp + (size_t)(p + 2 * rows) * pitch), g2 = __ldg(gp + (size_t)(p + 2 * rows) * pitch), t2 = __ldg(tp + (size_t)(p + 2 * rows) * pitch);
+        row(p, x0, g0, t0); row(p + rows, x1, g1, t1); row(p + 2 * rows, x2, g2, t2);
     }
+    for (; p < P; p += rows) row(p, __ldg(xp + (size_t)p * pitch), __ldg(gp + (size_t)p * pitch), __ldg(tp + (size_t)p * pitch));
     a0 = colsum4(a0, red, cols, tx);
     a1 = colsum4(a1, red, cols, tx);
     const float4 mg = make_float4(a0.x / P, a0.y / P, a0.z / P, a0.w / P), mt = make_float4(a1.x / P, a1.y / P, a1.z / P, a1.w / P);
@@ -418,11 +431,12 @@ instnorm_bwd2_sm(const float* __restrict__ x, const float* __restrict__ stats, c
 // channel-group width (in float4 columns) such that `tensors` slabs of P rows fit in shared memory; 0: use the
 // multi-pass kernels
 // Preference: the widest group whose slabs stay below 64 KB (>= 3 blocks per SM, so that one block's load phase overlaps
-// another's reduction / store phases -- with one 128 KB block per SM the r02 capture showed 25 % of the HBM roofline);
-// 64-byte rows (cols = 4) before 32-byte rows; above that whatever still fits in 200 KB.
+// another's reduction / store phases -- with one 128 KB block per SM the r02 capture showed 25 % of the HBM roofline),
+// down to 32-byte rows;
+// above that whatever still fits in 200 KB.
 int sm_cols(int P, int C, int tensors) {
-    for (int cols = 8; cols >= 4; cols >>= 1)
-        if (C % (cols * 4) == 0 && (size_t)P * cols * 16 * tensors <= 64 * 1024) return cols;
+    for (int cols = 8; cols >= 2; cols >>= 1)
+        if (C % (cols * 4) == 0 && (size_t)P * cols * 16 * tensors <= 72 * 1024) return cols;
     for (int cols = 8; cols >= 2; cols >>= 1)
         if (C % (cols * 4) == 0 && (size_t)P * cols * 16 * tensors <= kSmCap) return cols;
     return 0;
