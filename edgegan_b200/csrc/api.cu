@@ -13,7 +13,7 @@ int eg_simt_conv2d_bwd_weight(const eg_conv_shape* s, const float* x, const floa
 int eg_tc_supported_fwd(const eg_conv_shape* s);
 int eg_tc_supported_bwd_data(const eg_conv_shape* s);
 int eg_tc_supported_bwd_weight(const eg_conv_shape* s);
-int eg_tc_conv2d_fwd(const eg_conv_shape* s, const float* x, const float* w, const float* bias, float* y, int three_x, cudaStream_t st, const EgEpi* epi);
+int eg_tc_conv2d_fwd(const eg_conv_shape* s, const float* x, const float* w, const float* bias, float* y, int three_x, cudaStream_t st, const EgEpi* epi, const eg_conv_shape* scatter = nullptr);
 int eg_tc_conv2d_bwd_data(const eg_conv_shape* s, const float* dy, const float* w, const float* bias, float* dx, int three_x, cudaStream_t st, const EgEpi* epi);
 int eg_tc_conv2d_bwd_weight(const eg_conv_shape* s, const float* x, const float* dy, float* dw, int accumulate, int three_x, cudaStream_t st);
 

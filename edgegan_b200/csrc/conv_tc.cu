@@ -321,6 +321,33 @@ __device__ __forceinline__ bool get_item(const TcParams& P, int id, WorkItem& t)
     return true;
 }
 
+// col2im scatter (TcGather.on == 2): the accumulator row of output pixel (n, oh, ow) holds dy . w^T for every im2col column
+// j = (kh, kw, ci); each valid one is ADDED to dx[n, oh*s - pad + kh, ow*s - pad + kw, ci] (red.global.add; with 8 channels
+// per tap two 16-byte reductions per tap).  Replaces the [P, Npad] product matrix round trip + col2im pass of the thin
+// layers' input gradient; dx is initialised (bias or zero) by the caller.
+struct ScatterCtx { float* base; uint32_t hmask, wmask; };
+__device__ __forceinline__ void drain_scatter_group(const TcParams& P, const ScatterCtx& sc, const int* gtab, const float (&a32)[32],
+                                                    const int c) {
+    if (sc.base == nullptr) return;
+    if (P.g.C == 8) {
+#pragma unroll
+        for (int tp = 0; tp < 4; ++tp) {
+            const int tv = gtab[c + tp * 8];
+            if (((sc.hmask >> (tv >> 24)) & (sc.wmask >> ((tv >> 16) & 255)) & 1u) != 0) {
+                float* o = sc.base + (tv & 0xffff);
+                red_add_v4(o, make_float4(a32[tp * 8], a32[tp * 8 + 1], a32[tp * 8 + 2], a32[tp * 8 + 3]));
+                red_add_v4(o + 4, make_float4(a32[tp * 8 + 4], a32[tp * 8 + 5], a32[tp * 8 + 6], a32[tp * 8 + 7]));
+            }
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            const int tv = gtab[c + j];
+            if (((sc.hmask >> (tv >> 24)) & (sc.wmask >> ((tv >> 16) & 255)) & 1u) != 0) atomicAdd(sc.base + (tv & 0xffff), a32[j]);
+        }
+    }
+}
+
 // One 32-column group of a finished accumulator tile: registers -> per-warp staging tile (XOR-swizzled transpose) -> global.
 // A thread owns one accumulator row, so direct stores would touch 32 different 128-byte lines per instruction; after the
 // transpose each instruction writes 4 rows x 128 contiguous bytes.  `plain`: full tile, no mask / split (bias add and the
@@ -595,7 +622,7 @@ conv_tc_kmajor(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
             // gather mode: this thread's output pixel and the validity masks of its KH x KW window
             const float* gbase = nullptr;
             uint32_t hmask = 0, wmask = 0;
-            if (P.g.on) {
+            if (P.g.on == 1) {
                 const long long pix = (long long)t.n0 + arow;
                 if (pix < P.g.P) {
                     const uint32_t r1 = fd_div((uint32_t)pix, P.g.fow), ow = (uint32_t)pix - r1 * (uint32_t)P.g.OW;
@@ -610,7 +637,7 @@ conv_tc_kmajor(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
                 if ((stage & 1) != grp) { if (++stage == kStages) { stage = 0; phase ^= 1; } continue; }
                 const uint32_t sa = smem_base + stage * stage_bytes;
                 const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + a_col0 + (uint32_t)(stage * 64);
-                if (P.g.on) {
+                if (P.g.on == 1) {
                     // Gather this thread's row of the stage (32 im2col columns) into ITS OWN row of the stage's shared-memory
                     // A tile (no other thread touches that row, so no barrier is involved), then take the common path.
                     // Deliberately compact, rolled loops: ncu's source view of the fully unrolled version (32 loads, ~830
@@ -723,6 +750,19 @@ conv_tc_kmajor(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
             const bool plain = vmask == 0xffu && P.ksplit == 1 && P.epi != EG_EPI_MASK;
             DrainCtx dc;
             dc.stg = stg; dc.vmask = vmask; dc.lane = lane; dc.sub = sub; dc.cj = cj; dc.obase = obase; dc.brow = brow; dc.plain = plain;
+            ScatterCtx sc;
+            sc.base = nullptr; sc.hmask = 0; sc.wmask = 0;
+            if (P.g.on == 2) {                               // this thread's accumulator row = output pixel t.n0 + q*32 + lane
+                const long long pix = (long long)t.n0 + q * 32 + lane;
+                if (pix < P.g.P && !(P.dbg & 4)) {
+                    const uint32_t r1 = fd_div((uint32_t)pix, P.g.fow), ow = (uint32_t)pix - r1 * (uint32_t)P.g.OW;
+                    const uint32_t n = fd_div(r1, P.g.foh), oh = r1 - n * (uint32_t)P.g.OH;
+                    const int h0 = (int)oh * P.g.stride - P.g.pad_t, w0 = (int)ow * P.g.stride - P.g.pad_l;
+                    for (int k = 0; k < P.g.KH; ++k) sc.hmask |= (uint32_t)(h0 + k >= 0 && h0 + k < P.g.H) << k;
+                    for (int k = 0; k < P.g.KW; ++k) sc.wmask |= (uint32_t)(w0 + k >= 0 && w0 + k < P.g.W) << k;
+                    sc.base = P.out + (((long long)n * P.g.H + h0) * P.g.W + w0) * P.g.C;
+                }
+            }
             const int nchunks = (t.niter + kChunkStages - 1) / kChunkStages;
             if (nchunks == 1) {
                 // Short-K item (one chunk): nothing accumulates across chunks, so the groups go TMEM -> staging -> global one
@@ -742,7 +782,8 @@ conv_tc_kmajor(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
                         __syncwarp();
                         if (lane == 0) mbar_arrive(smem_u32(&acc_empty_bar[buf]));
                     }
-                    drain_store_group(P, dc, loff, reinterpret_cast<const float (&)[32]>(r), g * 32);
+                    if (P.g.on == 2) { if (g * 32 < P.g.K) drain_scatter_group(P, sc, gtab, reinterpret_cast<const float (&)[32]>(r), g * 32); }
+                    else drain_store_group(P, dc, loff, reinterpret_cast<const float (&)[32]>(r), g * 32);
                 }
                 ++cg;
                 continue;
@@ -782,8 +823,12 @@ conv_tc_kmajor(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
                 if (lane == 0) mbar_arrive(smem_u32(&acc_empty_bar[buf]));
             }
 #pragma unroll
-            for (int g = 0; g < 4; ++g)
-                if (g * 32 < BN) drain_store_group(P, dc, loff, reinterpret_cast<const float (&)[32]>(acc[g * 32]), g * 32);
+            for (int g = 0; g < 4; ++g) {
+                if (g * 32 < BN) {
+                    if (P.g.on == 2) { if (g * 32 < P.g.K) drain_scatter_group(P, sc, gtab, reinterpret_cast<const float (&)[32]>(acc[g * 32]), g * 32); }
+                    else drain_store_group(P, dc, loff, reinterpret_cast<const float (&)[32]>(acc[g * 32]), g * 32);
+                }
+            }
         }
     }
     tc_fence_before();
@@ -1538,9 +1583,11 @@ static int tc_conv2d_fwd_gather(const eg_conv_shape* s, const float* x, const fl
     return unfused;
 }
 
+// `scatter` (conv_thin.cu): the product is not stored as y[P, Co] but col2im-scattered into y = dx of the conv `scatter`
+// describes (s is then the dense [P pixels] x [Ci] . [Ci x Npad] product, Npad = one column tile)
 int eg_tc_conv2d_fwd(const eg_conv_shape* s, const float* x, const float* w, const float* bias, float* y, int three_x,
-                     cudaStream_t st, const EgEpi* epi) {
-    if (gather_fwd(s)) return tc_conv2d_fwd_gather(s, x, w, bias, y, three_x, st, epi);
+                     cudaStream_t st, const EgEpi* epi, const eg_conv_shape* scatter) {
+    if (scatter == nullptr && gather_fwd(s)) return tc_conv2d_fwd_gather(s, x, w, bias, y, three_x, st, epi);
     if (thin_fwd(s)) {
         if (int r = eg_thin_conv2d_fwd(s, x, w, bias, y, three_x, st)) return r;
         return (epi && epi->mode != EG_EPI_NONE) ? 1 : 0;
@@ -1570,13 +1617,39 @@ int eg_tc_conv2d_fwd(const eg_conv_shape* s, const float* x, const float* w, con
     P.ksplit = pick_ksplit(ph.tiles_w * ph.tiles_h * ph.tiles_n * (s->Co / P.BN), ph.ntaps * ph.kchunks);
     const int unfused = set_epilogue(P, epi);
     if (P.epi == EG_EPI_ACT) P.ksplit = 1;                  // a non-linear epilogue needs the whole sum in one CTA
-    if (P.ksplit > 1) {
+    if (scatter != nullptr) {
+        if (s->Co != P.BN || s->H != 1 || s->W != 1 || P.epi != EG_EPI_NONE || bias != nullptr)
+            return eg_fail_arg("scatter epilogue: one column tile, pixel-list product, no bias / activation", __FILE__, __LINE__);
+        TcGather& g = P.g;
+        g.x = nullptr; g.on = 2; g.H = scatter->H; g.W = scatter->W; g.C = scatter->Ci; g.OH = scatter->OH; g.OW = scatter->OW;
+        g.KH = scatter->KH; g.KW = scatter->KW; g.stride = scatter->stride; g.pad_t = scatter->pad_t; g.pad_l = scatter->pad_l;
+        g.K = scatter->KH * scatter->KW * scatter->Ci; g.P = (long long)scatter->N * scatter->OH * scatter->OW;
+        auto fd = [&](int d, long long nmax) {
+            FastDiv f; f.d = (uint32_t)d;
+            f.m = (d > 1 && nmax * d < (1ll << 32)) ? (uint32_t)(((1ull << 32) + (uint32_t)d - 1) / (uint32_t)d) : 0u;
+            return f;
+        };
+        g.fow = fd(scatter->OW, g.P); g.foh = fd(scatter->OH, g.P);
+    } else if (P.ksplit > 1) {
         cudaError_t e = cudaMemsetAsync(y, 0, sizeof(float) * (size_t)s->N * s->OH * s->OW * s->Co, st);
         if (e != cudaSuccess) return eg_fail(e, __FILE__, __LINE__);
     }
     launch_kmajor(maps, P, ph.tiles_w * ph.tiles_h * ph.tiles_n, s->Co / P.BN, mode, st);
     EG_CHECK_LAUNCH();
     return unfused;
+}
+
+// whether the thin input gradient may use the scatter epilogue (conv_thin.cu)
+int eg_tc_scatter_supported(const eg_conv_shape* c) {
+    const int K = c->KH * c->KW * c->Ci;
+    // OFF by default (eg_debug_set(5, |32) turns it on): measured equal to the product matrix + col2im pass (94.5 vs 94 us on
+    // the critic first layer at batch 64, tools/thin_time.py) -- the atomics cost what the round trip did -- and the col2im
+    // pass is deterministic
+    if (!(g_dbg[5] & 32)) return 0;
+    if (K > kGatherMaxK || K > 128 || c->KH > 8 || c->KW > 8) return 0;
+    if (((c->KH - 1) * c->W + c->KW) * c->Ci >= 65536) return 0;
+    if ((long long)c->N * c->OH * c->OW >= (1ll << 31)) return 0;
+    return 1;
 }
 
 int eg_tc_conv2d_bwd_data(const eg_conv_shape* s, const float* dy, const float* w, const float* bias, float* dx,

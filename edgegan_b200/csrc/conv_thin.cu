@@ -16,7 +16,8 @@
 #include "common.cuh"
 
 int eg_tc_scratch(cudaStream_t st, int slot, size_t bytes, float** out);
-int eg_tc_conv2d_fwd(const eg_conv_shape* s, const float* x, const float* w, const float* bias, float* y, int three_x, cudaStream_t st, const EgEpi* epi = nullptr);
+int eg_tc_conv2d_fwd(const eg_conv_shape* s, const float* x, const float* w, const float* bias, float* y, int three_x, cudaStream_t st, const EgEpi* epi = nullptr, const eg_conv_shape* scatter = nullptr);
+int eg_tc_scatter_supported(const eg_conv_shape* c);
 int eg_tc_conv2d_bwd_weight(const eg_conv_shape* s, const float* x, const float* dy, float* dw, int accumulate, int three_x, cudaStream_t st);
 
 namespace {
@@ -198,6 +199,12 @@ __global__ void thin_transpose_w_k(const float* __restrict__ w, float* __restric
     out[i] = j < K ? __ldg(w + (long long)j * Co + co) : 0.f;
 }
 
+// dx[i] = bias[i % C] (or 0): the initial value the scatter epilogue adds to
+__global__ void thin_bias_fill_k(float* __restrict__ dx, const float* __restrict__ bias, long long n, int C) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        dx[i] = bias != nullptr ? __ldg(bias + (int)(i % C)) : 0.f;
+}
+
 __global__ void thin_dw_out_k(const float* __restrict__ dW, float* __restrict__ dw, int n, int accumulate) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -347,11 +354,19 @@ int eg_thin_conv2d_bwd_data(const eg_conv_shape* s, const float* dy, const float
     const long long P = (long long)s->N * s->OH * s->OW;
     const int Npad = p.K <= 64 ? 64 : 128;
     float *C = nullptr, *wt = nullptr;
-    if (int r = eg_tc_scratch(st, 1, sizeof(float) * (size_t)P * Npad, &C)) return r;
     if (int r = eg_tc_scratch(st, 2, sizeof(float) * (size_t)Npad * s->Co, &wt)) return r;
     thin_transpose_w_k<<<eg_ceil_div((long long)Npad * s->Co, 256), 256, 0, st>>>(w, wt, p.K, Npad, s->Co);
     EG_CHECK_LAUNCH();
     const eg_conv_shape g = gemm_shape(P, s->Co, Npad);
+    if (eg_tc_scatter_supported(s)) {
+        // dx = bias (or 0), then the dense product's epilogue adds every im2col column where it belongs: no [P, Npad]
+        // product matrix, no col2im pass
+        const long long pixels = (long long)s->N * s->H * s->W;
+        thin_bias_fill_k<<<eg_ceil_div(pixels * s->Ci, 256 * 4), 256, 0, st>>>(dx, bias, pixels * s->Ci, s->Ci);
+        EG_CHECK_LAUNCH();
+        return eg_tc_conv2d_fwd(&g, dy, wt, nullptr, dx, three_x, st, nullptr, s);
+    }
+    if (int r = eg_tc_scratch(st, 1, sizeof(float) * (size_t)P * Npad, &C)) return r;
     {
         if (int r = eg_tc_conv2d_fwd(&g, dy, wt, nullptr, C, three_x, st)) return r;
     }

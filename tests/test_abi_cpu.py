@@ -51,3 +51,12 @@ def test_product_has_no_cpu_fallback():
     from edgegan_b200.ops import DeviceOps
     with pytest.raises(RuntimeError):
         DeviceOps()
+
+
+def test_library_has_no_unresolved_internal_symbols():
+    """internal cross-file calls are plain C++ declarations repeated per .cu file: a signature that drifts in one file
+    links as an undefined symbol of a shared library and only fails when first called -- bind everything now"""
+    import ctypes
+    import os
+    from edgegan_b200 import _lib
+    ctypes.CDLL(_lib.LIB_PATH, mode=os.RTLD_NOW | os.RTLD_LOCAL)

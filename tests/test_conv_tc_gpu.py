@@ -79,9 +79,11 @@ def test_tc_conv_trio(dev, ref, case, algo, request):
     request.addfinalizer(lambda: dev.lib.eg_debug_set(5, 2))
     # eg_debug_set(5, mask): bit 0 / 1 / 2 = forward / input gradient / filter gradient through the patch-matrix route of
     # conv_thin.cu, bit 3 = forward gather route OFF, bit 4 = filter-gradient gather route ON.  Thin layers run twice:
-    # (a) forward gathered by the conditioning warps (the default) + gathered filter gradient, (b) everything through
-    # the patch matrix; the default for the filter gradient of these layers is the FFMA kernel (test_ops_gpu.py).
-    routes = [2 | 16, 7 | 8] if Ci <= 8 else [2]
+    # bit 5 = input gradient scattered by the dense product's epilogue instead of product matrix + col2im pass.
+    # (a) forward gathered by the conditioning warps (the default) + gathered filter gradient + scatter epilogue,
+    # (b) everything through the patch matrix; the default for the filter gradient of these layers is the FFMA kernel
+    # (test_ops_gpu.py).
+    routes = [2 | 16 | 32, 7 | 8] if Ci <= 8 else [2]
     for route in routes:
         dev.lib.eg_debug_set(5, route)
         used = [dev.lib.eg_conv2d_algo_for(C.byref(cs), i, 2) for i in range(3)]

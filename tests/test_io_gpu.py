@@ -129,13 +129,13 @@ def test_train_loop_graph_step_equals_eager_step(dev):
         m.update_model(*batches[k])                             # ... and the same iteration launched eagerly
         torch.cuda.synchronize()
         w_eager, l_eager = m.export_variables("var"), m.read_losses()
-        # The critics and the classifier are updated first (runs 1-4), from the snapshot: their weights agree to rounding
-        # (a functional difference -- stale alpha, a missed buffer refill -- would show as O(lr) = 2e-4 there).  G1 / G2 / E
-        # are updated AFTER the critics moved, and the step amplifies the ~1e-7 reordering noise of the fp32 atomics by
-        # ~1e3 per run, so they are held to one learning rate.
+        # The critics and the classifier are updated first (runs 1-4), from the snapshot: half a learning rate (a functional
+        # difference -- stale alpha, a missed buffer refill -- moves their weights by several lr; measured run-to-run
+        # scatter from the reordering of fp32 atomics, amplified by the penalty: up to 0.12 lr).  G1 / G2 / E are updated
+        # AFTER the critics moved, which amplifies that noise once more: 1.5 lr.
         for n in w_eager:
             assert np.isfinite(w_graph[n]).all(), n
-            tol = 5e-6 if n.startswith(("D/", "D_patch2/", "D_patch3/", "D2/")) else 2e-4
+            tol = 1e-4 if n.startswith(("D/", "D_patch2/", "D_patch3/", "D2/")) else 3e-4
             assert np.abs(w_graph[n] - w_eager[n]).max() <= tol, (k, n, np.abs(w_graph[n] - w_eager[n]).max())
         for n in l_eager:
             assert abs(l_graph[n] - l_eager[n]) <= 5e-3 * max(1.0, abs(l_eager[n])), (k, n, l_graph[n], l_eager[n])
