@@ -373,7 +373,7 @@ def main():
         leg2.release()
 
     cpu = None
-    if rank == 0 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:       # reported at N = 1 only (the other ranks would idle in a barrier)
         threads = os.cpu_count() or 1
         sec = oracle_step_time(B, multiclass, 1, 1, threads, H, W)     # ~20-30 s of CPU work on 16 cores
         cpu = {"value": B / sec, "unit": "images/s", "cores": threads, "kind": "port",

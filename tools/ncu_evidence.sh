@@ -23,4 +23,9 @@ cap wgrad     'conv_tc_wgrad'    90 4
 cap instnorm  'instnorm_.*_sm'   140 8
 cap mrugate   'mru_gate_'        26 4
 cap simt      'igemm_simt'       60 4
+# the dominant layer class alone (roofline.traffic): DRAM bytes of one launch against its algorithmic bytes
+for what in fwd dgrad wgrad; do
+  $NCU --set full -k "regex:conv_tc_" --launch-skip 2 --launch-count 1 -f -o "/tmp/r02_conv3x3_$what" python tools/one_conv.py $what > "gpurun_out/r02_conv3x3_$what.log" 2>&1
+  ncu -i "/tmp/r02_conv3x3_$what.ncu-rep" --page raw --csv > "gpurun_out/r02_conv3x3_${what}_raw.csv" 2>/dev/null
+done
 ls -la gpurun_out/ /tmp/*.ncu-rep; du -sh gpurun_out
