@@ -47,6 +47,8 @@ class FilterSet:
         self.handle = h.value
         lib, handle = ops.lib, self.handle
         self._fin = [weakref.finalize(w, lib.eg_filter_set_destroy, handle) for w in filters]
+        for f in self._fin:
+            f.atexit = False         # at interpreter exit the CUDA context may already be gone; the driver frees the memory
 
     def prepare(self):
         _lib.check(self.ops.lib.eg_filter_set_prepare(self.handle, self.ops._st), "eg_filter_set_prepare")
