@@ -498,11 +498,25 @@ def conv_roofline(model, ops, step_fn, algo):
     shapes = [{"pass": k[0], "path": k[1], "shape": k[2], "launches": v[2], "ms": round(v[1], 3),
                "tflops": round(v[0] / v[1] / 1e9, 1) if v[1] > 0 else None,
                "gbs": round(v[3] / v[1] / 1e6, 0) if v[1] > 0 else None} for k, v in top]
+    # DRAM traffic of the dominant launch class from the committed ncu --set full capture (tools/ncu_evidence.sh), next to its
+    # live CUDA-event throughput of this run
+    traffic, dominant = None, None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
+        live = [x for x in shapes if x["shape"] == tj["shape"] and x["pass"] == "conv_fwd" and x["path"] == "tc"]
+        traffic = tj["dram_bytes_per_launch"]
+        dominant = {"kernel": tj["kernel"], "shape": tj["shape"], "algorithmic_bytes_per_launch": tj["algorithmic_bytes_per_launch"],
+                    "dram_bytes_per_launch": tj["dram_bytes_per_launch"], "tensor_pipe_active_pct_ncu": tj["tensor_pipe_active_pct"],
+                    "live_tflops": live[0]["tflops"] if live else None,
+                    "live_frac_of_tf32_peak": (live[0]["tflops"] / peak_kind) if live else None, "source": tj["source"]}
+    except Exception:
+        pass
     if tc_ms > 0:
         ach = tc_fl / tc_ms / 1e9
         mult = 3.0 if algo == "tc3x" else 1.0
         return {"bound": "tensor", "kernel": "tcgen05 implicit-GEMM conv (fwd/dgrad/wgrad), kind::tf32",
-                "achieved": ach, "peak": peak_kind, "unit": "TFLOP/s", "frac": ach / peak_kind, "traffic": None,
+                "achieved": ach, "peak": peak_kind, "unit": "TFLOP/s", "frac": ach / peak_kind, "traffic": traffic,
+                "dominant_launch": dominant,
                 "peak_source": f"{src} bf16 sustained / 2 (tf32 rate)", "conv_ms_per_step": all_ms,
                 "mma_per_algorithmic_flop": mult,
                 "tensor_pipe_work_frac": mult * ach / peak_kind,

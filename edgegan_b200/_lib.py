@@ -33,6 +33,7 @@ SIGNATURES = {
     "eg_set_default_algo": [i32],
     "eg_get_default_algo": [],
     "eg_debug_set": [i32, i32],
+    "eg_norm_debug": [i32],
     "eg_kernel_launches": [],
     "eg_filter_set_create": [vp, i32, i32, C.POINTER(i64)],
     "eg_filter_set_prepare": [i64, vp],

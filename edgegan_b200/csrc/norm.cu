@@ -428,6 +428,67 @@ instnorm_bwd2_sm(const float* __restrict__ x, const float* __restrict__ stats, c
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Streaming two-kernel backward for large slabs: (A) per-(sample, channel) sums of gn and gn*c by a grid over
+// (channel group, pixel chunk, sample) with a red.global.add of 8 floats per block column, (B) a plain element-wise apply.
+// 5 tensor passes instead of 3, but both kernels stream at the copy rate (and B re-reads x / gy largely from L2), where the
+// one-block-per-slab kernel above serialises load / reduce / store phases inside few resident blocks (2.2-2.4 TB/s on the
+// 64x64-pixel... 32x32-pixel slabs, tools/norm_time.py).
+constexpr int kRedRows = 256;      // pixel rows per block of kernel A
+
+__global__ void __launch_bounds__(256)
+instnorm_bwd_reduce_k(const float* __restrict__ x, const float* __restrict__ stats, const float* __restrict__ gy,
+                      float* __restrict__ sums, int P, int C, float eps, int act) {
+    __shared__ float4 red[8][8];
+    const int tx = threadIdx.x & 7, ty = threadIdx.x >> 3;          // 8 float4 columns x 32 rows
+    const int n = blockIdx.z, c = (blockIdx.x * 8 + tx) * 4;
+    const int p0 = blockIdx.y * kRedRows, p1 = min(P, p0 + kRedRows);
+    const size_t base = (size_t)n * P * C + c, pitch = C / 4;
+    const float4* xp = reinterpret_cast<const float4*>(x + base);
+    const float4* gp = reinterpret_cast<const float4*>(gy + base);
+    const Stat4 s = load_stats4(stats, (size_t)n * C + c, eps);
+    float4 v0 = f4z(), v1 = f4z();
+#pragma unroll 4
+    for (int p = p0 + ty; p < p1; p += 32) {
+        const float4 t = __ldg(xp + (size_t)p * pitch), g = __ldg(gp + (size_t)p * pitch);
+        float cc, gn;
+        cc = t.x - s.mean.x; gn = g.x * act_grad(act, cc * s.r.x); v0.x += gn; v1.x = fmaf(gn, cc, v1.x);
+        cc = t.y - s.mean.y; gn = g.y * act_grad(act, cc * s.r.y); v0.y += gn; v1.y = fmaf(gn, cc, v1.y);
+        cc = t.z - s.mean.z; gn = g.z * act_grad(act, cc * s.r.z); v0.z += gn; v1.z = fmaf(gn, cc, v1.z);
+        cc = t.w - s.mean.w; gn = g.w * act_grad(act, cc * s.r.w); v0.w += gn; v1.w = fmaf(gn, cc, v1.w);
+    }
+    v0 = colsum4(v0, red, 8, tx);
+    v1 = colsum4(v1, red, 8, tx);
+    if (ty == 0) {
+        float* o = sums + ((size_t)n * C + c) * 2;               // [n][c][2] = (sum gn, sum gn*c)
+        atomicAdd(o + 0, v0.x); atomicAdd(o + 1, v1.x); atomicAdd(o + 2, v0.y); atomicAdd(o + 3, v1.y);
+        atomicAdd(o + 4, v0.z); atomicAdd(o + 5, v1.z); atomicAdd(o + 6, v0.w); atomicAdd(o + 7, v1.w);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+instnorm_bwd_apply_k(const float* __restrict__ x, const float* __restrict__ stats, const float* __restrict__ gy,
+                     const float* __restrict__ addend, const float* __restrict__ sums, float* __restrict__ gx, long long n4,
+                     int P, int C, float eps, int act) {
+    const int c4 = C / 4;
+    const float invP = 1.f / P;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        const int cq = (int)(i % c4);
+        const long long n = i / ((long long)c4 * P);
+        const size_t sidx = (size_t)n * C + cq * 4;
+        const Stat4 s = load_stats4(stats, sidx, eps);
+        const float4 a = __ldg(reinterpret_cast<const float4*>(sums + sidx * 2)), b = __ldg(reinterpret_cast<const float4*>(sums + sidx * 2 + 4));
+        const float4 t = __ldg(reinterpret_cast<const float4*>(x) + i), g = __ldg(reinterpret_cast<const float4*>(gy) + i);
+        float4 o; float cc, gn;
+        cc = t.x - s.mean.x; gn = g.x * act_grad(act, cc * s.r.x); o.x = s.r.x * (gn - a.x * invP) - s.r.x * s.r.x / s.sd.x * (a.y * invP) * cc;
+        cc = t.y - s.mean.y; gn = g.y * act_grad(act, cc * s.r.y); o.y = s.r.y * (gn - a.z * invP) - s.r.y * s.r.y / s.sd.y * (a.w * invP) * cc;
+        cc = t.z - s.mean.z; gn = g.z * act_grad(act, cc * s.r.z); o.z = s.r.z * (gn - b.x * invP) - s.r.z * s.r.z / s.sd.z * (b.y * invP) * cc;
+        cc = t.w - s.mean.w; gn = g.w * act_grad(act, cc * s.r.w); o.w = s.r.w * (gn - b.z * invP) - s.r.w * s.r.w / s.sd.w * (b.w * invP) * cc;
+        if (addend != nullptr) { const float4 ad = __ldg(reinterpret_cast<const float4*>(addend) + i); o.x += ad.x; o.y += ad.y; o.z += ad.z; o.w += ad.w; }
+        reinterpret_cast<float4*>(gx)[i] = o;
+    }
+}
+
 // channel-group width (in float4 columns) such that `tensors` slabs of P rows fit in shared memory; 0: use the
 // multi-pass kernels
 // Preference: the widest group whose slabs stay below 64 KB (>= 3 blocks per SM, so that one block's load phase overlaps
@@ -450,6 +511,7 @@ int sm_threads(int P, int cols) {
     if (t > kSmThreads) t = kSmThreads;
     return t;
 }
+int g_in_stream = 0;              // eg_norm_debug: -1 never stream, 0 default threshold (P >= 512), > 0 threshold in pixels
 bool g_sm_attr = false;
 int sm_attrs() {
     if (g_sm_attr) return 0;
@@ -531,7 +593,12 @@ __global__ void bn_bwd_apply_k(const float* __restrict__ x, const float* __restr
 
 }  // namespace
 
+int eg_tc_scratch(cudaStream_t st, int slot, size_t bytes, float** out);
+
 extern "C" {
+
+/* development knob (tools/norm_time.py): pixel count from which the instance-norm backward streams in two kernels */
+int eg_norm_debug(int value) { g_in_stream = value; return 0; }
 
 int eg_instnorm_fwd(const float* x, float* y, float* stats, int N, int P, int C, float eps, int act, void* stream) {
     EG_REQUIRE(x && y && stats && N > 0 && P > 0 && C > 0 && N <= 65535);
@@ -556,6 +623,20 @@ int eg_instnorm_fwd(const float* x, float* y, float* stats, int N, int P, int C,
 int eg_instnorm_bwd(const float* x, const float* stats, const float* gy, const float* addend, float* gx, int N,
                     int P, int C, float eps, int act, void* stream) {
     EG_REQUIRE(x && stats && gy && gx && N > 0 && P > 0 && C > 0 && N <= 65535);
+    if (g_in_stream >= 0 && P >= (g_in_stream > 0 ? g_in_stream : 512) && C % 32 == 0 && al16all({x, stats, gy, addend, gx})) {
+        float* sums = nullptr;
+        if (int r = eg_tc_scratch((cudaStream_t)stream, 4, sizeof(float) * (size_t)N * C * 2, &sums)) return r;
+        cudaError_t e = cudaMemsetAsync(sums, 0, sizeof(float) * (size_t)N * C * 2, (cudaStream_t)stream);
+        if (e != cudaSuccess) return eg_fail(e, __FILE__, __LINE__);
+        instnorm_bwd_reduce_k<<<dim3(C / 32, eg_ceil_div(P, kRedRows), N), 256, 0, (cudaStream_t)stream>>>(x, stats, gy, sums, P, C, eps, act);
+        EG_CHECK_LAUNCH();
+        const long long n4 = (long long)N * P * C / 4;
+        long long blocks = (n4 + 256 * 4 - 1) / (256 * 4);
+        if (blocks > 148 * 16) blocks = 148 * 16;
+        instnorm_bwd_apply_k<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, stats, gy, addend, sums, gx, n4, P, C, eps, act);
+        EG_CHECK_LAUNCH();
+        return 0;
+    }
     if (const int cols = al16all({x, stats, gy, addend, gx}) ? sm_cols(P, C, 2) : 0) {
         if (int r = sm_attrs()) return r;
         instnorm_bwd_sm<<<dim3(C / (cols * 4), N), sm_threads(P, cols), (size_t)P * cols * 32, (cudaStream_t)stream>>>(x, stats, gy, addend, gx, P, C, eps, act, cols);

@@ -45,8 +45,9 @@ int eg_device_info(int* sm_count, int* cc_major, int* cc_minor);
 int eg_set_default_algo(int algo);
 int eg_get_default_algo(void);
 
-/* development knob (kernel layout experiments from tools/tc_probe.py); not part of the stable surface */
+/* development knobs (kernel layout / route experiments from tools/); not part of the stable surface */
 int eg_debug_set(int key, int value);
+int eg_norm_debug(int value);
 
 /* Prepared-filter sets.  The tensor-core conv kernels read a re-laid-out copy of the filter (forward: [tap][Co][Ci],
  * input gradient: [tap][Ci][Co]; in the 3xTF32 mode each with its low-order split next to it).  A set keeps those

@@ -32,9 +32,13 @@ for shape in SHAPES:
         i = k[0] % ncopy; k[0] += 1
         dev.instnorm_bwd2(xs[i], st, gs[i], ys[i], ys[(i + 1) % ncopy], gs[(i + 1) % ncopy], "lrelu")
     mb = n_el * 4 / 1e6
+    dev.lib.eg_norm_debug(-1)            # one block per slab (shared-memory resident)
     t1, t2, t3 = timeit(fwd, ncopy), timeit(bwd, ncopy), timeit(bwd2, ncopy)
-    print(f"IN {str(shape):22s} {mb:6.1f} MB/tensor | fwd {t1*1e3:6.1f} us {2*mb/t1/1e3:5.2f} TB/s | bwd {t2*1e3:6.1f} us {3*mb/t2/1e3:5.2f} TB/s | "
-          f"bwd2 {t3*1e3:6.1f} us {5*mb/t3/1e3:5.2f} TB/s", flush=True)
+    dev.lib.eg_norm_debug(1)             # streaming reduce + apply kernels at every size
+    t2s = timeit(bwd, ncopy)
+    dev.lib.eg_norm_debug(0)
+    print(f"IN {str(shape):22s} {mb:6.1f} MB/tensor | fwd {t1*1e3:6.1f} us {2*mb/t1/1e3:5.2f} TB/s | bwd {t2*1e3:6.1f} us {3*mb/t2/1e3:5.2f} TB/s "
+          f"(streaming 2-kernel: {t2s*1e3:6.1f} us) | bwd2 {t3*1e3:6.1f} us {5*mb/t3/1e3:5.2f} TB/s", flush=True)
     del xs, gs, ys
 # thin-layer filter gradient: dedicated FFMA kernel vs the generic implicit GEMM (eg_debug_set(7, 1))
 rnd = lambda *s: dev.from_numpy(rs.standard_normal(s).astype(np.float32))
