@@ -431,9 +431,9 @@ instnorm_bwd2_sm(const float* __restrict__ x, const float* __restrict__ stats, c
 // ---------------------------------------------------------------------------------------------------
 // Streaming two-kernel backward for large slabs: (A) per-(sample, channel) sums of gn and gn*c by a grid over
 // (channel group, pixel chunk, sample) with a red.global.add of 8 floats per block column, (B) a plain element-wise apply.
-// 5 tensor passes instead of 3, but both kernels stream at the copy rate (and B re-reads x / gy largely from L2), where the
-// one-block-per-slab kernel above serialises load / reduce / store phases inside few resident blocks (2.2-2.4 TB/s on the
-// 64x64-pixel... 32x32-pixel slabs, tools/norm_time.py).
+// 5 tensor passes instead of 3.  Built to test whether two streaming kernels beat the one-block-per-slab kernel above, which
+// serialises load / reduce / store phases inside few resident blocks (2.2-2.4 TB/s on 32x32-pixel slabs): they do not --
+// 281 vs 252 us on [384, 32x32, 128], 102 vs 42 us on [384, 8x8, 512] (tools/norm_time.py) -- so this path is OFF by default.
 constexpr int kRedRows = 256;      // pixel rows per block of kernel A
 
 __global__ void __launch_bounds__(256)
@@ -511,7 +511,8 @@ int sm_threads(int P, int cols) {
     if (t > kSmThreads) t = kSmThreads;
     return t;
 }
-int g_in_stream = 0;              // eg_norm_debug: -1 never stream, 0 default threshold (P >= 512), > 0 threshold in pixels
+int g_in_stream = -1;             // eg_norm_debug: -1 never stream (default: measured slower at every size), 0 threshold
+                                  // P >= 512, > 0 threshold in pixels
 bool g_sm_attr = false;
 int sm_attrs() {
     if (g_sm_attr) return 0;
