@@ -498,6 +498,10 @@ def conv_roofline(model, ops, step_fn, algo):
     shapes = [{"pass": k[0], "path": k[1], "shape": k[2], "launches": v[2], "ms": round(v[1], 3),
                "tflops": round(v[0] / v[1] / 1e9, 1) if v[1] > 0 else None,
                "gbs": round(v[3] / v[1] / 1e6, 0) if v[1] > 0 else None} for k, v in top]
+    thin_shapes = [{"pass": k[0], "shape": k[2], "launches": v[2], "ms": round(v[1], 3),
+                    "gbs": round(v[3] / v[1] / 1e6, 0) if v[1] > 0 else None,
+                    "hbm_frac": round(v[3] / v[1] / 1e6 / hbm, 3) if v[1] > 0 else None}
+                   for k, v in sorted(by_shape.items(), key=lambda kv: -kv[1][1]) if k[1] == "thin"]
     # DRAM traffic of the dominant launch class from the committed ncu --set full capture (tools/ncu_evidence.sh), next to its
     # live CUDA-event throughput of this run
     traffic, dominant = None, None
@@ -524,7 +528,8 @@ def conv_roofline(model, ops, step_fn, algo):
                          "MMA (hi*hi + lo*hi + hi*lo), so the tensor pipe is busy tensor_pipe_work_frac of its tf32 peak"),
                 "thin_layers": {"bound": "hbm", "achieved": thin_b / thin_ms / 1e6 if thin_ms > 0 else None, "peak": hbm, "unit": "GB/s",
                                 "frac": thin_b / thin_ms / 1e6 / hbm if thin_ms > 0 else None, "ms_per_step": thin_ms,
-                                "note": "image-side layers (<= 8 channels on one side): algorithmic bytes = 4*(input + output) per launch"},
+                                "note": "image-side layers (<= 8 channels on one side): algorithmic bytes = 4*(input + output) per launch",
+                                "by_shape": thin_shapes},
                 "detail": detail, "by_shape": shapes}
     simt_fl = sum(v[0] for v in agg.values())
     ach = simt_fl / all_ms / 1e9 if all_ms > 0 else 0.0
