@@ -26,6 +26,11 @@ class FilterDesc(C.Structure):
     """eg_filter_desc (include/edgegan_b200.h)"""
     _fields_ = [("w", C.c_void_p), ("taps", C.c_int), ("Ci", C.c_int), ("Co", C.c_int)]
 
+class SnDesc(C.Structure):
+    """eg_sn_desc (include/edgegan_b200.h)"""
+    _fields_ = [(n, C.c_void_p) for n in ("W", "u", "Wbar", "ws", "G", "gW", "Wa", "Wi", "Ga", "Gi")] + \
+               [(n, C.c_int) for n in ("K", "C", "cin", "hd")]
+
 # name -> argtypes ; every function returns int (0 = ok) unless listed in _RESTYPE
 SIGNATURES = {
     "eg_abi_version": [],
@@ -96,6 +101,10 @@ SIGNATURES = {
     "eg_spectral_norm_ws_floats": [i32, i32],
     "eg_spectral_norm_fwd": [vp, vp, vp, vp, i32, i32, vp],
     "eg_spectral_norm_bwd": [vp, vp, vp, vp, vp, i32, i32, vp],
+    "eg_spectral_norm_set_create": [vp, i32, C.POINTER(i64)],
+    "eg_spectral_norm_set_fwd": [i64, vp],
+    "eg_spectral_norm_set_bwd": [i64, vp],
+    "eg_spectral_norm_set_destroy": [i64],
     "eg_softmax_ce_bwd": [vp, vp, i32, i32, i32, i32, i32, f32, f32, vp, vp, vp],
     "eg_onehot_concat": [vp, i32, i32, i32, vp, vp],
     "eg_rmsprop": [vp, vp, vp, i64, f32, f32, f32, vp],

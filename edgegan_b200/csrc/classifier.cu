@@ -2,6 +2,9 @@
 // nn/modules/conv.py:133-243, spectral norm nn/modules/normalization.py:38-76, focal / CE losses
 // nn/functional.py:5-16).  All HBM-bound glue; the classifier's convolutions use the shared conv trio.
 #include "common.cuh"
+#include <algorithm>
+#include <mutex>
+#include <vector>
 
 namespace {
 
@@ -376,6 +379,151 @@ sn_gw_k(const float* __restrict__ W, const float* __restrict__ u, const float* _
     }
 }
 
+// ---- the same for a whole network in three launches per direction (eg_spectral_norm_set_*) ------------------------------
+// One table entry per weight tensor; blockIdx.y (z for the r pass) selects the tensor and blocks beyond a tensor's own
+// extent leave.  A tensor may be SPLIT along its input-channel axis (cin = hd + rest): Wbar is then also written as two
+// contiguous filters (Wa [taps, hd, C], Wi [taps, cin - hd, C]) and dL/dWbar is read from two such parts (Ga, Gi) --
+// the classifier's update gate convolves concat(a, image) as two convs (classifier.py:69-76 of the reference builds the concat).
+struct SnDesc {
+    const float* W; const float* u; float* Wbar; float* ws;
+    const float* G; float* gW;
+    float* Wa; float* Wi;
+    const float* Ga; const float* Gi;
+    int K, C, cin, hd;
+};
+struct SnSet { SnDesc* tab; float* dots; int n, Kmax, Cmax; long long nmax; bool bwd_ok; };
+static std::mutex g_sn_mu;
+static std::vector<SnSet*> g_sn_sets;
+
+__device__ __forceinline__ unsigned sn_blocks(long long n) {
+    long long g = (n + 1023) / 1024;
+    return (unsigned)(g > 1184 ? 1184 : (g < 1 ? 1 : g));
+}
+// offset of element (k, c) inside the split part it belongs to; part = 0 (a) or 1 (i)
+__device__ __forceinline__ long long sn_split(const SnDesc& d, int k, int c, int& part) {
+    const int tap = k / d.cin, ci = k - tap * d.cin;
+    if (ci < d.hd) { part = 0; return ((long long)tap * d.hd + ci) * d.C + c; }
+    part = 1;
+    return ((long long)tap * (d.cin - d.hd) + (ci - d.hd)) * d.C + c;
+}
+__device__ __forceinline__ float sn_G(const SnDesc& d, long long i) {
+    if (d.Ga == nullptr) return d.G[i];
+    int part;
+    const int k = (int)(i / d.C), c = (int)(i - (long long)k * d.C);
+    const long long o = sn_split(d, k, c, part);
+    return part == 0 ? d.Ga[o] : d.Gi[o];
+}
+__global__ void __launch_bounds__(256)
+sn_set_p_k(const SnDesc* __restrict__ tab) {
+    const SnDesc d = tab[blockIdx.y];
+    if (blockIdx.x == 0)                                     // r and the scalars are accumulated by the passes that follow
+        for (int i = threadIdx.x; i < d.C + 8; i += blockDim.x) d.ws[d.K + i] = 0.f;
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= d.K) return;
+    float s = 0.f;
+    for (int c = lane; c < d.C; c += 32) s = fmaf(d.W[(size_t)row * d.C + c], d.u[c], s);
+    s = warp_sum(s);
+    if (lane == 0) d.ws[row] = s;
+}
+__global__ void __launch_bounds__(256)
+sn_set_r_k(const SnDesc* __restrict__ tab, int kslab) {
+    __shared__ float red[33];
+    const SnDesc d = tab[blockIdx.z];
+    const int k0 = blockIdx.y * kslab;
+    if (k0 >= d.K || blockIdx.x * blockDim.x >= d.C) return;
+    const float* p = d.ws;
+    float s = 0.f;
+    for (int k = threadIdx.x; k < d.K; k += blockDim.x) s = fmaf(p[k], p[k], s);
+    const float np = sqrtf(block_sum(s, red));
+    const float inv = 1.f / (np + SN_EPS);
+    const int k1 = min(d.K, k0 + kslab);
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= d.C) return;
+    float acc = 0.f;
+    for (int k = k0; k < k1; ++k) acc = fmaf(p[k] * inv, d.W[(size_t)k * d.C + c], acc);
+    atomicAdd(d.ws + d.K + c, acc);
+}
+__global__ void __launch_bounds__(256)
+sn_set_scale_k(const SnDesc* __restrict__ tab) {
+    __shared__ float red[33];
+    const SnDesc d = tab[blockIdx.y];
+    const long long n = (long long)d.K * d.C;
+    const unsigned g = sn_blocks(n);
+    if (blockIdx.x >= g) return;
+    const float *p = d.ws, *r = d.ws + d.K;
+    float* scal = d.ws + d.K + d.C;
+    float s = 0.f;
+    for (int c = threadIdx.x; c < d.C; c += blockDim.x) s = fmaf(r[c], r[c], s);
+    const float nr = sqrtf(block_sum(s, red));
+    const float sigma = nr * nr / (nr + SN_EPS);
+    if (blockIdx.x == 0) {
+        float t = 0.f;
+        for (int k = threadIdx.x; k < d.K; k += blockDim.x) t = fmaf(p[k], p[k], t);
+        t = block_sum(t, red);
+        if (threadIdx.x == 0) { scal[0] = sqrtf(t); scal[1] = nr; scal[2] = sigma; }
+    }
+    const float inv = 1.f / sigma;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)g * blockDim.x) {
+        const float v = d.W[i] * inv;
+        d.Wbar[i] = v;
+        if (d.Wa != nullptr) {
+            int part;
+            const int k = (int)(i / d.C), c = (int)(i - (long long)k * d.C);
+            const long long o = sn_split(d, k, c, part);
+            (part == 0 ? d.Wa : d.Wi)[o] = v;
+        }
+    }
+}
+__global__ void __launch_bounds__(256)
+sn_set_dot_k(const SnDesc* __restrict__ tab, float* __restrict__ dots) {
+    __shared__ float red[33];
+    const SnDesc d = tab[blockIdx.y];
+    const long long n = (long long)d.K * d.C;
+    const unsigned g = sn_blocks(n);
+    if (blockIdx.x >= g) return;
+    float s = 0.f;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)g * blockDim.x)
+        s = fmaf(sn_G(d, i), d.W[i], s);
+    s = block_sum(s, red);
+    if (threadIdx.x == 0) atomicAdd(dots + blockIdx.y, s);
+}
+__global__ void __launch_bounds__(256)
+sn_set_gv_k(const SnDesc* __restrict__ tab) {
+    const SnDesc d = tab[blockIdx.y];
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= d.K) return;
+    const float *r = d.ws + d.K, *scal = d.ws + d.K + d.C;
+    const float nr = scal[1];
+    const float coef = (nr * nr + 2.f * SN_EPS * nr) / ((nr + SN_EPS) * (nr + SN_EPS)) / nr;
+    float s = 0.f;
+    for (int c = lane; c < d.C; c += 32) s = fmaf(d.W[(size_t)row * d.C + c], coef * r[c], s);
+    s = warp_sum(s);
+    if (lane == 0) d.ws[d.K + d.C + 8 + row] = s;
+}
+__global__ void __launch_bounds__(256)
+sn_set_gw_k(const SnDesc* __restrict__ tab, const float* __restrict__ dots) {
+    __shared__ float red[33];
+    const SnDesc d = tab[blockIdx.y];
+    const long long n = (long long)d.K * d.C;
+    const unsigned g = sn_blocks(n);
+    if (blockIdx.x >= g) return;
+    const float *p = d.ws, *r = d.ws + d.K, *scal = d.ws + d.K + d.C, *gv = d.ws + d.K + d.C + 8;
+    float t = 0.f;
+    for (int k = threadIdx.x; k < d.K; k += blockDim.x) t = fmaf(gv[k], p[k], t);
+    const float gvp = block_sum(t, red);
+    const float np = scal[0], nr = scal[1], sigma = scal[2], sdot = dots[blockIdx.y];
+    const float coef = (nr * nr + 2.f * SN_EPS * nr) / ((nr + SN_EPS) * (nr + SN_EPS)) / nr;
+    const float a = 1.f / (np + SN_EPS), b = gvp / (np * (np + SN_EPS) * (np + SN_EPS));
+    const float f = sdot / (sigma * sigma), isg = 1.f / sigma;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)g * blockDim.x) {
+        const int k = (int)(i / d.C), c = (int)(i - (long long)k * d.C);
+        const float v = p[k] * a;
+        const float gp = gv[k] * a - b * p[k];
+        const float dsig = v * (coef * r[c]) + gp * d.u[c];
+        d.gW[i] = sn_G(d, i) * isg - f * dsig;
+    }
+}
+
 // ---- softmax cross-entropy losses (functional.py:5-16) -------------------------------------------------
 // one thread per sample; labels are the float class ids stored in column `label_col` of z
 __global__ void softmax_ce_bwd_k(const float* __restrict__ logits, const float* __restrict__ z, int zstride, int label_col,
@@ -621,6 +769,74 @@ int eg_spectral_norm_bwd(const float* W, const float* u, float* ws, const float*
     sn_gv_k<<<eg_ceil_div(K, 8), 256, 0, ST>>>(W, r, scal, gv, K, C);
     EG_CHECK_LAUNCH();
     sn_gw_k<<<g, 256, 0, ST>>>(W, u, p, r, scal, gv, Gbar, gW, K, C);
+    EG_CHECK_LAUNCH(); return 0;
+}
+// ---- spectral norm of a whole network: table on the device, 3 launches forward, memset + 3 launches backward ----------
+int eg_spectral_norm_set_create(const eg_sn_desc* descs, int n, long long* handle) {
+    EG_REQUIRE(descs && handle && n > 0);
+    static_assert(sizeof(eg_sn_desc) == sizeof(SnDesc), "eg_sn_desc and the device table entry must have the same layout");
+    SnSet* s = new SnSet();
+    s->n = n; s->Kmax = 0; s->Cmax = 0; s->nmax = 0; s->bwd_ok = true;
+    for (int i = 0; i < n; ++i) {
+        const eg_sn_desc& d = descs[i];
+        const bool split = d.Wa || d.Wi || d.Ga || d.Gi;
+        if (!(d.W && d.u && d.Wbar && d.ws && d.K > 0 && d.C > 0) ||
+            (split && !(d.Wa && d.Wi && d.cin > 0 && d.hd > 0 && d.hd < d.cin && d.K % d.cin == 0))) {
+            delete s;
+            return eg_fail_arg("eg_spectral_norm_set_create: bad descriptor", __FILE__, __LINE__);
+        }
+        if (!(d.gW && (d.G || (d.Ga && d.Gi && split)))) s->bwd_ok = false;
+        s->Kmax = std::max(s->Kmax, d.K); s->Cmax = std::max(s->Cmax, d.C);
+        s->nmax = std::max(s->nmax, (long long)d.K * d.C);
+    }
+    cudaError_t e = cudaMalloc(&s->tab, sizeof(SnDesc) * n);
+    if (e == cudaSuccess) e = cudaMalloc(&s->dots, sizeof(float) * n);
+    if (e == cudaSuccess) e = cudaMemcpy(s->tab, descs, sizeof(SnDesc) * n, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { delete s; return eg_fail(e, __FILE__, __LINE__); }
+    std::lock_guard<std::mutex> lk(g_sn_mu);
+    g_sn_sets.push_back(s);
+    *handle = (long long)g_sn_sets.size() - 1;
+    return 0;
+}
+static SnSet* sn_get(long long h) {
+    std::lock_guard<std::mutex> lk(g_sn_mu);
+    return (h >= 0 && h < (long long)g_sn_sets.size()) ? g_sn_sets[(size_t)h] : nullptr;
+}
+int eg_spectral_norm_set_destroy(long long handle) {
+    std::lock_guard<std::mutex> lk(g_sn_mu);
+    if (handle < 0 || handle >= (long long)g_sn_sets.size() || !g_sn_sets[(size_t)handle]) return 0;
+    SnSet* s = g_sn_sets[(size_t)handle];
+    g_sn_sets[(size_t)handle] = nullptr;
+    cudaFree(s->tab); cudaFree(s->dots);
+    delete s;
+    return 0;
+}
+static unsigned sn_host_blocks(long long n) {
+    long long g = (n + 1023) / 1024;
+    return (unsigned)(g > 1184 ? 1184 : (g < 1 ? 1 : g));
+}
+int eg_spectral_norm_set_fwd(long long handle, void* stream) {
+    SnSet* s = sn_get(handle);
+    EG_REQUIRE(s != nullptr);
+    sn_set_p_k<<<dim3(eg_ceil_div(s->Kmax, 8), s->n), 256, 0, ST>>>(s->tab);
+    EG_CHECK_LAUNCH();
+    const int kslab = 64;
+    sn_set_r_k<<<dim3(eg_ceil_div(s->Cmax, 256), eg_ceil_div(s->Kmax, kslab), s->n), 256, 0, ST>>>(s->tab, kslab);
+    EG_CHECK_LAUNCH();
+    sn_set_scale_k<<<dim3(sn_host_blocks(s->nmax), s->n), 256, 0, ST>>>(s->tab);
+    EG_CHECK_LAUNCH(); return 0;
+}
+int eg_spectral_norm_set_bwd(long long handle, void* stream) {
+    SnSet* s = sn_get(handle);
+    EG_REQUIRE(s != nullptr && s->bwd_ok);
+    cudaError_t e = cudaMemsetAsync(s->dots, 0, sizeof(float) * s->n, ST);
+    if (e != cudaSuccess) return eg_fail(e, __FILE__, __LINE__);
+    const dim3 g(sn_host_blocks(s->nmax), s->n);
+    sn_set_dot_k<<<g, 256, 0, ST>>>(s->tab, s->dots);
+    EG_CHECK_LAUNCH();
+    sn_set_gv_k<<<dim3(eg_ceil_div(s->Kmax, 8), s->n), 256, 0, ST>>>(s->tab);
+    EG_CHECK_LAUNCH();
+    sn_set_gw_k<<<g, 256, 0, ST>>>(s->tab, s->dots);
     EG_CHECK_LAUNCH(); return 0;
 }
 int eg_softmax_ce_bwd(const float* logits, const float* z, int z_stride, int label_col, int B, int C, int focal,

@@ -78,8 +78,6 @@ class Classifier(object):
         self.layers = [s.name[:-len("/weights")] for s in store.specs if s.name.endswith("/weights")]
         self._wbar_valid = False
         self.cache = None
-        biggest = max(int(np.prod(s.shape)) for s in store.specs if s.name.endswith("/weights"))
-        self._gbar = ops.buf(f"{name}/gbar", (biggest,))       # dL/dWbar scratch shared by all layers
 
     # ---- variables -----------------------------------------------------------------------------------
     def load_u(self, values):
@@ -102,24 +100,36 @@ class Classifier(object):
         if self._wbar_valid:
             return
         ops = self.ops
-        self.wbar, self.ws = {}, {}
+        self.wbar, self.ws, self.gbar, items = {}, {}, {}, []
         for scope in self.layers:
             W = self.store.var[scope + "/weights"]
             Cn = W.shape[-1]
             K = W.numel() // Cn
             wb = ops.buf(scope + "/wbar", W.shape)
             ws = ops.buf(scope + "/sn_ws", (ops.sn_ws_floats(K, Cn),))
-            ops.spectral_norm_fwd(W, self.aux.var[scope + "/u"], wb, ws)
             self.wbar[scope], self.ws[scope] = wb, ws
+            it = dict(W=W, u=self.aux.var[scope + "/u"], Wbar=wb, ws=ws, gW=self.store.g[scope + "/weights"])
             if scope.endswith("/update_gate"):
                 # conv(concat(a, inp)) = conv(a, W[:, :, :hd]) + conv(inp, W[:, :, hd:]): two contiguous filter copies, so
-                # the hd-channel part runs on the tensor cores (hd + 3 input channels would not) and no concat is built
+                # the hd-channel part runs on the tensor cores (hd + 3 input channels would not) and no concat is built;
+                # dL/dWbar likewise arrives as two filter gradients
                 k, _, cin, co = W.shape
                 hd = cin - self.c_dim
                 wa, wi = ops.buf(scope + "/wbar_a", (k, k, hd, co)), ops.buf(scope + "/wbar_i", (k, k, self.c_dim, co))
-                ops.copy2d(wb, 0, cin * co, wa, 0, hd * co, k * k, hd * co)
-                ops.copy2d(wb, hd * co, cin * co, wi, 0, self.c_dim * co, k * k, self.c_dim * co)
+                ga, gi = ops.buf(scope + "/gbar_a", (k, k, hd, co)), ops.buf(scope + "/gbar_i", (k, k, self.c_dim, co))
                 self.wbar[scope + "#a"], self.wbar[scope + "#i"] = wa, wi
+                self.gbar[scope + "#a"], self.gbar[scope + "#i"] = ga, gi
+                it.update(Wa=wa, Wi=wi, Ga=ga, Gi=gi, hd=hd)
+            else:
+                self.gbar[scope] = it["G"] = ops.buf(scope + "/gbar", W.shape)      # dL/dWbar of this layer
+            items.append(it)
+        # one descriptor table for the whole network: 3 launches normalise all filters (4 more map all dL/dWbar to dL/dW)
+        key = tuple(t.data_ptr() for it in items for t in it.values() if hasattr(t, "data_ptr"))
+        if getattr(self, "_sn_key", None) != key:
+            if getattr(self, "_sn", None) is not None:
+                self._sn.close()
+            self._sn, self._sn_key = ops.spectral_norm_set(items), key
+        self._sn.fwd()
         # prepared copies (tensor-core operand layouts) of the normalised filters: one kernel for the whole network
         algo = getattr(ops, "default_algo", None)
         tc = [w for w in self.wbar.values() if w.dim() == 4 and w.shape[2] % 32 == 0 and w.shape[3] % 32 == 0]
@@ -219,12 +229,9 @@ class Classifier(object):
 
     # ---- backward ------------------------------------------------------------------------------------
     def _wgrad(self, scope, x, dy, k, tag):
-        """dL/dWbar by the conv filter-gradient kernel, then through the spectral norm into the gradient store"""
+        """dL/dWbar by the conv filter-gradient kernel; backward() maps all of them through the spectral norm at its end"""
         ops, full = self.ops, f"{self.name}/{scope}"
-        W = self.store.var[full + "/weights"]
-        gbar = self._gbar[:W.numel()].view(W.shape)
-        ops.conv_bwd_weight(x, dy, gbar, 1, (k - 1) // 2, False)
-        ops.spectral_norm_bwd(W, self.aux.var[full + "/u"], self.ws[full], gbar, self.store.g[full + "/weights"])
+        ops.conv_bwd_weight(x, dy, self.gbar[full], 1, (k - 1) // 2, False)
         ops.bias_grad(dy, self.store.g[full + "/biases"].view(-1), False)
 
     def backward(self, glogits, param_grads, input_grad, tag="bwd"):
@@ -235,10 +242,7 @@ class Classifier(object):
         C, K = feat.shape[1], self.num_classes
         fc = f"{nm}/fully_connected"
         if param_grads:
-            Wfc = self.store.var[fc + "/weights"]
-            gbar = self._gbar[:Wfc.numel()].view(Wfc.shape)
-            ops.conv_bwd_weight(feat.view(n, 1, 1, C), glogits.view(n, 1, 1, K), gbar.view(1, 1, C, K), 1, 0, False)
-            ops.spectral_norm_bwd(Wfc, self.aux.var[fc + "/u"], self.ws[fc], gbar, self.store.g[fc + "/weights"])
+            ops.conv_bwd_weight(feat.view(n, 1, 1, C), glogits.view(n, 1, 1, K), self.gbar[fc].view(1, 1, C, K), 1, 0, False)
             ops.bias_grad(glogits, self._g("fully_connected/biases"), False)
         gfeat = B("gfeat", feat.shape)
         ops.conv_bwd_data(glogits.view(n, 1, 1, K), self.wbar[fc].view(1, 1, C, K), None, gfeat.view(n, 1, 1, C), 1, 0)
@@ -278,16 +282,9 @@ class Classifier(object):
                 self._wgrad(f"{p}/Conv", inp, g_img, 3, tag)
             gate = f"{nm}/{p}/update_gate"
             if param_grads:
-                # dL/dWbar of the two filter parts, assembled into the [k, k, hd+3, hd] layout for the spectral-norm backward
-                Wg = self.store.var[gate + "/weights"]
-                cin, co = hd + self.c_dim, hd
-                gbar = self._gbar[:Wg.numel()].view(Wg.shape)
-                ga, gi_w = B(f"u{t}/gbar_a", (3, 3, hd, co)), B(f"u{t}/gbar_i", (3, 3, self.c_dim, co))
-                ops.conv_bwd_weight(u["a_in"], g_cg, ga, 1, 1, False)
-                ops.conv_bwd_weight(inp, g_cg, gi_w, 1, 1, False)
-                ops.copy2d(ga, 0, hd * co, gbar, 0, cin * co, 9, hd * co)
-                ops.copy2d(gi_w, 0, self.c_dim * co, gbar, hd * co, cin * co, 9, self.c_dim * co)
-                ops.spectral_norm_bwd(Wg, self.aux.var[gate + "/u"], self.ws[gate], gbar, self.store.g[gate + "/weights"])
+                # dL/dWbar of the two filter parts; the spectral-norm backward reads them as one [k, k, hd+3, hd] tensor
+                ops.conv_bwd_weight(u["a_in"], g_cg, self.gbar[gate + "#a"], 1, 1, False)
+                ops.conv_bwd_weight(inp, g_cg, self.gbar[gate + "#i"], 1, 1, False)
                 ops.bias_grad(g_cg, self.store.g[gate + "/biases"].view(-1), False)
             g_ain = U("g_ain", hd)
             ops.conv_bwd_data(g_cg, self.wbar[gate + "#a"], None, g_ain, 1, 1)
@@ -306,6 +303,7 @@ class Classifier(object):
         ops.prelu_bwd(c["c0"], self._v("Conv/prelu/param"), g_out, g_c0, self._g("Conv/prelu/param") if param_grads else None)
         if param_grads:
             self._wgrad("Conv", c["x"], g_c0, 7, tag)
+            self._sn.bwd()                 # every dL/dWbar is in place: dL/dW of all 22 filters (through sigma, v and u')
         if not input_grad:
             return None
         for l in range(3, 0, -1):                      # pyramid: pyr[l] = mean_pool(pyr[l-1])

@@ -59,6 +59,48 @@ class FilterSet:
         self.ops.lib.eg_filter_set_destroy(self.handle)
 
 
+class SpectralNormSet:
+    """Device-side descriptor table of the spectrally normalised weights of one network; `fwd()` / `bwd()` enqueue 3 / 4
+    graph nodes for the whole network on the current stream.  Destroyed with the first of its tensors (FilterSet's rule)."""
+
+    def __init__(self, ops, items):
+        import weakref
+        self.ops = ops
+        descs = (_lib.SnDesc * len(items))()
+        keep = []
+        for d, it in zip(descs, items):
+            W = it["W"]
+            Cn = W.shape[-1]
+            d.K, d.C = W.numel() // Cn, Cn
+            for name in ("W", "u", "Wbar", "ws", "G", "gW", "Wa", "Wi", "Ga", "Gi"):
+                t = it.get(name)
+                if t is not None:
+                    if not t.is_contiguous():
+                        raise ValueError(f"spectral_norm_set: {name} must be contiguous")
+                    setattr(d, name, t.data_ptr())
+                    keep.append(t)
+            if it.get("Wa") is not None:
+                d.cin, d.hd = W.shape[-2], it["hd"]
+        h = C.c_longlong(-1)
+        _lib.check(ops.lib.eg_spectral_norm_set_create(descs, len(items), C.byref(h)), "eg_spectral_norm_set_create")
+        self.handle = h.value
+        lib, handle = ops.lib, self.handle
+        self._fin = [weakref.finalize(t, lib.eg_spectral_norm_set_destroy, handle) for t in keep]
+        for f in self._fin:
+            f.atexit = False
+
+    def fwd(self):
+        _lib.check(self.ops.lib.eg_spectral_norm_set_fwd(self.handle, self.ops._st), "eg_spectral_norm_set_fwd")
+
+    def bwd(self):
+        _lib.check(self.ops.lib.eg_spectral_norm_set_bwd(self.handle, self.ops._st), "eg_spectral_norm_set_bwd")
+
+    def close(self):
+        for f in self._fin:
+            f.detach()
+        _lib.check(self.ops.lib.eg_spectral_norm_set_destroy(self.handle), "eg_spectral_norm_set_destroy")
+
+
 class DeviceOps:
     """CUDA implementation (the only one the product has)."""
 
@@ -398,6 +440,11 @@ class DeviceOps:
     def spectral_norm_bwd(self, W, u, ws, Gbar, gW):
         Cn = W.shape[-1]
         _lib.check(self.lib.eg_spectral_norm_bwd(_p(W), _p(u), _p(ws), _p(Gbar), _p(gW), W.numel() // Cn, Cn, self._st), "spectral_norm_bwd")
+
+    def spectral_norm_set(self, items):
+        """One table for all spectrally normalised weights of a network (eg_spectral_norm_set_*): `items` = dicts with W,
+        u, Wbar, ws and optionally G, gW (backward) and Wa, Wi, Ga, Gi, hd (tensor split along its input-channel axis)."""
+        return SpectralNormSet(self, items)
 
     def softmax_ce_bwd(self, logits, z, label_col, focal, weight, inv_global_batch, glogits, loss):
         B, Cn = logits.shape

@@ -245,6 +245,23 @@ int eg_spectral_norm_ws_floats(int K, int C);
 int eg_spectral_norm_fwd(const float* W, const float* u, float* Wbar, float* ws, int K, int C, void* stream);
 int eg_spectral_norm_bwd(const float* W, const float* u, float* ws, const float* Gbar, float* gW, int K, int C,
                          void* stream);
+/* The same for every weight tensor of a network at once (the classifier normalises 22 filters per step,
+ * classifier.py:12-119 through conv.py's spectral_normed_weight): a device-side table of descriptors, forward = 3
+ * launches, backward = 1 memset + 3 launches, instead of 4 nodes per tensor and direction.  G / gW are read / written by
+ * the backward only.  A tensor [taps, cin, C] may be split along cin at `hd` (all of Wa, Wi set): the forward also writes
+ * Wbar as the two contiguous filters Wa [taps, hd, C] and Wi [taps, cin-hd, C]; with Ga / Gi set the backward reads
+ * dL/dWbar from two such parts instead of G.  Pointers must stay valid for the life of the set. */
+typedef struct {
+    const float* W; const float* u; float* Wbar; float* ws;
+    const float* G; float* gW;
+    float* Wa; float* Wi;
+    const float* Ga; const float* Gi;
+    int K, C, cin, hd;
+} eg_sn_desc;
+int eg_spectral_norm_set_create(const eg_sn_desc* descs, int n, long long* handle);
+int eg_spectral_norm_set_fwd(long long handle, void* stream);
+int eg_spectral_norm_set_bwd(long long handle, void* stream);
+int eg_spectral_norm_set_destroy(long long handle);
 /* softmax cross-entropy heads (functional.py:5-16): labels = (int) z[b, label_col];
  * focal = 0: loss += weight * mean CE ; focal = 1: loss += weight * mean (1-p_y)^2 CE ; glogits = dloss/dlogits */
 int eg_softmax_ce_bwd(const float* logits, const float* z, int z_stride, int label_col, int B, int C, int focal,

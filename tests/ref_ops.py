@@ -456,6 +456,26 @@ class RefOps:
         (g,) = torch.autograd.grad(self._sn(Wr, u), Wr, Gbar)
         gW.copy_(g)
 
+    def spectral_norm_set(self, items):
+        ops = self
+
+        class Set:
+            def fwd(self):
+                for it in items:
+                    ops.spectral_norm_fwd(it["W"], it["u"], it["Wbar"], it["ws"])
+                    if it.get("Wa") is not None:
+                        hd = it["hd"]
+                        it["Wa"].copy_(it["Wbar"][:, :, :hd]), it["Wi"].copy_(it["Wbar"][:, :, hd:])
+
+            def bwd(self):
+                for it in items:
+                    G = it["G"] if it.get("Ga") is None else torch.cat([it["Ga"], it["Gi"]], dim=2)
+                    ops.spectral_norm_bwd(it["W"], it["u"], it["ws"], G, it["gW"])
+
+            def close(self):
+                pass
+        return Set()
+
     def softmax_ce_bwd(self, logits, z, label_col, focal, weight, inv_global_batch, glogits, loss):
         lr_ = logits.detach().clone().requires_grad_(True)
         lab = z[:, label_col].to(torch.int64)

@@ -364,6 +364,53 @@ def test_spectral_norm(dev, ref, shape):
     close(res[0][1], res[1][1], 1e-4, "gW")
 
 
+def test_spectral_norm_set(dev, ref):
+    """the whole-network table (eg_spectral_norm_set_*): tensors of very different sizes in one launch set, one of them
+    split along its input-channel axis (the classifier's update gate), forward twice / backward twice per set"""
+    rs = np.random.RandomState(29)
+    shapes = [(7, 7, 3, 8), (3, 3, 11, 8), (3, 3, 128, 256), (1, 1, 768, 14), (3, 3, 131, 128), (3, 3, 768, 768)]
+    split_at = {4: 128}
+    host = [(rnd(rs, *sh, scale=0.02), rnd(rs, 1, sh[-1]), rnd(rs, *sh)) for sh in shapes]
+    res = []
+    for o in (dev, ref):
+        items, outs = [], []
+        for i, (sh, (W, u, G)) in enumerate(zip(shapes, host)):
+            Cn = sh[-1]
+            K = int(np.prod(sh)) // Cn
+            it = dict(W=o.from_numpy(W), u=o.from_numpy(u), Wbar=o.zeros(sh), ws=o.zeros((o.sn_ws_floats(K, Cn),)), gW=o.zeros(sh))
+            if i in split_at:
+                hd = split_at[i]
+                it.update(Wa=o.zeros(sh[:2] + (hd, Cn)), Wi=o.zeros(sh[:2] + (sh[2] - hd, Cn)), hd=hd,
+                          Ga=o.from_numpy(np.ascontiguousarray(G[:, :, :hd])), Gi=o.from_numpy(np.ascontiguousarray(G[:, :, hd:])))
+            else:
+                it["G"] = o.from_numpy(G)
+            items.append(it)
+        st = o.spectral_norm_set(items)
+        for _ in range(2):
+            st.fwd()
+            st.bwd()
+        st.bwd()
+        res.append([(o.to_numpy(it["Wbar"]), o.to_numpy(it["gW"]),
+                     o.to_numpy(it["Wa"]) if "Wa" in it else None, o.to_numpy(it["Wi"]) if "Wi" in it else None) for it in items])
+        if o is dev:
+            # against the single-tensor entry points of the same library
+            for it, (W, u, G) in zip(items, host):
+                wb, gw = o.zeros(it["W"].shape), o.zeros(it["W"].shape)
+                ws = o.zeros(it["ws"].shape)
+                o.spectral_norm_fwd(it["W"], it["u"], wb, ws)
+                o.spectral_norm_bwd(it["W"], it["u"], ws, o.from_numpy(G), gw)
+                close(o.to_numpy(it["Wbar"]), o.to_numpy(wb), 1e-6, "set vs single wbar")     # r is summed by atomics
+                close(o.to_numpy(it["gW"]), o.to_numpy(gw), 1e-5, "set vs single gW")
+            st.close()
+    for i, (a, b) in enumerate(zip(*res)):
+        close(a[0], b[0], 2e-5, f"wbar {i}")
+        close(a[1], b[1], 1e-4, f"gW {i}")
+        if a[2] is not None:
+            hd = split_at[i]
+            np.testing.assert_array_equal(a[2], a[0][:, :, :hd])
+            np.testing.assert_array_equal(a[3], a[0][:, :, hd:])
+
+
 @pytest.mark.parametrize("focal", [False, True])
 def test_softmax_ce(dev, ref, focal):
     rs = np.random.RandomState(24)
