@@ -1253,9 +1253,15 @@ struct FilterSetEntry {          // device-side descriptor of one filter
     const float* w; float* fwd; float* dgr;
     int taps, A, B;              // filter [taps][A][B]  (A = conv input channels, B = output channels)
     int tile0, tiles_b, tiles_ab;
+    // kind 1 = thin filter (A <= 8): fwd = the gathered forward's K-major [B][Kpad] hi, lo; dgr = the patch-matrix input
+    // gradient's operand [Npad][B] hi, lo (= the filter itself, zero-padded to Npad rows), see conv_thin.cu
+    int kind, Kpad, Npad;
 };
-struct ManagedFilter { float* fwd; float* dgr; size_t n; int mode; int set; };
-struct FilterSet { std::vector<const float*> keys; float* buf = nullptr; FilterSetEntry* table = nullptr; int nfilters = 0, tiles = 0, mode = 0; bool live = false; };
+struct ManagedFilter { float* fwd; float* dgr; size_t n; int mode; int set; int kind; };
+// buffers of a set that already ARE a forward-prepared operand (the thin input gradient's [Npad][B] copy): prep_filter()
+// serves them as they are when such a buffer is passed as the filter of the dense product
+std::map<const float*, size_t> g_preformed;
+struct FilterSet { std::vector<const float*> keys, preformed; float* buf = nullptr; FilterSetEntry* table = nullptr; int nfilters = 0, tiles = 0, mode = 0; bool live = false; };
 std::map<const float*, ManagedFilter> g_managed;
 std::vector<FilterSet> g_sets;
 unsigned long long g_managed_hits = 0;
@@ -1270,6 +1276,24 @@ __global__ void prep_filter_set_k(const FilterSetEntry* __restrict__ table, int 
     }
     __syncthreads();
     const int local = (int)blockIdx.x - e.tile0;
+    if (e.kind == 1) {
+        const int K = e.taps * e.A, Co = e.B;
+        const int i = local * 256 + threadIdx.y * 32 + threadIdx.x;
+        if (i < Co * e.Kpad) {
+            const int co = i / e.Kpad, j = i - co * e.Kpad;
+            const float v = j < K ? e.w[(size_t)j * Co + co] : 0.f;
+            const uint32_t u = __float_as_uint(v);
+            if (mode == 3) { e.fwd[i] = v; e.fwd[(size_t)Co * e.Kpad + i] = __uint_as_float(tf32_lo(u)); }
+            else e.fwd[i] = __uint_as_float(tf32_rna(u));
+        }
+        if (i < e.Npad * Co) {
+            const float v = i < K * Co ? e.w[i] : 0.f;
+            const uint32_t u = __float_as_uint(v);
+            if (mode == 3) { e.dgr[i] = v; e.dgr[(size_t)e.Npad * Co + i] = __uint_as_float(tf32_lo(u)); }
+            else e.dgr[i] = __uint_as_float(tf32_rna(u));
+        }
+        return;
+    }
     const int tap = local / e.tiles_ab, rem = local - tap * e.tiles_ab;
     const int a0 = (rem / e.tiles_b) * 32, b0 = (rem % e.tiles_b) * 32;
     const size_t n = (size_t)e.taps * e.A * e.B, tb = (size_t)tap * e.A * e.B;
@@ -1305,9 +1329,15 @@ int prep_filter(const eg_conv_shape* s, const float* w, int transpose, int mode,
     {
         std::lock_guard<std::mutex> lk(g_mu);
         auto it = g_managed.find(w);
-        if (it != g_managed.end() && it->second.n == n && it->second.mode == mode) {
+        if (it != g_managed.end() && it->second.kind == 0 && it->second.n == n && it->second.mode == mode) {
             ++g_managed_hits;
             *out = transpose ? it->second.fwd : it->second.dgr;
+            return 0;
+        }
+        auto pf = g_preformed.find(w);
+        if (pf != g_preformed.end() && transpose && pf->second == n) {
+            ++g_managed_hits;
+            *out = const_cast<float*>(w);
             return 0;
         }
     }
@@ -1334,6 +1364,16 @@ extern "C" int eg_filter_set_create(const eg_filter_desc* descs, int n, int algo
         if (!d.w || d.taps <= 0 || d.Ci <= 0 || d.Co <= 0) return eg_fail_arg("eg_filter_set_create: descriptor", __FILE__, __LINE__);
         FilterSetEntry& e = host[i];
         e.w = d.w; e.taps = d.taps; e.A = d.Ci; e.B = d.Co;
+        e.kind = 0; e.Kpad = 0; e.Npad = 0;
+        const int K = d.taps * d.Ci;
+        if (d.Ci <= 8 && K <= 128 && d.Co % 32 == 0) {           // thin filter: the operands of the gathered forward and of
+            e.kind = 1;                                          // the patch-matrix input gradient (conv_thin.cu)
+            e.Kpad = (K + 31) / 32 * 32; e.Npad = K <= 64 ? 64 : 128;
+            e.tiles_b = 0; e.tiles_ab = 0;
+            e.tile0 = tiles; tiles += eg_ceil_div((long long)std::max(e.Kpad, e.Npad) * d.Co, 256);
+            total += 2 * (size_t)d.Co * e.Kpad + 2 * (size_t)e.Npad * d.Co + 128;
+            continue;
+        }
         e.tiles_b = eg_ceil_div(d.Co, 32); e.tiles_ab = e.tiles_b * eg_ceil_div(d.Ci, 32);
         e.tile0 = tiles; tiles += e.taps * e.tiles_ab;
         total += 4 * (size_t)d.taps * d.Ci * d.Co + 64;
@@ -1346,6 +1386,12 @@ extern "C" int eg_filter_set_create(const eg_filter_desc* descs, int n, int algo
     float* p = fs.buf;
     for (int i = 0; i < n; ++i) {
         const size_t ni = (size_t)host[i].taps * host[i].A * host[i].B;
+        if (host[i].kind == 1) {
+            const size_t nf = 2 * (size_t)host[i].B * host[i].Kpad, nd = 2 * (size_t)host[i].Npad * host[i].B;
+            host[i].fwd = p; p += (nf + 63) / 64 * 64;
+            host[i].dgr = p; p += (nd + 63) / 64 * 64;
+            continue;
+        }
         host[i].fwd = p; host[i].dgr = p + 2 * ni;
         p += (4 * ni + 63) / 64 * 64;                        // keep every copy 256-byte aligned (TMA global address)
     }
@@ -1358,8 +1404,12 @@ extern "C" int eg_filter_set_create(const eg_filter_desc* descs, int n, int algo
         const size_t ni = (size_t)host[i].taps * host[i].A * host[i].B;
         auto old = g_managed.find(host[i].w);                // a pointer belongs to at most one set: the newest
         if (old != g_managed.end()) g_managed.erase(old);
-        g_managed[host[i].w] = ManagedFilter{host[i].fwd, host[i].dgr, ni, mode, id};
+        g_managed[host[i].w] = ManagedFilter{host[i].fwd, host[i].dgr, ni, mode, id, host[i].kind};
         fs.keys.push_back(host[i].w);
+        if (host[i].kind == 1) {
+            g_preformed[host[i].dgr] = (size_t)host[i].Npad * host[i].B;
+            fs.preformed.push_back(host[i].dgr);
+        }
     }
     g_sets.push_back(fs);
     *handle = id;
@@ -1386,10 +1436,21 @@ extern "C" int eg_filter_set_destroy(long long handle) {
         auto it = g_managed.find(k);
         if (it != g_managed.end() && it->second.set == (int)handle) g_managed.erase(it);
     }
+    for (const float* k : fs.preformed) g_preformed.erase(k);
     cudaDeviceSynchronize();                                 // no kernel may still read the copies
     cudaFree(fs.buf); cudaFree(fs.table);
-    fs.buf = nullptr; fs.table = nullptr; fs.live = false; fs.keys.clear();
+    fs.buf = nullptr; fs.table = nullptr; fs.live = false; fs.keys.clear(); fs.preformed.clear();
     return 0;
+}
+
+// thin filter of a set: the gathered forward's operand (which = 0) or the patch-matrix input gradient's (which = 1);
+// NULL when `w` is not in a set of this mode
+float* eg_tc_managed_thin(const float* w, size_t n, int mode, int which) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g_managed.find(w);
+    if (it == g_managed.end() || it->second.kind != 1 || it->second.n != n || it->second.mode != mode) return nullptr;
+    if (which == 0) ++g_managed_hits;        // (the input gradient's copy is counted when prep_filter() serves it)
+    return which == 0 ? it->second.fwd : it->second.dgr;
 }
 
 // conv calls served from a prepared-filter set so far (no preparation launch)
@@ -1547,10 +1608,12 @@ static int tc_conv2d_fwd_gather(const eg_conv_shape* s, const float* x, const fl
     const int mode = three_x ? 3 : 1;
     const int K = s->KH * s->KW * s->Ci, Kpad = (K + 31) / 32 * 32;
     const long long Ppix = (long long)s->N * s->OH * s->OW;
-    float* wt = nullptr;
-    if (int r = get_scratch(st, sizeof(float) * (size_t)2 * s->Co * Kpad, &wt, 3)) return r;
-    prep_filter_gather_k<<<eg_ceil_div((long long)s->Co * Kpad, 256), 256, 0, st>>>(w, wt, wt + (size_t)s->Co * Kpad, K, Kpad, s->Co, mode);
-    EG_CHECK_LAUNCH();
+    float* wt = eg_tc_managed_thin(w, (size_t)K * s->Co, mode, 0);
+    if (wt == nullptr) {
+        if (int r = get_scratch(st, sizeof(float) * (size_t)2 * s->Co * Kpad, &wt, 3)) return r;
+        prep_filter_gather_k<<<eg_ceil_div((long long)s->Co * Kpad, 256), 256, 0, st>>>(w, wt, wt + (size_t)s->Co * Kpad, K, Kpad, s->Co, mode);
+        EG_CHECK_LAUNCH();
+    }
     TcMaps maps;
     TcParams P{};
     P.bw = 1; P.bh = 1; P.bn = 128;

@@ -16,6 +16,7 @@
 #include "common.cuh"
 
 int eg_tc_scratch(cudaStream_t st, int slot, size_t bytes, float** out);
+float* eg_tc_managed_thin(const float* w, size_t n, int mode, int which);
 int eg_tc_conv2d_fwd(const eg_conv_shape* s, const float* x, const float* w, const float* bias, float* y, int three_x, cudaStream_t st, const EgEpi* epi = nullptr, const eg_conv_shape* scatter = nullptr);
 int eg_tc_scatter_supported(const eg_conv_shape* c);
 int eg_tc_conv2d_bwd_weight(const eg_conv_shape* s, const float* x, const float* dy, float* dw, int accumulate, int three_x, cudaStream_t st);
@@ -353,10 +354,14 @@ int eg_thin_conv2d_bwd_data(const eg_conv_shape* s, const float* dy, const float
     const ThinP p = make_p(s);
     const long long P = (long long)s->N * s->OH * s->OW;
     const int Npad = p.K <= 64 ? 64 : 128;
-    float *C = nullptr, *wt = nullptr;
-    if (int r = eg_tc_scratch(st, 2, sizeof(float) * (size_t)Npad * s->Co, &wt)) return r;
-    thin_transpose_w_k<<<eg_ceil_div((long long)Npad * s->Co, 256), 256, 0, st>>>(w, wt, p.K, Npad, s->Co);
-    EG_CHECK_LAUNCH();
+    float *C = nullptr;
+    // filter of a prepared-filter set: its [Npad][Co] hi/lo copy IS the dense product's prepared operand (no launch here)
+    float* wt = eg_tc_managed_thin(w, (size_t)p.K * s->Co, three_x ? 3 : 1, 1);
+    if (wt == nullptr) {
+        if (int r = eg_tc_scratch(st, 2, sizeof(float) * (size_t)Npad * s->Co, &wt)) return r;
+        thin_transpose_w_k<<<eg_ceil_div((long long)Npad * s->Co, 256), 256, 0, st>>>(w, wt, p.K, Npad, s->Co);
+        EG_CHECK_LAUNCH();
+    }
     const eg_conv_shape g = gemm_shape(P, s->Co, Npad);
     if (eg_tc_scatter_supported(s)) {
         // dx = bias (or 0), then the dense product's epilogue adds every im2col column where it belongs: no [P, Npad]

@@ -132,7 +132,7 @@ class Classifier(object):
         self._sn.fwd()
         # prepared copies (tensor-core operand layouts) of the normalised filters: one kernel for the whole network
         algo = getattr(ops, "default_algo", None)
-        tc = [w for w in self.wbar.values() if w.dim() == 4 and w.shape[2] % 32 == 0 and w.shape[3] % 32 == 0]
+        tc = [w for w in self.wbar.values() if ops.in_filter_set(w.shape)]
         ids = tuple(w.data_ptr() for w in tc)
         if getattr(self, "_fset_key", None) != (algo, ids):
             if getattr(self, "_fset", None) is not None:

@@ -296,6 +296,16 @@ class DeviceOps:
         _lib.check(self.lib.eg_copy2d(_p(src), src.numel(), _p(dst), dst.numel(), 1, src.numel(), self._st), "copy2d")
 
     # ---- prepared-filter sets (eg_filter_set_*) -------------------------------------------------------
+    @staticmethod
+    def in_filter_set(shape):
+        """filters [kh, kw, ci, co] the library keeps prepared copies of: both channel counts multiples of 32 (the operand
+        layouts of the tcgen05 kernels), or a thin image-side filter (ci <= 8: the gathered forward's K-major copy and the
+        patch-matrix input gradient's padded copy)"""
+        if len(shape) != 4:
+            return False
+        kh, kw, ci, co = shape
+        return (ci % 32 == 0 and co % 32 == 0 and kh * kw <= 25) or (ci <= 8 and co % 32 == 0 and kh * kw * ci <= 128)
+
     def filter_set(self, filters):
         """-> FilterSet over the given 4-D HWIO filter tensors (or None when the default conv algorithm is the SIMT
         path, which reads the filters as they are).  Call `.prepare()` after every write to those tensors."""

@@ -128,10 +128,8 @@ class ParamStore:
 
     # ---- prepared copies of the conv filters (ops.filter_set) --------------------------------------------------
     def conv_filters(self):
-        """the 4-D filters a tensor-core conv kernel can take in at least one direction (both channel counts
-        multiples of 32); the thin-channel image layers are read as they are"""
-        return [self.var[s.name] for s in self.specs
-                if len(s.shape) == 4 and s.shape[2] % 32 == 0 and s.shape[3] % 32 == 0 and s.shape[0] * s.shape[1] <= 25]
+        """the 4-D filters a tensor-core conv kernel reads through a prepared copy (ops.in_filter_set)"""
+        return [self.var[s.name] for s in self.specs if self.ops.in_filter_set(s.shape)]
 
     def prepare_filters(self):
         """Refresh the library-side prepared copies of this network's conv filters: ONE kernel, enqueued after every

@@ -120,6 +120,10 @@ class RefOps:
             return v * act_grad(act, mask)
         return act_fwd(act, v)
 
+    @staticmethod
+    def in_filter_set(shape):
+        return len(shape) == 4
+
     def filter_set(self, filters):
         return None          # the CPU operator set reads the filters as they are
 

@@ -225,3 +225,51 @@ def test_prepared_filter_set(dev, ref):
     dev.upload(wd, w1)
     dev.conv_fwd(xd, wd, None, y, s, p, "tc3x")
     assert dev.filter_set_hits() == h1 and relerr(dev.to_numpy(y), want1) < 2e-5
+
+
+@pytest.mark.parametrize("Ci,Co,k,st,H", [(3, 64, 4, 2, 16), (8, 128, 3, 1, 12), (3, 128, 3, 1, 9), (3, 64, 5, 2, 16)])
+def test_prepared_filter_set_thin_filters(dev, ref, Ci, Co, k, st, H):
+    """thin (image-side) filters in a set: the gathered forward and the patch-matrix input gradient read the set's copies
+    (no per-call preparation launch) and follow the weights of the last prepare()"""
+    rs = np.random.RandomState(6)
+    N, p = 3, (k - 1) // 2
+    OH = (H + 2 * p - k) // st + 1
+    x, dy = rnd(rs, N, H, H, Ci), rnd(rs, N, OH, OH, Co)
+    w1, w2 = rnd(rs, k, k, Ci, Co, scale=0.1), rnd(rs, k, k, Ci, Co, scale=0.1)
+    wbig = rnd(rs, 3, 3, 64, 64, scale=0.05)                             # a standard member next to the thin one
+    dev.set_default_algo("tc3x")
+    xd, dyd, wd, wbd = dev.from_numpy(x), dev.from_numpy(dy), dev.from_numpy(w1), dev.from_numpy(wbig)
+    y, dx = dev.zeros((N, OH, OH, Co)), dev.zeros((N, H, H, Ci))
+    # per-call preparation first: launches of the unmanaged route
+    l0 = dev.launches
+    dev.conv_fwd(xd, wd, None, y, st, p, "tc3x")
+    dev.conv_bwd_data(dyd, wd, None, dx, st, p, "tc3x")
+    unmanaged = dev.launches - l0
+    y_un, dx_un = dev.to_numpy(y), dev.to_numpy(dx)
+    fs = dev.filter_set([wbd, wd])
+    fs.prepare()
+    h0, l0 = dev.filter_set_hits(), dev.launches
+    dev.conv_fwd(xd, wd, None, y, st, p, "tc3x")
+    dev.conv_bwd_data(dyd, wd, None, dx, st, p, "tc3x")
+    assert dev.filter_set_hits() == h0 + 2, "thin filter not served from the set"
+    assert dev.launches - l0 == unmanaged - 3            # gather copy; transpose + operand preparation of the input gradient
+    np.testing.assert_array_equal(dev.to_numpy(y), y_un)
+    np.testing.assert_array_equal(dev.to_numpy(dx), dx_un)
+    assert relerr(y_un, run(ref, "conv_fwd", [x, w1, None], (N, OH, OH, Co), st, p)) < 2e-5
+    assert relerr(dx_un, run(ref, "conv_bwd_data", [dy, w1, None], (N, H, H, Ci), st, p)) < 2e-5
+    dev.upload(wd, w2)
+    fs.prepare()
+    dev.conv_fwd(xd, wd, None, y, st, p, "tc3x")
+    dev.conv_bwd_data(dyd, wd, None, dx, st, p, "tc3x")
+    assert relerr(dev.to_numpy(y), run(ref, "conv_fwd", [x, w2, None], (N, OH, OH, Co), st, p)) < 2e-5
+    assert relerr(dev.to_numpy(dx), run(ref, "conv_bwd_data", [dy, w2, None], (N, H, H, Ci), st, p)) < 2e-5
+    y2 = dev.zeros((N, H, H, 64))
+    x2 = rnd(rs, N, H, H, 64)
+    dev.conv_fwd(dev.from_numpy(x2), wbd, None, y2, 1, 1, "tc3x")        # the standard member is untouched by the thin one
+    assert relerr(dev.to_numpy(y2), run(ref, "conv_fwd", [x2, wbig, None], (N, H, H, 64), 1, 1)) < 2e-5
+    fs.close()
+    h1 = dev.filter_set_hits()
+    dev.conv_fwd(xd, wd, None, y, st, p, "tc3x")
+    dev.conv_bwd_data(dyd, wd, None, dx, st, p, "tc3x")
+    assert dev.filter_set_hits() == h1
+    assert relerr(dev.to_numpy(y), run(ref, "conv_fwd", [x, w2, None], (N, OH, OH, Co), st, p)) < 2e-5
