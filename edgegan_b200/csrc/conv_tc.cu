@@ -353,12 +353,33 @@ __device__ __forceinline__ void drain_scatter_group(const TcParams& P, const Sca
 // transpose each instruction writes 4 rows x 128 contiguous bytes.  `plain`: full tile, no mask / split (bias add and the
 // sign-type activation folded in); otherwise the general path (ragged tiles, activation-derivative mask, k-split red.add).
 struct DrainCtx {
-    uint32_t stg, vmask;
+    uint32_t stg, vmask, pos;
     int lane, sub, cj;
     float* obase;
     const float* brow;
     bool plain;
 };
+// EG_EPI_MASK: sign bits (4 per stored row) of the mask values under one 32-column group of this lane's 8 output rows.
+// Called for every group of an item BEFORE the drain warp waits for the accumulator, so that the DRAM latency of the
+// mask lies under the item's MMAs instead of between the chunk drains (where it stalled the tensor pipe: both
+// accumulator buffers filled up while the drain warps waited for the previous item's mask).
+__device__ __forceinline__ uint32_t drain_mask_bits(const TcParams& P, const float* mbase, const long long (&loff)[8],
+                                                    uint32_t vmask, int c) {
+    float4 mk[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+        mk[i] = (vmask & (1u << i)) ? __ldg(reinterpret_cast<const float4*>(mbase + loff[i] + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    uint32_t pos = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const float4 m = mk[i];
+        const bool px = P.epi_ge ? m.x >= 0.f : m.x > 0.f, py = P.epi_ge ? m.y >= 0.f : m.y > 0.f;
+        const bool pz = P.epi_ge ? m.z >= 0.f : m.z > 0.f, pw = P.epi_ge ? m.w >= 0.f : m.w > 0.f;
+        pos |= ((uint32_t)px | ((uint32_t)py << 1) | ((uint32_t)pz << 2) | ((uint32_t)pw << 3)) << (4 * i);
+    }
+    return pos;
+}
+
 __device__ __forceinline__ void drain_store_group(const TcParams& P, const DrainCtx& d, const long long (&loff)[8],
                                                   const float (&a32)[32], const int c) {
     const uint32_t stg = d.stg, vmask = d.vmask;
@@ -390,6 +411,17 @@ __device__ __forceinline__ void drain_store_group(const TcParams& P, const Drain
                     v.z = v.z > thr ? v.z : P.epi_neg * v.z; v.w = v.w > thr ? v.w : P.epi_neg * v.w;
                     *reinterpret_cast<float4*>(obase + loff[i] + c) = v;
                 }
+            } else if (P.epi == EG_EPI_MASK) {
+                const float ng = P.epi_neg;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int rr = i * 4 + sub;
+                    const uint4 u = lds128(stg + (uint32_t)rr * 128u + (uint32_t)((cj ^ (rr & 7)) << 4));
+                    const uint32_t b = d.pos >> (4 * i);
+                    *reinterpret_cast<float4*>(obase + loff[i] + c) =
+                        make_float4((__uint_as_float(u.x) + bb.x) * ((b & 1u) ? 1.f : ng), (__uint_as_float(u.y) + bb.y) * ((b & 2u) ? 1.f : ng),
+                                    (__uint_as_float(u.z) + bb.z) * ((b & 4u) ? 1.f : ng), (__uint_as_float(u.w) + bb.w) * ((b & 8u) ? 1.f : ng));
+                }
             } else {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
@@ -403,25 +435,7 @@ __device__ __forceinline__ void drain_store_group(const TcParams& P, const Drain
         } else {
             float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
             if (brow != nullptr) bb = __ldg(reinterpret_cast<const float4*>(brow + c));
-            // mask epilogue: the 8 global loads of this column group are issued back to back, then reduced to one
-            // sign bit per value (the shared-memory asm below is a compiler barrier: a load per row inside the
-            // loop would cost 8 DRAM latencies, and 32 live floats across it would spill)
-            uint32_t pos = 0;
-            if (P.epi == EG_EPI_MASK) {
-                const float* mbase = P.mask + (obase - P.out) + c;
-                float4 mk[8];
-#pragma unroll
-                for (int i = 0; i < 8; ++i)
-                    mk[i] = (vmask & (1u << i)) ? __ldg(reinterpret_cast<const float4*>(mbase + loff[i]))
-                                                : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const float4 m = mk[i];
-                    const bool px = P.epi_ge ? m.x >= 0.f : m.x > 0.f, py = P.epi_ge ? m.y >= 0.f : m.y > 0.f;
-                    const bool pz = P.epi_ge ? m.z >= 0.f : m.z > 0.f, pw = P.epi_ge ? m.w >= 0.f : m.w > 0.f;
-                    pos |= ((uint32_t)px | ((uint32_t)py << 1) | ((uint32_t)pz << 2) | ((uint32_t)pw << 3)) << (4 * i);
-                }
-            }
+            const uint32_t pos = d.pos;          // sign bits of the activation-derivative mask (drain_mask_bits, loaded early)
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const int rr = i * 4 + sub;
@@ -747,9 +761,16 @@ conv_tc_kmajor(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
             float* obase = P.out + ph.out_off + (long long)t.n0 * ph.sn + (long long)t.h0 * ph.sh + (long long)t.w0 * ph.sw + t.col0;
             const float* brow = (P.bias != nullptr && t.split == 0) ? P.bias + t.col0 + cj * 4 : nullptr;
             // full tile, no mask / split: the transposed copy with the bias add and the sign-type activation folded in
-            const bool plain = vmask == 0xffu && P.ksplit == 1 && P.epi != EG_EPI_MASK;
+            const bool plain = vmask == 0xffu && P.ksplit == 1;
             DrainCtx dc;
-            dc.stg = stg; dc.vmask = vmask; dc.lane = lane; dc.sub = sub; dc.cj = cj; dc.obase = obase; dc.brow = brow; dc.plain = plain;
+            dc.stg = stg; dc.vmask = vmask; dc.pos = 0; dc.lane = lane; dc.sub = sub; dc.cj = cj; dc.obase = obase; dc.brow = brow; dc.plain = plain;
+            uint32_t mpos0 = 0, mpos1 = 0, mpos2 = 0, mpos3 = 0;
+            if (P.epi == EG_EPI_MASK) {
+                const float* mbase = P.mask + (obase - P.out);
+                mpos0 = drain_mask_bits(P, mbase, loff, vmask, 0);
+                if (BN > 32) mpos1 = drain_mask_bits(P, mbase, loff, vmask, 32);
+                if (BN > 64) { mpos2 = drain_mask_bits(P, mbase, loff, vmask, 64); mpos3 = drain_mask_bits(P, mbase, loff, vmask, 96); }
+            }
             ScatterCtx sc;
             sc.base = nullptr; sc.hmask = 0; sc.wmask = 0;
             if (P.g.on == 2) {                               // this thread's accumulator row = output pixel t.n0 + q*32 + lane
@@ -782,6 +803,7 @@ conv_tc_kmajor(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
                         __syncwarp();
                         if (lane == 0) mbar_arrive(smem_u32(&acc_empty_bar[buf]));
                     }
+                    dc.pos = g == 0 ? mpos0 : (g == 1 ? mpos1 : (g == 2 ? mpos2 : mpos3));
                     if (P.g.on == 2) { if (g * 32 < P.g.K) drain_scatter_group(P, sc, gtab, reinterpret_cast<const float (&)[32]>(r), g * 32); }
                     else drain_store_group(P, dc, loff, reinterpret_cast<const float (&)[32]>(r), g * 32);
                 }
@@ -825,6 +847,7 @@ conv_tc_kmajor(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
                 if (g * 32 < BN) {
+                    dc.pos = g == 0 ? mpos0 : (g == 1 ? mpos1 : (g == 2 ? mpos2 : mpos3));
                     if (P.g.on == 2) { if (g * 32 < P.g.K) drain_scatter_group(P, sc, gtab, reinterpret_cast<const float (&)[32]>(acc[g * 32]), g * 32); }
                     else drain_store_group(P, dc, loff, reinterpret_cast<const float (&)[32]>(acc[g * 32]), g * 32);
                 }
