@@ -395,8 +395,16 @@ int eg_conv_shape_check(const eg_conv_shape* s) {
     return 0;
 }
 
+// conv_small.cu: direct kernels for layers with <= 8 channels on both sides (-100 = not covered)
+int eg_small_conv2d(const eg_conv_shape* s, const float* in, const float* w, const float* bias, float* out, int dgrad, cudaStream_t st);
+int eg_small_conv2d_bwd_weight(const eg_conv_shape* s, const float* x, const float* dy, float* dw, int accumulate, int sms, cudaStream_t st);
+
 int eg_simt_conv2d_fwd(const eg_conv_shape* s, const float* x, const float* w, const float* bias, float* y,
                        const EgEpi* epi, cudaStream_t st) {
+    {
+        const int r = eg_small_conv2d(s, x, w, bias, y, 0, st);
+        if (r != -100) return r ? r : ((epi && epi->mode != EG_EPI_NONE) ? 1 : 0);
+    }
     ConvP p = to_p(s);
     const int unfused = set_epilogue(p, epi);
     Phase f{};
@@ -410,6 +418,10 @@ int eg_simt_conv2d_fwd(const eg_conv_shape* s, const float* x, const float* w, c
 // returns 1 (instead of 0) when `epi` was NOT applied (the 3-channel kernel has no fused epilogue): the caller runs it
 int eg_simt_conv2d_bwd_data(const eg_conv_shape* s, const float* dy, const float* w, const float* bias, float* dx,
                             const EgEpi* epi, cudaStream_t st) {
+    {
+        const int r = eg_small_conv2d(s, dy, w, bias, dx, 1, st);
+        if (r != -100) return r ? r : ((epi && epi->mode != EG_EPI_NONE) ? 1 : 0);
+    }
     ConvP p = to_p(s);
     const int unfused = set_epilogue(p, epi);
     Phase f{};
@@ -456,6 +468,10 @@ int eg_simt_conv2d_bwd_weight(const eg_conv_shape* s, const float* x, const floa
                               int sm_count, cudaStream_t st) {
     // stride-1 thin layers only: measured (tools/norm_time.py) 433 vs 554 us on the 8 -> 128 classifier layer, 71 vs 82 / 42 vs
     // 51 us on the 3 -> 128 / 256 image convs, but 499 vs 438 us on the stride-2 critic first layer
+    {
+        const int r = eg_small_conv2d_bwd_weight(s, x, dy, dw, accumulate, sm_count, st);
+        if (r != -100) return r;
+    }
     if (s->Ci <= 8 && s->stride == 1 && !g_eg_thin_wgrad_off) {
         const int r = eg_thin_wgrad_ffma(s, x, dy, dw, accumulate, sm_count, st);
         if (r != -100) return r;

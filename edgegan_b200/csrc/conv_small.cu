@@ -1,0 +1,283 @@
+// Direct convolutions for layers whose channel counts are BOTH <= 8 (stride 1): the stem of the multi-class classifier
+// (reference models/classifier.py:27-33 `Conv` 7x7 3 -> 8, and the first MRU block's image conv / update gate at 8
+// channels, nn/modules/conv.py:133-243).  An implicit GEMM wastes its tile on them (N = 8 columns) and the generic FFMA
+// kernel ran them at 6 TFLOP/s (185 us for 1.2 GFLOP); here a block keeps a 32 x 32 output tile's input window and the
+// whole filter in shared memory, every thread owns 4 pixels x all output channels (one 16-byte shared load per pixel
+// and tap, the filter as broadcast loads), so the loop is FFMA-bound.
+//   small_conv_k : forward, and the input gradient as the same correlation with the flipped / transposed filter
+//   small_wgrad_k: filter gradient, one thread per (tap, input channel) x all output channels, persistent over tiles
+#include "common.cuh"
+
+namespace {
+
+constexpr int kTile = 32;      // output tile width (= lanes) of both kernels
+constexpr int kRowsW = 16;     // output tile height of the filter-gradient kernel
+
+struct SmallP {
+    int N, IH, IW, OH, OW;     // input / output extents of THIS pass (input gradient: input = dy, output = dx)
+    int PT, PL;                // out(r, c) reads in(r + a - PT, c + b - PL)
+    int tiles_x, tiles_y;
+    int flip;                  // input gradient: W[a][b][ic][oc] = w[K-1-a][K-1-b][ci = oc][co = ic]
+};
+
+__device__ __forceinline__ float comp(const float4& v, int i) { return i == 0 ? v.x : (i == 1 ? v.y : (i == 2 ? v.z : v.w)); }
+
+// input window of one tile -> sIn[plane][row][col] (float4 = 4 channels, zero outside the image / above IC)
+template <int IC, int ROWS, int K>
+__device__ __forceinline__ void load_window(const float* __restrict__ in, float4* sIn, const SmallP& p, int n, int r0, int c0) {
+    constexpr int PLN = (IC + 3) / 4, TWp = kTile + K - 1, THp = ROWS + K - 1;
+    for (int i = threadIdx.x; i < THp * TWp; i += blockDim.x) {
+        const int rr = i / TWp, cc = i - rr * TWp;
+        const int gr = r0 + rr - p.PT, gc = c0 + cc - p.PL;
+        const bool ok = gr >= 0 && gr < p.IH && gc >= 0 && gc < p.IW;
+        const float* src = in + (((size_t)n * p.IH + gr) * p.IW + gc) * IC;
+        if (IC == 8) {
+            float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
+            if (ok) { v0 = __ldg(reinterpret_cast<const float4*>(src)); v1 = __ldg(reinterpret_cast<const float4*>(src) + 1); }
+            sIn[i] = v0; sIn[THp * TWp + i] = v1;
+        } else {
+#pragma unroll
+            for (int pl = 0; pl < PLN; ++pl) {
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (ok) {
+                    if (pl * 4 + 0 < IC) v.x = __ldg(src + pl * 4 + 0);
+                    if (pl * 4 + 1 < IC) v.y = __ldg(src + pl * 4 + 1);
+                    if (pl * 4 + 2 < IC) v.z = __ldg(src + pl * 4 + 2);
+                    if (pl * 4 + 3 < IC) v.w = __ldg(src + pl * 4 + 3);
+                }
+                sIn[pl * THp * TWp + i] = v;
+            }
+        }
+    }
+}
+
+template <int IC, int OC, int K>
+__global__ void __launch_bounds__(256)
+small_conv_k(const float* __restrict__ in, const float* __restrict__ w, const float* __restrict__ bias, float* __restrict__ out,
+             const SmallP p) {
+    constexpr int PLN = (IC + 3) / 4, OCP = OC <= 4 ? 4 : 8, TWp = kTile + K - 1, THp = kTile + K - 1;
+    extern __shared__ float4 sm4[];
+    float4* sIn = sm4;                                                     // [PLN][THp][TWp]
+    float4* sW = sm4 + PLN * THp * TWp;                                    // [K*K*IC][OCP / 4]
+    {
+        float* sWf = reinterpret_cast<float*>(sW);
+        for (int i = threadIdx.x; i < K * K * IC * OCP; i += blockDim.x) {
+            const int oc = i % OCP, t = i / OCP, ic = t % IC, ab = t / IC, a = ab / K, b = ab - a * K;
+            float v = 0.f;
+            if (oc < OC) v = p.flip ? __ldg(w + ((((K - 1 - a) * K + (K - 1 - b)) * OC + oc) * IC + ic))
+                                    : __ldg(w + (((a * K + b) * IC + ic) * OC + oc));
+            sWf[i] = v;
+        }
+    }
+    int tile = blockIdx.x;
+    const int tx = tile % p.tiles_x; tile /= p.tiles_x;
+    const int ty = tile % p.tiles_y;
+    const int n = tile / p.tiles_y;
+    const int r0 = ty * kTile, c0 = tx * kTile;
+    load_window<IC, kTile, K>(in, sIn, p, n, r0, c0);
+    __syncthreads();
+    const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;                // pixel rows ly, ly + 8, ly + 16, ly + 24
+    float acc[4][OCP];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int o = 0; o < OCP; ++o) acc[j][o] = 0.f;
+#pragma unroll 1
+    for (int a = 0; a < K; ++a) {
+#pragma unroll
+        for (int b = 0; b < K; ++b) {
+            float4 xv[4][PLN];
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int pl = 0; pl < PLN; ++pl) xv[j][pl] = sIn[(pl * THp + ly + 8 * j + a) * TWp + lx + b];
+#pragma unroll
+            for (int ic = 0; ic < IC; ++ic) {
+                const float4 w0 = sW[((a * K + b) * IC + ic) * (OCP / 4)];
+                float4 w1 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (OCP == 8) w1 = sW[((a * K + b) * IC + ic) * (OCP / 4) + 1];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float x = comp(xv[j][ic >> 2], ic & 3);
+                    acc[j][0] = fmaf(x, w0.x, acc[j][0]); acc[j][1] = fmaf(x, w0.y, acc[j][1]);
+                    acc[j][2] = fmaf(x, w0.z, acc[j][2]); acc[j][3] = fmaf(x, w0.w, acc[j][3]);
+                    if (OCP == 8) {
+                        acc[j][4] = fmaf(x, w1.x, acc[j][4]); acc[j][5] = fmaf(x, w1.y, acc[j][5]);
+                        acc[j][6] = fmaf(x, w1.z, acc[j][6]); acc[j][7] = fmaf(x, w1.w, acc[j][7]);
+                    }
+                }
+            }
+        }
+    }
+    float bv[OCP];
+#pragma unroll
+    for (int o = 0; o < OCP; ++o) bv[o] = (bias != nullptr && o < OC) ? __ldg(bias + o) : 0.f;
+    const int c = c0 + lx;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int r = r0 + ly + 8 * j;
+        if (r >= p.OH || c >= p.OW) continue;
+        float* dst = out + (((size_t)n * p.OH + r) * p.OW + c) * OC;
+        if (OC == 8) {
+            reinterpret_cast<float4*>(dst)[0] = make_float4(acc[j][0] + bv[0], acc[j][1] + bv[1], acc[j][2] + bv[2], acc[j][3] + bv[3]);
+            reinterpret_cast<float4*>(dst)[1] = make_float4(acc[j][4] + bv[4], acc[j][5] + bv[5], acc[j][6] + bv[6], acc[j][7] + bv[7]);
+        } else {
+#pragma unroll
+            for (int o = 0; o < OC; ++o) dst[o] = acc[j][o] + bv[o];
+        }
+    }
+}
+
+// dw[a][b][ic][oc] (+)= sum over pixels x[n, r + a - PT, c + b - PL, ic] * dy[n, r, c, oc]
+template <int IC, int OC, int K>
+__global__ void __launch_bounds__(256)
+small_wgrad_k(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dw, const SmallP p, int ntiles) {
+    constexpr int PLN = (IC + 3) / 4, OCP = OC <= 4 ? 4 : 8, TWp = kTile + K - 1, THp = kRowsW + K - 1;
+    constexpr int T = K * K * IC, G = 256 / T;                            // (tap, ic) owners x pixel groups
+    static_assert(T <= 256 && G >= 1, "one thread per (tap, input channel)");
+    extern __shared__ float4 sm4[];
+    float4* sX = sm4;                                                      // [PLN][THp][TWp]
+    float4* sD = sm4 + PLN * THp * TWp;                                    // [kRowsW * kTile][OCP / 4]
+    float* sRed = reinterpret_cast<float*>(sD + kRowsW * kTile * (OCP / 4));   // [T][OC]
+    for (int i = threadIdx.x; i < T * OC; i += blockDim.x) sRed[i] = 0.f;
+    const int e = threadIdx.x % T, g = threadIdx.x / T;
+    const bool active = g < G;
+    const int ic = e % IC, ab = e / IC, a = ab / K, b = ab - a * K;
+    const float* xs = reinterpret_cast<const float*>(sX) + ((size_t)((ic >> 2) * THp + a) * TWp + b) * 4 + (ic & 3);
+    float acc[OCP];
+#pragma unroll
+    for (int o = 0; o < OCP; ++o) acc[o] = 0.f;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        int t = tile;
+        const int tx = t % p.tiles_x; t /= p.tiles_x;
+        const int ty = t % p.tiles_y;
+        const int n = t / p.tiles_y;
+        const int r0 = ty * kRowsW, c0 = tx * kTile;
+        __syncthreads();                                                   // the previous tile is consumed
+        load_window<IC, kRowsW, K>(x, sX, p, n, r0, c0);
+        for (int i = threadIdx.x; i < kRowsW * kTile; i += blockDim.x) {
+            const int rr = i / kTile, cc = i - rr * kTile;
+            const int r = r0 + rr, c = c0 + cc;
+            const bool ok = r < p.OH && c < p.OW;
+            const float* src = dy + (((size_t)n * p.OH + r) * p.OW + c) * OC;
+            float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
+            if (ok) {
+                if (OC == 8) { v0 = __ldg(reinterpret_cast<const float4*>(src)); v1 = __ldg(reinterpret_cast<const float4*>(src) + 1); }
+                else { v0.x = __ldg(src); if (OC > 1) v0.y = __ldg(src + 1); if (OC > 2) v0.z = __ldg(src + 2); if (OC > 3) v0.w = __ldg(src + 3); }
+            }
+            sD[i * (OCP / 4)] = v0;
+            if (OCP == 8) sD[i * 2 + 1] = v1;
+        }
+        __syncthreads();
+        if (active) {
+#pragma unroll 4
+            for (int pix = g; pix < kRowsW * kTile; pix += G) {
+                const int rr = pix >> 5, cc = pix & 31;
+                const float xv = xs[(rr * TWp + cc) * 4];
+                const float4 d0 = sD[pix * (OCP / 4)];
+                acc[0] = fmaf(xv, d0.x, acc[0]); acc[1] = fmaf(xv, d0.y, acc[1]);
+                acc[2] = fmaf(xv, d0.z, acc[2]); acc[3] = fmaf(xv, d0.w, acc[3]);
+                if (OCP == 8) {
+                    const float4 d1 = sD[pix * 2 + 1];
+                    acc[4] = fmaf(xv, d1.x, acc[4]); acc[5] = fmaf(xv, d1.y, acc[5]);
+                    acc[6] = fmaf(xv, d1.z, acc[6]); acc[7] = fmaf(xv, d1.w, acc[7]);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    if (active) {
+#pragma unroll
+        for (int o = 0; o < OC; ++o) atomicAdd(sRed + e * OC + o, acc[o]);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < T * OC; i += blockDim.x) atomicAdd(dw + i, sRed[i]);
+}
+
+template <int IC, int OC, int K>
+int launch_conv(const float* in, const float* w, const float* bias, float* out, const SmallP& p, cudaStream_t st) {
+    constexpr int PLN = (IC + 3) / 4, OCP = OC <= 4 ? 4 : 8, Tp = kTile + K - 1;
+    const size_t smem = sizeof(float4) * (size_t)PLN * Tp * Tp + sizeof(float) * (size_t)K * K * IC * OCP;
+    static bool attr = false;
+    if (!attr && smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(small_conv_k<IC, OC, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return eg_fail(e, __FILE__, __LINE__);
+        attr = true;
+    }
+    small_conv_k<IC, OC, K><<<p.tiles_x * p.tiles_y * p.N, 256, smem, st>>>(in, w, bias, out, p);
+    EG_CHECK_LAUNCH();
+    return 0;
+}
+
+template <int IC, int OC, int K>
+int launch_wgrad(const float* x, const float* dy, float* dw, const SmallP& p, int sms, cudaStream_t st) {
+    constexpr int PLN = (IC + 3) / 4, OCP = OC <= 4 ? 4 : 8, TWp = kTile + K - 1, THp = kRowsW + K - 1;
+    const size_t smem = sizeof(float4) * ((size_t)PLN * THp * TWp + (size_t)kRowsW * kTile * (OCP / 4)) + sizeof(float) * (size_t)K * K * IC * OC;
+    static bool attr = false;
+    if (!attr && smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(small_wgrad_k<IC, OC, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return eg_fail(e, __FILE__, __LINE__);
+        attr = true;
+    }
+    const int ntiles = p.tiles_x * p.tiles_y * p.N;
+    int blocks = 2 * sms;
+    if (blocks > ntiles) blocks = ntiles;
+    small_wgrad_k<IC, OC, K><<<blocks, 256, smem, st>>>(x, dy, dw, p, ntiles);
+    EG_CHECK_LAUNCH();
+    return 0;
+}
+
+bool small_shape(const eg_conv_shape* s) {
+    if (s->stride != 1 || s->KH != s->KW || (s->KH != 3 && s->KH != 7)) return false;
+    if (!((s->Ci == 3 || s->Ci == 8) && s->Co == 8)) return false;
+    if (s->Ci == 8 && s->KH != 3) return false;
+    return true;
+}
+
+}  // namespace
+
+int g_eg_small_off = 0;            // eg_debug_set(7, 2): generic kernels for these layers too (the tests compare both)
+
+// forward (dgrad = 0: in = x, out = y) / input gradient (dgrad = 1: in = dy, out = dx); -100 = shape not covered
+int eg_small_conv2d(const eg_conv_shape* s, const float* in, const float* w, const float* bias, float* out, int dgrad,
+                    cudaStream_t st) {
+    if (g_eg_small_off || !small_shape(s)) return -100;
+    if ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) return -100;
+    SmallP p{};
+    p.N = s->N; p.flip = dgrad;
+    const int K = s->KH;
+    if (!dgrad) { p.IH = s->H; p.IW = s->W; p.OH = s->OH; p.OW = s->OW; p.PT = s->pad_t; p.PL = s->pad_l; }
+    else { p.IH = s->OH; p.IW = s->OW; p.OH = s->H; p.OW = s->W; p.PT = K - 1 - s->pad_t; p.PL = K - 1 - s->pad_l; }
+    p.tiles_x = eg_ceil_div(p.OW, kTile); p.tiles_y = eg_ceil_div(p.OH, kTile);
+    if ((long long)p.tiles_x * p.tiles_y * p.N >= (1ll << 31)) return -100;
+    if (!dgrad) {
+        if (s->Ci == 3 && K == 7) return launch_conv<3, 8, 7>(in, w, bias, out, p, st);
+        if (s->Ci == 3 && K == 3) return launch_conv<3, 8, 3>(in, w, bias, out, p, st);
+        if (s->Ci == 8 && K == 3) return launch_conv<8, 8, 3>(in, w, bias, out, p, st);
+    } else {
+        if (s->Ci == 3 && K == 7) return launch_conv<8, 3, 7>(in, w, bias, out, p, st);
+        if (s->Ci == 3 && K == 3) return launch_conv<8, 3, 3>(in, w, bias, out, p, st);
+        if (s->Ci == 8 && K == 3) return launch_conv<8, 8, 3>(in, w, bias, out, p, st);
+    }
+    return -100;
+}
+
+int eg_small_conv2d_bwd_weight(const eg_conv_shape* s, const float* x, const float* dy, float* dw, int accumulate, int sms,
+                               cudaStream_t st) {
+    if (g_eg_small_off || !small_shape(s)) return -100;
+    if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy)) & 15) return -100;
+    SmallP p{};
+    p.N = s->N; p.flip = 0;
+    p.IH = s->H; p.IW = s->W; p.OH = s->OH; p.OW = s->OW; p.PT = s->pad_t; p.PL = s->pad_l;
+    p.tiles_x = eg_ceil_div(p.OW, kTile); p.tiles_y = eg_ceil_div(p.OH, kRowsW);
+    if ((long long)p.tiles_x * p.tiles_y * p.N >= (1ll << 31)) return -100;
+    if (!accumulate) {
+        cudaError_t e = cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)s->KH * s->KW * s->Ci * s->Co, st);
+        if (e != cudaSuccess) return eg_fail(e, __FILE__, __LINE__);
+    }
+    const int K = s->KH;
+    if (s->Ci == 3 && K == 7) return launch_wgrad<3, 8, 7>(x, dy, dw, p, sms, st);
+    if (s->Ci == 3 && K == 3) return launch_wgrad<3, 8, 3>(x, dy, dw, p, sms, st);
+    if (s->Ci == 8 && K == 3) return launch_wgrad<8, 8, 3>(x, dy, dw, p, sms, st);
+    return -100;
+}

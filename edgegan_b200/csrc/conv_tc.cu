@@ -1480,11 +1480,12 @@ float* eg_tc_managed_thin(const float* w, size_t n, int mode, int which) {
 extern "C" long long eg_filter_set_hits(void) { return (long long)g_managed_hits; }
 
 int g_eg_thin_wgrad_off = 0;
+extern int g_eg_small_off;        // conv_small.cu
 
 extern "C" int eg_debug_set(int key, int value) {
     if (key < 0 || key >= 8) return -2;
     g_dbg[key] = value;
-    if (key == 7) g_eg_thin_wgrad_off = value;
+    if (key == 7) { g_eg_thin_wgrad_off = value & 1; g_eg_small_off = (value >> 1) & 1; }
     return 0;
 }
 

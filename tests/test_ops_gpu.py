@@ -82,6 +82,45 @@ def test_conv_trio_simt(dev, ref, case):
     both(dev, ref, "conv_bwd_weight", [x, dy], [rnd(rs, k, k, Ci, Co)], s, p, True, "simt")
 
 
+SMALL_CASES = [
+    # N, H, W, Ci, Co, k, pad  (stride 1): the classifier's stem, both channel counts <= 8 (conv_small.cu)
+    (2, 64, 64, 3, 8, 7, 3),        # `Conv` 7x7 (classifier.py:27)
+    (3, 40, 24, 3, 8, 7, 3),        # ragged tiles
+    (2, 64, 64, 3, 8, 3, 1),        # unit-1 image conv / gate part
+    (3, 33, 70, 3, 8, 3, 1),
+    (2, 64, 64, 8, 8, 3, 1),        # unit-1 update gate on the hidden state
+    (5, 17, 31, 8, 8, 3, 1),
+    (2, 12, 12, 8, 8, 3, 0),        # VALID
+]
+
+
+@pytest.mark.parametrize("case", SMALL_CASES)
+def test_conv_trio_small_channels(dev, ref, case, request):
+    """direct kernels of the <= 8-channel layers against the CPU operator set and against the generic implicit GEMM
+    (eg_debug_set(7, 2) switches them off)"""
+    N, H, W, Ci, Co, k, p = case
+    OH, OW = H + 2 * p - k + 1, W + 2 * p - k + 1
+    rs = np.random.RandomState(hash(case) % 2**31)
+    x, w, b = rnd(rs, N, H, W, Ci), rnd(rs, k, k, Ci, Co, scale=0.1), rnd(rs, Co)
+    dy, bi, dw0 = rnd(rs, N, OH, OW, Co), rnd(rs, Ci), rnd(rs, k, k, Ci, Co)
+    request.addfinalizer(lambda: dev.lib.eg_debug_set(7, 0))
+    outs = {}
+    for route in (0, 2):
+        dev.lib.eg_debug_set(7, route)
+        l0 = dev.launches
+        outs[route] = [
+            both(dev, ref, "conv_fwd", [x, w, b], [(N, OH, OW, Co)], 1, p, "simt")[0],
+            both(dev, ref, "conv_fwd", [x, w, None], [(N, OH, OW, Co)], 1, p, "simt")[0],
+            both(dev, ref, "conv_bwd_data", [dy, w, None], [(N, H, W, Ci)], 1, p, "simt")[0],
+            both(dev, ref, "conv_bwd_data", [dy, w, bi], [(N, H, W, Ci)], 1, p, "simt")[0],
+            both(dev, ref, "conv_bwd_weight", [x, dy], [(k, k, Ci, Co)], 1, p, False, "simt", tol=5e-5)[0],
+            both(dev, ref, "conv_bwd_weight", [x, dy], [dw0.copy()], 1, p, True, "simt", tol=5e-5)[0]]
+        if route == 0:
+            assert dev.launches - l0 == 6, "one kernel per call on the direct route"
+    for a, g in zip(outs[0], outs[2]):
+        close(a, g, 5e-5, "direct vs generic")
+
+
 def test_conv_large_splitk(dev, ref):
     # big pixel count -> split-K wgrad with atomics
     rs = np.random.RandomState(5)
