@@ -139,15 +139,18 @@ __global__ void thin_im2col_row_k(const float* __restrict__ x, float* __restrict
     }
 }
 
-// col2im with the stride known at compile time: one block per input row (n, h).  The filter rows kh that reach
-// row h (at most ceil(KH / S)) each read one row of C pixels; their KW*Ci-column segments are staged in shared memory
-// with coalesced loads, then one thread per pixel w sums its taps from there.
+// col2im with the stride known at compile time: one block (256 threads) per input row (n, h).  The filter rows kh that
+// reach row h (at most ceil(KH / S)) each read one row of C pixels; their KW*Ci-column segments are staged in shared
+// memory with coalesced (16-byte when KW*Ci % 4 == 0) loads, then the threads -- pixel w x a slice of the channels, so that
+// a 64-pixel row still keeps 256 threads busy -- sum their taps from there in a fixed order (deterministic).
 template <int S>
-__global__ void thin_col2im_row_k(const float* __restrict__ C, const float* __restrict__ bias, float* __restrict__ dx,
-                                  ThinP p, int Npad) {
-    extern __shared__ float cs[];                            // [valid kh][OW][KW * Ci]
+__global__ void __launch_bounds__(256)
+thin_col2im_row_k(const float* __restrict__ C, const float* __restrict__ bias, float* __restrict__ dx, ThinP p, int Npad) {
+    extern __shared__ float4 cs4[];                          // [valid kh][OW][KW * Ci]
+    float* cs = reinterpret_cast<float*>(cs4);
     const int row = blockIdx.x, n = row / p.H, h = row - n * p.H;
     const int kwc = p.KW * p.Ci, seg = p.OW * kwc;
+    const bool vec = (kwc & 3) == 0 && (Npad & 3) == 0;
     int nv = 0;
     for (int kh = 0; kh < p.KH; ++kh) {
         const int hh = h + p.pad_t - kh;
@@ -155,33 +158,48 @@ __global__ void thin_col2im_row_k(const float* __restrict__ C, const float* __re
         const int oh = hh / S;
         if (oh >= p.OH) continue;
         const float* src = C + ((long long)n * p.OH + oh) * p.OW * Npad + kh * kwc;
-        for (int i = threadIdx.x; i < seg; i += blockDim.x) {
-            const int ow = i / kwc, e = i - ow * kwc;
-            cs[nv * seg + i] = __ldg(src + (long long)ow * Npad + e);
+        if (vec) {
+            const int kq = kwc >> 2;
+            float4* dst = reinterpret_cast<float4*>(cs + nv * seg);
+            for (int i = threadIdx.x; i < p.OW * kq; i += blockDim.x) {
+                const int ow = i / kq, e = i - ow * kq;
+                dst[i] = __ldg(reinterpret_cast<const float4*>(src + (long long)ow * Npad) + e);
+            }
+        } else {
+            for (int i = threadIdx.x; i < seg; i += blockDim.x) {
+                const int ow = i / kwc, e = i - ow * kwc;
+                cs[nv * seg + i] = __ldg(src + (long long)ow * Npad + e);
+            }
         }
         ++nv;
     }
     __syncthreads();
-    for (int w = threadIdx.x; w < p.W; w += blockDim.x) {
+    const int Wr = (p.W + 31) & ~31;
+    const int parts = (int)blockDim.x >= Wr ? (int)blockDim.x / Wr : 1;
+    const int cpt = (p.Ci + parts - 1) / parts;              // channels per thread
+    for (int t = threadIdx.x; t < Wr * parts; t += blockDim.x) {
+        const int w = t % Wr, c0 = (t / Wr) * cpt;
+        const int cnt = min(p.Ci - c0, cpt);
+        if (w >= p.W || cnt <= 0) continue;
         float acc[kThinMaxCi];
 #pragma unroll
-        for (int c = 0; c < kThinMaxCi; ++c) acc[c] = (bias != nullptr && c < p.Ci) ? __ldg(bias + c) : 0.f;
+        for (int j = 0; j < kThinMaxCi; ++j) acc[j] = (bias != nullptr && j < cnt) ? __ldg(bias + c0 + j) : 0.f;
         for (int v = 0; v < nv; ++v) {
             for (int kw = 0; kw < p.KW; ++kw) {
                 const int ww = w + p.pad_l - kw;
                 if (ww < 0 || ww % S) continue;
                 const int ow = ww / S;
                 if (ow >= p.OW) continue;
-                const float* r = cs + v * seg + ow * kwc + kw * p.Ci;
+                const float* r = cs + v * seg + ow * kwc + kw * p.Ci + c0;
 #pragma unroll
-                for (int c = 0; c < kThinMaxCi; ++c)
-                    if (c < p.Ci) acc[c] += r[c];
+                for (int j = 0; j < kThinMaxCi; ++j)
+                    if (j < cnt) acc[j] += r[j];
             }
         }
-        float* o = dx + ((long long)row * p.W + w) * p.Ci;
+        float* o = dx + ((long long)row * p.W + w) * p.Ci + c0;
 #pragma unroll
-        for (int c = 0; c < kThinMaxCi; ++c)
-            if (c < p.Ci) o[c] = acc[c];
+        for (int j = 0; j < kThinMaxCi; ++j)
+            if (j < cnt) o[j] = acc[j];
     }
 }
 
@@ -375,7 +393,7 @@ int eg_thin_conv2d_bwd_data(const eg_conv_shape* s, const float* dy, const float
     {
         if (int r = eg_tc_conv2d_fwd(&g, dy, wt, nullptr, C, three_x, st)) return r;
     }
-    const int threads = s->W >= 256 ? 256 : (s->W + 31) / 32 * 32;
+    const int threads = 256;
     const size_t smem = sizeof(float) * (size_t)((s->KH + s->stride - 1) / s->stride) * s->OW * s->KW * s->Ci;
     if (s->stride == 1 && smem <= 40 * 1024) thin_col2im_row_k<1><<<s->N * s->H, threads, smem, st>>>(C, bias, dx, p, Npad);
     else if (s->stride == 2 && smem <= 40 * 1024) thin_col2im_row_k<2><<<s->N * s->H, threads, smem, st>>>(C, bias, dx, p, Npad);
