@@ -1262,7 +1262,7 @@ int set_attrs() {
 int pick_bn(int n) { return n % 128 == 0 ? 128 : 64; }
 
 // wgrad operand layout knobs: {TMA swizzle enum, UMMA layout type, SBO bytes} (tools/tc_probe.py can sweep them)
-int g_dbg[8] = {(int)CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, 1, 512, 0, 64, 2, 0, 0};
+int g_dbg[8] = {(int)CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, 1, 512, 0, 64, 2 | 4, 0, 0};
 
 // Prepared-filter sets (eg_filter_set_*): the tensor-core kernels read a re-laid-out / hi+lo-split copy of the filter.
 // Preparing it before every launch cost 221 small kernels per 14-class training step although the weights only change
@@ -1501,8 +1501,10 @@ int eg_thin_conv2d_bwd_weight(const eg_conv_shape* s, const float* x, const floa
 
 // ---- capability queries ------------------------------------------------------------------------------
 // g_dbg[5]: which passes take the thin-channel route of conv_thin.cu (bit 0 fwd, bit 1 input grad, bit 2 filter grad).
-// Measured on B200 (tools/thin_time.py): the input gradient is 1.9x faster than the FFMA kernel, forward and filter
-// gradient are not (the patch matrix round trip costs what the dense product saves), so only bit 1 is on by default.
+// Measured on B200: the input gradient is 1.9x faster than the FFMA kernel (tools/thin_time.py); the filter gradient is
+// 1.15x (critic first layer) to 2x (8 -> 128 classifier layers) faster since the round-2 filter-gradient kernel
+// (tools/thin_wgrad_time.py: 442 -> 385, 452 -> 271, 216 -> 106 us); the forward is faster gathered (TcGather).  Default:
+// bits 1 and 2.
 static bool thin_fwd(const eg_conv_shape* s) { return (g_dbg[5] & 1) && eg_thin_supported_fwd(s); }
 static bool thin_bwd_data(const eg_conv_shape* s) { return (g_dbg[5] & 2) && eg_thin_supported_bwd_data(s); }
 static bool thin_bwd_weight(const eg_conv_shape* s) { return (g_dbg[5] & 4) && eg_thin_supported_bwd_weight(s); }

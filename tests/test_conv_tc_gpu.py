@@ -76,13 +76,13 @@ def test_tc_conv_trio(dev, ref, case, algo, request):
     x, w, b = rnd(rs, N, H, W, Ci), rnd(rs, k, k, Ci, Co, scale=0.05), rnd(rs, Co)
     dy, bi = rnd(rs, N, OH, OW, Co), rnd(rs, Ci)
     cs = dev._cs(x.shape, w.shape, dy.shape, s, p)
-    request.addfinalizer(lambda: dev.lib.eg_debug_set(5, 2))
+    request.addfinalizer(lambda: dev.lib.eg_debug_set(5, 2 | 4))
     # eg_debug_set(5, mask): bit 0 / 1 / 2 = forward / input gradient / filter gradient through the patch-matrix route of
     # conv_thin.cu, bit 3 = forward gather route OFF, bit 4 = filter-gradient gather route ON.  Thin layers run twice:
     # bit 5 = input gradient scattered by the dense product's epilogue instead of product matrix + col2im pass.
     # (a) forward gathered by the conditioning warps (the default) + gathered filter gradient + scatter epilogue,
-    # (b) everything through the patch matrix; the default for the filter gradient of these layers is the FFMA kernel
-    # (test_ops_gpu.py).
+    # (b) everything through the patch matrix.  Default (2 | 4): gathered forward, input and filter gradient through the
+    # patch matrix; the FFMA filter gradient of these layers is covered by test_ops_gpu.py.
     routes = [2 | 16 | 32, 7 | 8] if Ci <= 8 else [2]
     for route in routes:
         dev.lib.eg_debug_set(5, route)

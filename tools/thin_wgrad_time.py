@@ -1,5 +1,5 @@
 """Filter gradient of the thin (image-side) layers: FFMA kernels (default) against the patch-matrix route on the tensor
-cores (eg_debug_set(5, 2 | 4): im2col + tcgen05 filter-gradient kernel), cold inputs (a 256 MB buffer is rewritten between
+cores (eg_debug_set(5, 2 | 4), the default since this measurement: im2col + tcgen05 filter-gradient kernel), cold inputs (a 256 MB buffer is rewritten between
 launches)."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -32,7 +32,6 @@ for name, N, H, W, Ci, Co, k, s, p in CASES:
     t0 = timeit(lambda: dev.conv_bwd_weight(x, dy, ref, s, p, False, "tc3x"))
     dev.lib.eg_debug_set(5, 2 | 4)
     t1 = timeit(lambda: dev.conv_bwd_weight(x, dy, dw, s, p, False, "tc3x"))
-    dev.lib.eg_debug_set(5, 2)
     err = float((dw - ref).abs().max() / ref.abs().max())
     nbytes = 4.0 * (x.numel() + dy.numel())
     print(f"{name:32s} FFMA {t0*1e3:7.1f} us | patch matrix + tcgen05 {t1*1e3:7.1f} us | HBM floor {nbytes/6.5e12*1e6:6.1f} us | rel diff {err:.1e}", flush=True)
