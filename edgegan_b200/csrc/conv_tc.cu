@@ -1503,7 +1503,7 @@ int eg_thin_conv2d_bwd_weight(const eg_conv_shape* s, const float* x, const floa
 // g_dbg[5]: which passes take the thin-channel route of conv_thin.cu (bit 0 fwd, bit 1 input grad, bit 2 filter grad).
 // Measured on B200: the input gradient is 1.9x faster than the FFMA kernel (tools/thin_time.py); the filter gradient is
 // 1.15x (critic first layer) to 2x (8 -> 128 classifier layers) faster since the round-2 filter-gradient kernel
-// (tools/thin_wgrad_time.py: 442 -> 385, 452 -> 271, 216 -> 106 us); the forward is faster gathered (TcGather).  Default:
+// (tools/thin_routes_time.py: 442 -> 385, 452 -> 271, 216 -> 106 us); the forward is faster gathered (TcGather).  Default:
 // bits 1 and 2.
 static bool thin_fwd(const eg_conv_shape* s) { return (g_dbg[5] & 1) && eg_thin_supported_fwd(s); }
 static bool thin_bwd_data(const eg_conv_shape* s) { return (g_dbg[5] & 2) && eg_thin_supported_bwd_data(s); }
