@@ -1262,7 +1262,7 @@ int set_attrs() {
 int pick_bn(int n) { return n % 128 == 0 ? 128 : 64; }
 
 // wgrad operand layout knobs: {TMA swizzle enum, UMMA layout type, SBO bytes} (tools/tc_probe.py can sweep them)
-int g_dbg[8] = {(int)CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, 1, 512, 0, 64, 2 | 4, 0, 0};
+int g_dbg[8] = {(int)CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, 1, 512, 0, 64, 2 | 4 | 32, 0, 0};
 
 // Prepared-filter sets (eg_filter_set_*): the tensor-core kernels read a re-laid-out / hi+lo-split copy of the filter.
 // Preparing it before every launch cost 221 small kernels per 14-class training step although the weights only change
@@ -1504,7 +1504,7 @@ int eg_thin_conv2d_bwd_weight(const eg_conv_shape* s, const float* x, const floa
 // Measured on B200: the input gradient is 1.9x faster than the FFMA kernel (tools/thin_time.py); the filter gradient is
 // 1.15x (critic first layer) to 2x (8 -> 128 classifier layers) faster since the round-2 filter-gradient kernel
 // (tools/thin_routes_time.py: 442 -> 385, 452 -> 271, 216 -> 106 us); the forward is faster gathered (TcGather).  Default:
-// bits 1 and 2.
+// bits 1 and 2 (and bit 5: the input gradient's scatter epilogue, below).
 static bool thin_fwd(const eg_conv_shape* s) { return (g_dbg[5] & 1) && eg_thin_supported_fwd(s); }
 static bool thin_bwd_data(const eg_conv_shape* s) { return (g_dbg[5] & 2) && eg_thin_supported_bwd_data(s); }
 static bool thin_bwd_weight(const eg_conv_shape* s) { return (g_dbg[5] & 4) && eg_thin_supported_bwd_weight(s); }
@@ -1731,9 +1731,10 @@ int eg_tc_conv2d_fwd(const eg_conv_shape* s, const float* x, const float* w, con
 // whether the thin input gradient may use the scatter epilogue (conv_thin.cu)
 int eg_tc_scatter_supported(const eg_conv_shape* c) {
     const int K = c->KH * c->KW * c->Ci;
-    // OFF by default (eg_debug_set(5, |32) turns it on): measured equal to the product matrix + col2im pass (94.5 vs 94 us on
-    // the critic first layer at batch 64, tools/thin_time.py) -- the atomics cost what the round trip did -- and the col2im
-    // pass is deterministic
+    // ON by default (g_dbg[5] bit 5).  With warm inputs it measured equal to the product matrix + col2im pass (94.5 vs 94 us,
+    // critic first layer at batch 64); with cold inputs, as inside the step, it is 6-40 % faster at batch 128
+    // (tools/thin_routes_time.py: 201 -> 123, 126 -> 99, 465 -> 436, 174 -> 159, 100 -> 73, 65 -> 50 us): the product matrix
+    // never goes to HBM.  The sums arrive by red.add, so the last bits depend on the order (like the filter gradients').
     if (!(g_dbg[5] & 32)) return 0;
     if (K > kGatherMaxK || K > 128 || c->KH > 8 || c->KW > 8) return 0;
     if (((c->KH - 1) * c->W + c->KW) * c->Ci >= 65536) return 0;

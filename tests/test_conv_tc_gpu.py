@@ -76,13 +76,14 @@ def test_tc_conv_trio(dev, ref, case, algo, request):
     x, w, b = rnd(rs, N, H, W, Ci), rnd(rs, k, k, Ci, Co, scale=0.05), rnd(rs, Co)
     dy, bi = rnd(rs, N, OH, OW, Co), rnd(rs, Ci)
     cs = dev._cs(x.shape, w.shape, dy.shape, s, p)
-    request.addfinalizer(lambda: dev.lib.eg_debug_set(5, 2 | 4))
+    request.addfinalizer(lambda: dev.lib.eg_debug_set(5, 2 | 4 | 32))
     # eg_debug_set(5, mask): bit 0 / 1 / 2 = forward / input gradient / filter gradient through the patch-matrix route of
     # conv_thin.cu, bit 3 = forward gather route OFF, bit 4 = filter-gradient gather route ON.  Thin layers run twice:
     # bit 5 = input gradient scattered by the dense product's epilogue instead of product matrix + col2im pass.
     # (a) forward gathered by the conditioning warps (the default) + gathered filter gradient + scatter epilogue,
-    # (b) everything through the patch matrix.  Default (2 | 4): gathered forward, input and filter gradient through the
-    # patch matrix; the FFMA filter gradient of these layers is covered by test_ops_gpu.py.
+    # (b) everything through the patch matrix, col2im pass for the input gradient.  Default (2 | 4 | 32): gathered forward,
+    # input gradient scattered by the dense product's epilogue, filter gradient through the patch matrix; the FFMA filter
+    # gradient of these layers is covered by test_ops_gpu.py.
     routes = [2 | 16 | 32, 7 | 8] if Ci <= 8 else [2]
     for route in routes:
         dev.lib.eg_debug_set(5, route)
@@ -254,7 +255,7 @@ def test_prepared_filter_set_thin_filters(dev, ref, Ci, Co, k, st, H):
     assert dev.filter_set_hits() == h0 + 2, "thin filter not served from the set"
     assert dev.launches - l0 == unmanaged - 3            # gather copy; transpose + operand preparation of the input gradient
     np.testing.assert_array_equal(dev.to_numpy(y), y_un)
-    np.testing.assert_array_equal(dev.to_numpy(dx), dx_un)
+    assert relerr(dev.to_numpy(dx), dx_un) < 1e-6        # scattered by red.add: same terms, order-dependent last bits
     assert relerr(y_un, run(ref, "conv_fwd", [x, w1, None], (N, OH, OH, Co), st, p)) < 2e-5
     assert relerr(dx_un, run(ref, "conv_bwd_data", [dy, w1, None], (N, H, H, Ci), st, p)) < 2e-5
     dev.upload(wd, w2)

@@ -7,7 +7,7 @@ dev = DeviceOps()
 rs = np.random.RandomState(0)
 rnd = lambda *s: dev.from_numpy(rs.standard_normal(s).astype(np.float32))
 N = int(os.environ.get("N", "64"))
-dev.lib.eg_debug_set(5, int(os.environ.get("THIN", "6")))     # which passes take the conv_thin.cu route (bit 0 fwd, 1 dgrad, 2 wgrad)
+dev.lib.eg_debug_set(5, int(os.environ.get("THIN", "38")))     # which passes take the conv_thin.cu route (bit 0 fwd, 1 dgrad, 2 wgrad)
 CASES = [("critic l0 128", N, 128, 128, 3, 64, 4, 2, 1), ("gen last 64", N, 64, 64, 3, 64, 5, 2, 1)]
 def timeit(f, n=5):
     f(); torch.cuda.synchronize()
