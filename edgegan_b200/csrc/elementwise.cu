@@ -94,6 +94,37 @@ __global__ void bicubic_up2_fwd_k(const float* __restrict__ x, float* __restrict
     y[i] = acc;
 }
 
+// the same, one thread per output PIXEL (C <= 4 channels: the image tensors in front of the patch critics): the tap
+// indices / weights and the 32-bit index arithmetic are shared by the channels
+template <int C>
+__global__ void __launch_bounds__(256) bicubic_up2_fwd_px_k(const float* __restrict__ x, float* __restrict__ y, int N, int H, int W) {
+    const int total = N * 2 * H * 2 * W;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int ox = i % (2 * W); int t = i / (2 * W);
+    const int oy = t % (2 * H); const int n = t / (2 * H);
+    int iy[4], ix[4]; float wy[4], wx[4];
+    const int ny = up2_taps(oy, H, iy, wy), nx = up2_taps(ox, W, ix, wx);
+    float acc[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) acc[c] = 0.f;
+    for (int b = 0; b < nx; ++b) {
+        float col[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) col[c] = 0.f;
+        for (int a = 0; a < ny; ++a) {
+            const float* src = x + ((size_t)(n * H + iy[a]) * W + ix[b]) * C;
+#pragma unroll
+            for (int c = 0; c < C; ++c) col[c] = fmaf(wy[a], __ldg(src + c), col[c]);
+        }
+#pragma unroll
+        for (int c = 0; c < C; ++c) acc[c] = fmaf(wx[b], col[c], acc[c]);
+    }
+    float* dst = y + (size_t)i * C;
+#pragma unroll
+    for (int c = 0; c < C; ++c) dst[c] = acc[c];
+}
+
 __global__ void bicubic_up2_bwd_k(const float* __restrict__ gy, float* __restrict__ gx, int N, int H, int W, int C) {
     const long long total = (long long)N * H * W * C;
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -302,6 +333,36 @@ __global__ void reflect_pad_bwd_k(const float* __restrict__ gy, float* __restric
     gx[i] = acc;
 }
 
+// 16-byte versions (C % 4 == 0, < 2^31 float4 elements): the encoder's maps have 64+ channels
+__global__ void __launch_bounds__(256) reflect_pad_fwd_v4_k(const float4* __restrict__ x, float4* __restrict__ y, int N, int H, int W, int C4, int p) {
+    const int HP = H + 2 * p, WP = W + 2 * p;
+    const unsigned total = (unsigned)N * HP * WP * C4;
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const unsigned c = i % C4; unsigned t = i / C4;
+    const int xx = (int)(t % WP); t /= WP;
+    const int yy = (int)(t % HP); const int n = (int)(t / HP);
+    y[i] = __ldg(x + ((size_t)(n * H + reflecti(yy - p, H)) * W + reflecti(xx - p, W)) * C4 + c);
+}
+__global__ void __launch_bounds__(256) reflect_pad_bwd_v4_k(const float4* __restrict__ gy, float4* __restrict__ gx, int N, int H, int W, int C4, int p) {
+    const int HP = H + 2 * p, WP = W + 2 * p;
+    const unsigned total = (unsigned)N * H * W * C4;
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const unsigned c = i % C4; unsigned t = i / C4;
+    const int ix = (int)(t % W); t /= W;
+    const int iy = (int)(t % H); const int n = (int)(t / H);
+    int ys[3], xs[3];
+    const int ny = reflect_sources(iy, H, p, ys), nx = reflect_sources(ix, W, p, xs);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int a = 0; a < ny; ++a)
+        for (int b = 0; b < nx; ++b) {
+            const float4 v = __ldg(gy + ((size_t)(n * HP + ys[a]) * WP + xs[b]) * C4 + c);
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+    gx[i] = acc;
+}
+
 __global__ void addrelu_pool2_fwd_k(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ y,
                                     int N, int H, int W, int C) {
     const int OH = H / 2, OW = W / 2;
@@ -421,7 +482,10 @@ int eg_act_bwd(const float* x_pre, const float* gy, float* gx, long long n, int 
 }
 int eg_bicubic_up2_fwd(const float* x, float* y, int N, int H, int W, int C, void* stream) {
     EG_REQUIRE(x && y && N > 0 && H > 0 && W > 0 && C > 0);
-    bicubic_up2_fwd_k<<<grid1d((long long)N * 4 * H * W * C), TB, 0, ST>>>(x, y, N, H, W, C);
+    const long long px = (long long)N * 4 * H * W;
+    if (C == 3 && px < (1ll << 31) && px * C < (1ll << 31)) bicubic_up2_fwd_px_k<3><<<grid1d(px, 256), 256, 0, ST>>>(x, y, N, H, W);
+    else if (C == 1 && px < (1ll << 31)) bicubic_up2_fwd_px_k<1><<<grid1d(px, 256), 256, 0, ST>>>(x, y, N, H, W);
+    else bicubic_up2_fwd_k<<<grid1d((long long)N * 4 * H * W * C), TB, 0, ST>>>(x, y, N, H, W, C);
     EG_CHECK_LAUNCH(); return 0;
 }
 int eg_bicubic_up2_bwd(const float* gy, float* gx, int N, int H, int W, int C, void* stream) {
@@ -506,12 +570,20 @@ int eg_bias_grad(const float* dy, long long rows, int C, float* db, int accumula
 }
 int eg_reflect_pad_fwd(const float* x, float* y, int N, int H, int W, int C, int p, void* stream) {
     EG_REQUIRE(x && y && N > 0 && H > p && W > p && C > 0 && p >= 0);
-    reflect_pad_fwd_k<<<grid1d((long long)N * (H + 2 * p) * (W + 2 * p) * C), TB, 0, ST>>>(x, y, N, H, W, C, p);
+    const long long n4 = (long long)N * (H + 2 * p) * (W + 2 * p) * (C / 4);
+    if (C % 4 == 0 && n4 < (1ll << 31) && al16(x) && al16(y))
+        reflect_pad_fwd_v4_k<<<grid1d(n4, 256), 256, 0, ST>>>(reinterpret_cast<const float4*>(x), reinterpret_cast<float4*>(y), N, H, W, C / 4, p);
+    else
+        reflect_pad_fwd_k<<<grid1d((long long)N * (H + 2 * p) * (W + 2 * p) * C), TB, 0, ST>>>(x, y, N, H, W, C, p);
     EG_CHECK_LAUNCH(); return 0;
 }
 int eg_reflect_pad_bwd(const float* gy, float* gx, int N, int H, int W, int C, int p, void* stream) {
     EG_REQUIRE(gy && gx && N > 0 && H > p && W > p && C > 0 && p >= 0);
-    reflect_pad_bwd_k<<<grid1d((long long)N * H * W * C), TB, 0, ST>>>(gy, gx, N, H, W, C, p);
+    const long long n4 = (long long)N * (H + 2 * p) * (W + 2 * p) * (C / 4);
+    if (C % 4 == 0 && n4 < (1ll << 31) && al16(gy) && al16(gx))
+        reflect_pad_bwd_v4_k<<<grid1d((long long)N * H * W * (C / 4), 256), 256, 0, ST>>>(reinterpret_cast<const float4*>(gy), reinterpret_cast<float4*>(gx), N, H, W, C / 4, p);
+    else
+        reflect_pad_bwd_k<<<grid1d((long long)N * H * W * C), TB, 0, ST>>>(gy, gx, N, H, W, C, p);
     EG_CHECK_LAUNCH(); return 0;
 }
 int eg_addrelu_pool2_fwd(const float* a, const float* b, float* y, int N, int H, int W, int C, void* stream) {

@@ -180,7 +180,7 @@ def test_rowdot(dev, ref):
     both(dev, ref, "rowdot_bwd_weight", [gd, h], [rnd(rs, F, 1), rnd(rs, 1)], True)
 
 
-@pytest.mark.parametrize("shape", [(2, 8, 8, 3), (1, 5, 7, 4), (2, 64, 64, 3)])
+@pytest.mark.parametrize("shape", [(2, 8, 8, 3), (1, 5, 7, 4), (2, 64, 64, 3), (3, 6, 5, 1), (2, 2, 2, 3)])
 def test_bicubic(dev, ref, shape):
     rs = np.random.RandomState(6)
     N, H, W, C = shape
@@ -234,6 +234,10 @@ def test_encoder_pieces(dev, ref):
     both(dev, ref, "reflect_pad_fwd", [x], [(2, 8, 10, 5)], 1)
     both(dev, ref, "reflect_pad_bwd", [rnd(rs, 2, 8, 10, 5)], [shape], 1)
     both(dev, ref, "reflect_pad_bwd", [rnd(rs, 1, 4, 4, 3)], [(1, 2, 2, 3)], 1)     # smallest map (4x4 block)
+    for sh in ((3, 6, 8, 64), (2, 2, 2, 8), (2, 5, 3, 12)):                          # 16-byte kernels (C % 4 == 0)
+        N, H, W, Cn = sh
+        both(dev, ref, "reflect_pad_fwd", [rnd(rs, *sh)], [(N, H + 2, W + 2, Cn)], 1)
+        both(dev, ref, "reflect_pad_bwd", [rnd(rs, N, H + 2, W + 2, Cn)], [sh], 1)
     a, b = rnd(rs, *shape), rnd(rs, *shape)
     both(dev, ref, "addrelu_pool2_fwd", [a, b], [(2, 3, 4, 5)])
     both(dev, ref, "addrelu_pool2_bwd", [a, b, rnd(rs, 2, 3, 4, 5)], [shape])
