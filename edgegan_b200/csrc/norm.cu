@@ -5,6 +5,7 @@
 //
 // Reference: nn/modules/normalization.py:10-29.
 #include "common.cuh"
+#include <cooperative_groups.h>
 
 #include <initializer_list>
 
@@ -261,16 +262,46 @@ __device__ __forceinline__ float4 colsum4(float4 v, float4 (*red)[8], int cols, 
     return s;
 }
 
+// The same over a thread-block CLUSTER of CL blocks that split the pixels of one (sample, channel group) slab: every
+// block publishes its K partial sums in its own shared memory, one cluster barrier, every block adds the CL partials in
+// rank order (so all blocks hold bit-identical sums).  With the slab split over a cluster, rows stay 128 bytes wide and
+// a block's share stays below 64 KB (>= 3 blocks per SM) even for 32x32- and 64x64-pixel maps, which one block per slab
+// could only hold as 32-byte rows or not at all.  `part` must not be reused by a later exchange (no second barrier).
+template <int K>
+__device__ __forceinline__ void clsum4(float4 (&v)[K], float4 (*red)[8], float4 (*part)[8], int cols, int tx, int ty, int CL) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) v[k] = colsum4(v[k], red, cols, tx);
+    if (CL == 1) return;
+    cooperative_groups::cluster_group cl = cooperative_groups::this_cluster();
+    if (ty == 0) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) part[k][tx] = v[k];
+    }
+    cl.sync();
+#pragma unroll
+    for (int k = 0; k < K; ++k) v[k] = f4z();
+    for (int r = 0; r < CL; ++r) {
+        const float4* rp = reinterpret_cast<const float4*>(cl.map_shared_rank(&part[0][0], r));
+#pragma unroll
+        for (int k = 0; k < K; ++k) { const float4 t = rp[k * 8 + tx]; v[k].x += t.x; v[k].y += t.y; v[k].z += t.z; v[k].w += t.w; }
+    }
+}
+__device__ __forceinline__ void cl_exit(int CL) {            // no block may leave while a peer can still read its partials
+    if (CL > 1) cooperative_groups::this_cluster().sync();
+}
+
 __global__ void __launch_bounds__(kSmThreads)
-instnorm_fwd_sm(const float* __restrict__ x, float* __restrict__ y, float* __restrict__ stats, int P, int C, float eps,
-                int act, int cols) {
-    extern __shared__ float4 slab[];                         // [P][cols]
+instnorm_fwd_sm(const float* __restrict__ x, float* __restrict__ y, float* __restrict__ stats, int Pall, int C, float eps,
+                int act, int cols, int CL) {
+    extern __shared__ float4 slab[];                         // [P][cols], P = this block's share of the Pall pixels
     __shared__ float4 red[kSmThreads / 32][8];
+    __shared__ float4 part[2][8];
     const int rows = blockDim.x / cols, tx = threadIdx.x % cols, ty = threadIdx.x / cols;
-    const int n = blockIdx.y, c = (blockIdx.x * cols + tx) * 4;
+    const int n = blockIdx.y, c = ((blockIdx.x / CL) * cols + tx) * 4;
+    const int P = Pall / CL, p_off = (blockIdx.x % CL) * P;
     const size_t pitch = C / 4;
-    const float4* xp = reinterpret_cast<const float4*>(x + (size_t)n * P * C + c);
-    float4 a = f4z();
+    const float4* xp = reinterpret_cast<const float4*>(x + ((size_t)n * Pall + p_off) * C + c);
+    float4 a[1] = {f4z()};
     // four independent 16-byte loads in flight per thread before the first use (a one-load-per-iteration loop left the
     // kernel latency-bound at ~25 % of the HBM roofline)
     int p = ty;
@@ -278,54 +309,58 @@ instnorm_fwd_sm(const float* __restrict__ x, float* __restrict__ y, float* __res
         const float4 t0 = __ldg(xp + (size_t)p * pitch), t1 = __ldg(xp + (size_t)(p + rows) * pitch);
         const float4 t2 = __ldg(xp + (size_t)(p + 2 * rows) * pitch), t3 = __ldg(xp + (size_t)(p + 3 * rows) * pitch);
         slab[p * cols + tx] = t0; slab[(p + rows) * cols + tx] = t1; slab[(p + 2 * rows) * cols + tx] = t2; slab[(p + 3 * rows) * cols + tx] = t3;
-        a.x += (t0.x + t1.x) + (t2.x + t3.x); a.y += (t0.y + t1.y) + (t2.y + t3.y);
-        a.z += (t0.z + t1.z) + (t2.z + t3.z); a.w += (t0.w + t1.w) + (t2.w + t3.w);
+        a[0].x += (t0.x + t1.x) + (t2.x + t3.x); a[0].y += (t0.y + t1.y) + (t2.y + t3.y);
+        a[0].z += (t0.z + t1.z) + (t2.z + t3.z); a[0].w += (t0.w + t1.w) + (t2.w + t3.w);
     }
     for (; p < P; p += rows) {
         const float4 t = __ldg(xp + (size_t)p * pitch);
         slab[p * cols + tx] = t;
-        a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w;
+        a[0].x += t.x; a[0].y += t.y; a[0].z += t.z; a[0].w += t.w;
     }
-    a = colsum4(a, red, cols, tx);
-    const float4 mean = make_float4(a.x / P, a.y / P, a.z / P, a.w / P);
-    a = f4z();
+    clsum4<1>(a, red, part, cols, tx, ty, CL);
+    const float4 mean = make_float4(a[0].x / Pall, a[0].y / Pall, a[0].z / Pall, a[0].w / Pall);
+    a[0] = f4z();
     for (int p = ty; p < P; p += rows) {
         const float4 t = slab[p * cols + tx];
         float d;
-        d = t.x - mean.x; a.x = fmaf(d, d, a.x); d = t.y - mean.y; a.y = fmaf(d, d, a.y);
-        d = t.z - mean.z; a.z = fmaf(d, d, a.z); d = t.w - mean.w; a.w = fmaf(d, d, a.w);
+        d = t.x - mean.x; a[0].x = fmaf(d, d, a[0].x); d = t.y - mean.y; a[0].y = fmaf(d, d, a[0].y);
+        d = t.z - mean.z; a[0].z = fmaf(d, d, a[0].z); d = t.w - mean.w; a[0].w = fmaf(d, d, a[0].w);
     }
-    a = colsum4(a, red, cols, tx);
-    const float4 sd = make_float4(sqrtf(a.x / P), sqrtf(a.y / P), sqrtf(a.z / P), sqrtf(a.w / P));
+    clsum4<1>(a, red, part + 1, cols, tx, ty, CL);
+    const float4 sd = make_float4(sqrtf(a[0].x / Pall), sqrtf(a[0].y / Pall), sqrtf(a[0].z / Pall), sqrtf(a[0].w / Pall));
     const float4 r = make_float4(1.f / (sd.x + eps), 1.f / (sd.y + eps), 1.f / (sd.z + eps), 1.f / (sd.w + eps));
-    if (ty == 0) {
+    if (ty == 0 && p_off == 0) {
         float* st = stats + ((size_t)n * C + c) * 2;
         *reinterpret_cast<float4*>(st) = make_float4(mean.x, sd.x, mean.y, sd.y);
         *reinterpret_cast<float4*>(st + 4) = make_float4(mean.z, sd.z, mean.w, sd.w);
     }
-    float4* yp = reinterpret_cast<float4*>(y + (size_t)n * P * C + c);
+    float4* yp = reinterpret_cast<float4*>(y + ((size_t)n * Pall + p_off) * C + c);
 #pragma unroll 4
     for (int p = ty; p < P; p += rows) {
         const float4 t = slab[p * cols + tx];
         yp[p * pitch] = make_float4(act_fwd(act, (t.x - mean.x) * r.x), act_fwd(act, (t.y - mean.y) * r.y),
                                     act_fwd(act, (t.z - mean.z) * r.z), act_fwd(act, (t.w - mean.w) * r.w));
     }
+    cl_exit(CL);
 }
 
 __global__ void __launch_bounds__(kSmThreads)
 instnorm_bwd_sm(const float* __restrict__ x, const float* __restrict__ stats, const float* __restrict__ gy,
-                const float* __restrict__ addend, float* __restrict__ gx, int P, int C, float eps, int act, int cols) {
+                const float* __restrict__ addend, float* __restrict__ gx, int Pall, int C, float eps, int act, int cols, int CL) {
     extern __shared__ float4 slab[];                         // [2][P][cols]: centred x, masked cotangent
     __shared__ float4 red[kSmThreads / 32][8];
+    __shared__ float4 part[2][8];
     const int rows = blockDim.x / cols, tx = threadIdx.x % cols, ty = threadIdx.x / cols;
-    const int n = blockIdx.y, c = (blockIdx.x * cols + tx) * 4;
-    const size_t base = (size_t)n * P * C + c, pitch = C / 4;
+    const int n = blockIdx.y, c = ((blockIdx.x / CL) * cols + tx) * 4;
+    const int P = Pall / CL, p_off = (blockIdx.x % CL) * P;
+    const size_t base = ((size_t)n * Pall + p_off) * C + c, pitch = C / 4;
     const float4* xp = reinterpret_cast<const float4*>(x + base);
     const float4* gp = reinterpret_cast<const float4*>(gy + base);
     float4* scc = slab;
     float4* sgn = slab + (size_t)P * cols;
     const Stat4 s = load_stats4(stats, (size_t)n * C + c, eps);
-    float4 v0 = f4z(), v1 = f4z();
+    float4 vv[2] = {f4z(), f4z()};
+    float4 &v0 = vv[0], &v1 = vv[1];
     auto row = [&](int p, const float4 t, const float4 g) {
         float4 cc, gn;
         cc.x = t.x - s.mean.x; gn.x = g.x * act_grad(act, cc.x * s.r.x); v0.x += gn.x; v1.x = fmaf(gn.x, cc.x, v1.x);
@@ -343,11 +378,10 @@ instnorm_bwd_sm(const float* __restrict__ x, const float* __restrict__ stats, co
         row(p, t0, g0); row(p + rows, t1, g1); row(p + 2 * rows, t2, g2); row(p + 3 * rows, t3, g3);
     }
     for (; p < P; p += rows) row(p, __ldg(xp + (size_t)p * pitch), __ldg(gp + (size_t)p * pitch));
-    v0 = colsum4(v0, red, cols, tx);
-    v1 = colsum4(v1, red, cols, tx);
-    const float4 mg = make_float4(v0.x / P, v0.y / P, v0.z / P, v0.w / P);
-    const float4 kq = make_float4(s.r.x * s.r.x / s.sd.x * (v1.x / P), s.r.y * s.r.y / s.sd.y * (v1.y / P),
-                                  s.r.z * s.r.z / s.sd.z * (v1.z / P), s.r.w * s.r.w / s.sd.w * (v1.w / P));
+    clsum4<2>(vv, red, part, cols, tx, ty, CL);
+    const float4 mg = make_float4(v0.x / Pall, v0.y / Pall, v0.z / Pall, v0.w / Pall);
+    const float4 kq = make_float4(s.r.x * s.r.x / s.sd.x * (v1.x / Pall), s.r.y * s.r.y / s.sd.y * (v1.y / Pall),
+                                  s.r.z * s.r.z / s.sd.z * (v1.z / Pall), s.r.w * s.r.w / s.sd.w * (v1.w / Pall));
     const float4* ap = addend ? reinterpret_cast<const float4*>(addend + base) : nullptr;
     float4* op = reinterpret_cast<float4*>(gx + base);
 #pragma unroll 4
@@ -358,18 +392,21 @@ instnorm_bwd_sm(const float* __restrict__ x, const float* __restrict__ stats, co
         if (ap) { const float4 a = __ldg(ap + p * pitch); o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w; }
         op[p * pitch] = o;
     }
+    cl_exit(CL);
 }
 
 // second-order term of the gradient penalty (same formulas as instnorm_bwd2_k: centred second moments)
 __global__ void __launch_bounds__(kSmThreads)
 instnorm_bwd2_sm(const float* __restrict__ x, const float* __restrict__ stats, const float* __restrict__ gy,
-                 const float* __restrict__ t, float* __restrict__ out_gy, float* __restrict__ out_x, int P, int C,
-                 float eps, int act, int cols) {
+                 const float* __restrict__ t, float* __restrict__ out_gy, float* __restrict__ out_x, int Pall, int C,
+                 float eps, int act, int cols, int CL) {
     extern __shared__ float4 slab[];                         // [3][P][cols]: centred x, masked cotangent, tangent
     __shared__ float4 red[kSmThreads / 32][8];
+    __shared__ float4 part[5][8];
     const int rows = blockDim.x / cols, tx = threadIdx.x % cols, ty = threadIdx.x / cols;
-    const int n = blockIdx.y, c = (blockIdx.x * cols + tx) * 4;
-    const size_t base = (size_t)n * P * C + c, pitch = C / 4;
+    const int n = blockIdx.y, c = ((blockIdx.x / CL) * cols + tx) * 4;
+    const int P = Pall / CL, p_off = (blockIdx.x % CL) * P;
+    const size_t base = ((size_t)n * Pall + p_off) * C + c, pitch = C / 4;
     const float4* xp = reinterpret_cast<const float4*>(x + base);
     const float4* gp = reinterpret_cast<const float4*>(gy + base);
     const float4* tp = reinterpret_cast<const float4*>(t + base);
@@ -377,7 +414,8 @@ instnorm_bwd2_sm(const float* __restrict__ x, const float* __restrict__ stats, c
     float4* sgn = slab + (size_t)P * cols;
     float4* stt = slab + (size_t)2 * P * cols;
     const Stat4 s = load_stats4(stats, (size_t)n * C + c, eps);
-    float4 a0 = f4z(), a1 = f4z();
+    float4 aa[2] = {f4z(), f4z()};
+    float4 &a0 = aa[0], &a1 = aa[1];
     auto row = [&](int p, const float4 xv, const float4 g, const float4 tt) {
         float4 cc, gn;
         cc.x = xv.x - s.mean.x; gn.x = g.x * act_grad(act, cc.x * s.r.x);
@@ -396,10 +434,10 @@ instnorm_bwd2_sm(const float* __restrict__ x, const float* __restrict__ stats, c
         row(p, x0, g0, t0); row(p + rows, x1, g1, t1); row(p + 2 * rows, x2, g2, t2);
     }
     for (; p < P; p += rows) row(p, __ldg(xp + (size_t)p * pitch), __ldg(gp + (size_t)p * pitch), __ldg(tp + (size_t)p * pitch));
-    a0 = colsum4(a0, red, cols, tx);
-    a1 = colsum4(a1, red, cols, tx);
-    const float4 mg = make_float4(a0.x / P, a0.y / P, a0.z / P, a0.w / P), mt = make_float4(a1.x / P, a1.y / P, a1.z / P, a1.w / P);
-    float4 b0 = f4z(), b1 = f4z(), b2 = f4z();                // sum gn*c, sum t*c, sum (t-mt)*(gn-mg)
+    clsum4<2>(aa, red, part, cols, tx, ty, CL);
+    const float4 mg = make_float4(a0.x / Pall, a0.y / Pall, a0.z / Pall, a0.w / Pall), mt = make_float4(a1.x / Pall, a1.y / Pall, a1.z / Pall, a1.w / Pall);
+    float4 bb[3] = {f4z(), f4z(), f4z()};                     // sum gn*c, sum t*c, sum (t-mt)*(gn-mg)
+    float4 &b0 = bb[0], &b1 = bb[1], &b2 = bb[2];
     for (int p = ty; p < P; p += rows) {
         const float4 cc = scc[p * cols + tx], gn = sgn[p * cols + tx], tt = stt[p * cols + tx];
         b0.x = fmaf(gn.x, cc.x, b0.x); b1.x = fmaf(tt.x, cc.x, b1.x); b2.x = fmaf(tt.x - mt.x, gn.x - mg.x, b2.x);
@@ -407,11 +445,9 @@ instnorm_bwd2_sm(const float* __restrict__ x, const float* __restrict__ stats, c
         b0.z = fmaf(gn.z, cc.z, b0.z); b1.z = fmaf(tt.z, cc.z, b1.z); b2.z = fmaf(tt.z - mt.z, gn.z - mg.z, b2.z);
         b0.w = fmaf(gn.w, cc.w, b0.w); b1.w = fmaf(tt.w, cc.w, b1.w); b2.w = fmaf(tt.w - mt.w, gn.w - mg.w, b2.w);
     }
-    b0 = colsum4(b0, red, cols, tx);
-    b1 = colsum4(b1, red, cols, tx);
-    b2 = colsum4(b2, red, cols, tx);
+    clsum4<3>(bb, red, part + 2, cols, tx, ty, CL);
     float4 kap, ku, kqv, coef;
-#define EG_B2C(f) { const float q = b0.f / P, u = b1.f / P, w = b2.f / P, r = s.r.f, sd = s.sd.f; kap.f = r * r / sd; ku.f = kap.f * u; \
+#define EG_B2C(f) { const float q = b0.f / Pall, u = b1.f / Pall, w = b2.f / Pall, r = s.r.f, sd = s.sd.f; kap.f = r * r / sd; ku.f = kap.f * u; \
                     kqv.f = kap.f * q; coef.f = -kap.f * w + (2.f * r * r * r / (sd * sd) + r * r / (sd * sd * sd)) * q * u; }
     EG_B2C(x) EG_B2C(y) EG_B2C(z) EG_B2C(w)
 #undef EG_B2C
@@ -426,6 +462,7 @@ instnorm_bwd2_sm(const float* __restrict__ x, const float* __restrict__ stats, c
 #undef EG_B2O
         og[p * pitch] = o1; ox[p * pitch] = o2;
     }
+    cl_exit(CL);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -495,11 +532,33 @@ instnorm_bwd_apply_k(const float* __restrict__ x, const float* __restrict__ stat
 // another's reduction / store phases -- with one 128 KB block per SM the r02 capture showed 25 % of the HBM roofline),
 // down to 32-byte rows;
 // above that whatever still fits in 200 KB.
-int sm_cols(int P, int C, int tensors) {
-    for (int cols = 8; cols >= 2; cols >>= 1)
-        if (C % (cols * 4) == 0 && (size_t)P * cols * 16 * tensors <= 72 * 1024) return cols;
-    for (int cols = 8; cols >= 2; cols >>= 1)
-        if (C % (cols * 4) == 0 && (size_t)P * cols * 16 * tensors <= kSmCap) return cols;
+int g_in_cluster_off = 0;         // eg_norm_debug(-2): one block per slab only (the tests compare both)
+struct SmPick { int cols, cl; };
+// (row width in float4 columns, cluster size): the widest rows first, then the smallest cluster (1, 2, 4, 8 blocks that
+// split the pixels) whose per-block slabs stay below the limit; cols = 0: use the multi-pass kernels
+SmPick sm_pick(int P, int C, int tensors) {
+    const size_t limits[2] = {72 * 1024, kSmCap};
+    for (int l = 0; l < 2; ++l)
+        for (int cols = 8; cols >= 2; cols >>= 1) {
+            if (C % (cols * 4)) continue;
+            for (int cl = 1; cl <= (g_in_cluster_off ? 1 : 8); cl <<= 1) {
+                if (P % cl || (cl > 1 && P / cl < 64)) break;
+                if ((size_t)(P / cl) * cols * 16 * tensors <= limits[l]) return SmPick{cols, cl};
+            }
+        }
+    return SmPick{0, 1};
+}
+template <typename... KA, typename... A>
+int launch_sm(void (*kern)(KA...), int groups, int N, int threads, size_t smem, int CL, cudaStream_t st, A... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)(groups * CL), (unsigned)N); cfg.blockDim = dim3((unsigned)threads);
+    cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = (unsigned)CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = CL > 1 ? 1 : 0;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, static_cast<KA>(args)...);
+    if (e != cudaSuccess) return eg_fail(e, __FILE__, __LINE__);
     return 0;
 }
 // threads per block: about four rows per thread (small slabs are bound by the block-wide reductions, not by bytes)
@@ -599,13 +658,19 @@ int eg_tc_scratch(cudaStream_t st, int slot, size_t bytes, float** out);
 extern "C" {
 
 /* development knob (tools/norm_time.py): pixel count from which the instance-norm backward streams in two kernels */
-int eg_norm_debug(int value) { g_in_stream = value; return 0; }
+int eg_norm_debug(int value) {
+    if (value == -2) g_in_cluster_off = 1;                   // one block per slab only
+    else if (value == -3) g_in_cluster_off = 0;
+    else g_in_stream = value;
+    return 0;
+}
 
 int eg_instnorm_fwd(const float* x, float* y, float* stats, int N, int P, int C, float eps, int act, void* stream) {
     EG_REQUIRE(x && y && stats && N > 0 && P > 0 && C > 0 && N <= 65535);
-    if (const int cols = al16all({x, y, stats}) ? sm_cols(P, C, 1) : 0) {
+    if (const SmPick k = al16all({x, y, stats}) ? sm_pick(P, C, 1) : SmPick{0, 1}; k.cols) {
         if (int r = sm_attrs()) return r;
-        instnorm_fwd_sm<<<dim3(C / (cols * 4), N), sm_threads(P, cols), (size_t)P * cols * 16, (cudaStream_t)stream>>>(x, y, stats, P, C, eps, act, cols);
+        if (int r = launch_sm(instnorm_fwd_sm, C / (k.cols * 4), N, sm_threads(P / k.cl, k.cols), (size_t)(P / k.cl) * k.cols * 16, k.cl,
+                              (cudaStream_t)stream, x, y, stats, P, C, eps, act, k.cols, k.cl)) return r;
         EG_CHECK_LAUNCH();
         return 0;
     }
@@ -638,9 +703,10 @@ int eg_instnorm_bwd(const float* x, const float* stats, const float* gy, const f
         EG_CHECK_LAUNCH();
         return 0;
     }
-    if (const int cols = al16all({x, stats, gy, addend, gx}) ? sm_cols(P, C, 2) : 0) {
+    if (const SmPick k = al16all({x, stats, gy, addend, gx}) ? sm_pick(P, C, 2) : SmPick{0, 1}; k.cols) {
         if (int r = sm_attrs()) return r;
-        instnorm_bwd_sm<<<dim3(C / (cols * 4), N), sm_threads(P, cols), (size_t)P * cols * 32, (cudaStream_t)stream>>>(x, stats, gy, addend, gx, P, C, eps, act, cols);
+        if (int r = launch_sm(instnorm_bwd_sm, C / (k.cols * 4), N, sm_threads(P / k.cl, k.cols), (size_t)(P / k.cl) * k.cols * 32, k.cl,
+                              (cudaStream_t)stream, x, stats, gy, addend, gx, P, C, eps, act, k.cols, k.cl)) return r;
         EG_CHECK_LAUNCH();
         return 0;
     }
@@ -661,9 +727,10 @@ int eg_instnorm_bwd2(const float* x, const float* stats, const float* gy, const 
                      float* out_x, int N, int P, int C, float eps, int act, void* stream) {
     EG_REQUIRE(x && stats && gy && t && out_gy && out_x && N > 0 && P > 0 && C > 0 && N <= 65535);
     EG_REQUIRE(act != EG_ACT_TANH);   // second derivative of the activation is taken as zero
-    if (const int cols = al16all({x, stats, gy, t, out_gy, out_x}) ? sm_cols(P, C, 3) : 0) {
+    if (const SmPick k = al16all({x, stats, gy, t, out_gy, out_x}) ? sm_pick(P, C, 3) : SmPick{0, 1}; k.cols) {
         if (int r = sm_attrs()) return r;
-        instnorm_bwd2_sm<<<dim3(C / (cols * 4), N), sm_threads(P, cols), (size_t)P * cols * 48, (cudaStream_t)stream>>>(x, stats, gy, t, out_gy, out_x, P, C, eps, act, cols);
+        if (int r = launch_sm(instnorm_bwd2_sm, C / (k.cols * 4), N, sm_threads(P / k.cl, k.cols), (size_t)(P / k.cl) * k.cols * 48, k.cl,
+                              (cudaStream_t)stream, x, stats, gy, t, out_gy, out_x, P, C, eps, act, k.cols, k.cl)) return r;
         EG_CHECK_LAUNCH();
         return 0;
     }

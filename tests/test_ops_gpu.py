@@ -126,19 +126,25 @@ def test_conv_large_splitk(dev, ref):
     both(dev, ref, "conv_bwd_weight", [x, dy], [(4, 4, Ci, Co)], 2, 1, False, "simt", tol=5e-5)
 
 
-# (2, 32, 32, 128): 1024-pixel slabs -> the shared-memory kernels narrow the channel group to fit two / three slabs;
-# (1, 96, 96, 8): 9216 pixels do not fit at any width -> multi-pass kernels; (2, 4, 4, 40), (2, 5, 3, 6): odd channel counts
+# (2, 32, 32, 128), (2, 16, 32, 128): 512 / 1024-pixel slabs -> split over thread-block clusters of 2-8 blocks (128-byte rows);
+# (1, 64, 64, 64), (2, 64, 64, 32): 4096 pixels, clusters of 8 with narrower rows; (1, 96, 96, 8): 9216 pixels, 8 channels;
+# (1, 128, 128, 8): fits at no width -> multi-pass kernels; (2, 4, 4, 40), (2, 5, 3, 6): odd channel counts
 @pytest.mark.parametrize("shape", [(3, 8, 8, 64), (2, 16, 32, 128), (2, 4, 4, 40), (1, 2, 2, 512), (2, 32, 32, 128),
-                                   (1, 96, 96, 8), (2, 5, 3, 6)])
+                                   (1, 96, 96, 8), (2, 5, 3, 6), (1, 64, 64, 64), (2, 64, 64, 32), (1, 128, 128, 8),
+                                   (3, 24, 24, 96)])
 @pytest.mark.parametrize("act", ["none", "relu", "lrelu"])
-def test_instnorm(dev, ref, shape, act):
+def test_instnorm(dev, ref, shape, act, request):
+    """both block layouts: slabs split over thread-block clusters (default) and one block per slab (eg_norm_debug(-2))"""
     rs = np.random.RandomState(1)
     N, C = shape[0], shape[-1]
     x, gy, t, add = rnd(rs, *shape), rnd(rs, *shape), rnd(rs, *shape), rnd(rs, *shape)
-    y, st = both(dev, ref, "instnorm_fwd", [x], [shape, (N, C, 2)], act)
-    both(dev, ref, "instnorm_bwd", [x, st, gy, None], [shape], act, tol=1e-4)
-    both(dev, ref, "instnorm_bwd", [x, st, gy, add], [shape], act, tol=1e-4)
-    both(dev, ref, "instnorm_bwd2", [x, st, gy, t], [shape, shape], act, tol=2e-4)
+    request.addfinalizer(lambda: dev.lib.eg_norm_debug(-3))
+    for knob in (-3, -2):
+        dev.lib.eg_norm_debug(knob)
+        y, st = both(dev, ref, "instnorm_fwd", [x], [shape, (N, C, 2)], act)
+        both(dev, ref, "instnorm_bwd", [x, st, gy, None], [shape], act, tol=1e-4)
+        both(dev, ref, "instnorm_bwd", [x, st, gy, add], [shape], act, tol=1e-4)
+        both(dev, ref, "instnorm_bwd2", [x, st, gy, t], [shape, shape], act, tol=2e-4)
 
 
 @pytest.mark.parametrize("act", ["none", "relu", "lrelu", "tanh", "sigmoid"])
