@@ -264,9 +264,8 @@ __device__ __forceinline__ float4 colsum4(float4 v, float4 (*red)[8], int cols, 
 
 // The same over a thread-block CLUSTER of CL blocks that split the pixels of one (sample, channel group) slab: every
 // block publishes its K partial sums in its own shared memory, one cluster barrier, every block adds the CL partials in
-// rank order (so all blocks hold bit-identical sums).  With the slab split over a cluster, rows stay 128 bytes wide and
-// a block's share stays below 64 KB (>= 3 blocks per SM) even for 32x32- and 64x64-pixel maps, which one block per slab
-// could only hold as 32-byte rows or not at all.  `part` must not be reused by a later exchange (no second barrier).
+// rank order (so all blocks hold bit-identical sums).  Used for the slabs one block cannot hold below 72 KB (64x64-pixel
+// maps and larger, see sm_pick).  `part` must not be reused by a later exchange (no second barrier).
 template <int K>
 __device__ __forceinline__ void clsum4(float4 (&v)[K], float4 (*red)[8], float4 (*part)[8], int cols, int tx, int ty, int CL) {
 #pragma unroll
@@ -278,13 +277,20 @@ __device__ __forceinline__ void clsum4(float4 (&v)[K], float4 (*red)[8], float4 
         for (int k = 0; k < K; ++k) part[k][tx] = v[k];
     }
     cl.sync();
+    if (ty == 0) {                                           // one row of threads reads the peers, the block shares the totals
 #pragma unroll
-    for (int k = 0; k < K; ++k) v[k] = f4z();
-    for (int r = 0; r < CL; ++r) {
-        const float4* rp = reinterpret_cast<const float4*>(cl.map_shared_rank(&part[0][0], r));
+        for (int k = 0; k < K; ++k) v[k] = f4z();
+        for (int r = 0; r < CL; ++r) {
+            const float4* rp = reinterpret_cast<const float4*>(cl.map_shared_rank(&part[0][0], r));
 #pragma unroll
-        for (int k = 0; k < K; ++k) { const float4 t = rp[k * 8 + tx]; v[k].x += t.x; v[k].y += t.y; v[k].z += t.z; v[k].w += t.w; }
+            for (int k = 0; k < K; ++k) { const float4 t = rp[k * 8 + tx]; v[k].x += t.x; v[k].y += t.y; v[k].z += t.z; v[k].w += t.w; }
+        }
+#pragma unroll
+        for (int k = 0; k < K; ++k) red[k][tx] = v[k];
     }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < K; ++k) v[k] = red[k][tx];
 }
 __device__ __forceinline__ void cl_exit(int CL) {            // no block may leave while a peer can still read its partials
     if (CL > 1) cooperative_groups::this_cluster().sync();
@@ -534,18 +540,29 @@ instnorm_bwd_apply_k(const float* __restrict__ x, const float* __restrict__ stat
 // above that whatever still fits in 200 KB.
 int g_in_cluster_off = 0;         // eg_norm_debug(-2): one block per slab only (the tests compare both)
 struct SmPick { int cols, cl; };
-// (row width in float4 columns, cluster size): the widest rows first, then the smallest cluster (1, 2, 4, 8 blocks that
-// split the pixels) whose per-block slabs stay below the limit; cols = 0: use the multi-pass kernels
+// (row width in float4 columns, cluster size); cols = 0: use the multi-pass kernels.  Measured (tools/norm_time.py, cold
+// inputs): for slabs that fit one block below 72 KB at some width (down to 32-byte rows) one block per slab is as fast or
+// faster than a cluster (32x32 maps: backward 254 us against 361 us split over 4 blocks -- the cluster barriers and the
+// distributed-shared-memory exchange cost more than the wider rows give), so clusters serve the slabs that do not fit:
+// 64x64 maps and larger (forward 165 -> 115 us, backward 234 -> 165 us on [128, 64x64, 64]; the second-order kernel
+// 1315 -> 356 us, it had fallen back to the multi-pass kernel).
 SmPick sm_pick(int P, int C, int tensors) {
-    const size_t limits[2] = {72 * 1024, kSmCap};
-    for (int l = 0; l < 2; ++l)
-        for (int cols = 8; cols >= 2; cols >>= 1) {
+    const size_t soft = 72 * 1024;
+    for (int cols = 8; cols >= 2; cols >>= 1)                                  // one block per slab, >= 3 blocks per SM
+        if (C % (cols * 4) == 0 && (size_t)P * cols * 16 * tensors <= soft) return SmPick{cols, 1};
+    if (!g_in_cluster_off && P >= 4096)
+        for (int cols = 8; cols >= 2; cols >>= 1) {                            // slab split over 2 / 4 / 8 blocks
             if (C % (cols * 4)) continue;
-            for (int cl = 1; cl <= (g_in_cluster_off ? 1 : 8); cl <<= 1) {
-                if (P % cl || (cl > 1 && P / cl < 64)) break;
-                if ((size_t)(P / cl) * cols * 16 * tensors <= limits[l]) return SmPick{cols, cl};
+            for (int cl = 2; cl <= 8; cl <<= 1) {
+                if (P % cl || P / cl < 512) break;
+                if ((size_t)(P / cl) * cols * 16 * tensors <= soft) return SmPick{cols, cl};
             }
         }
+    for (int cols = 8; cols >= 2; cols >>= 1)                                  // one big block per SM
+        if (C % (cols * 4) == 0 && (size_t)P * cols * 16 * tensors <= kSmCap) return SmPick{cols, 1};
+    if (!g_in_cluster_off && P >= 4096)
+        for (int cols = 8; cols >= 2; cols >>= 1)
+            if (C % (cols * 4) == 0 && P % 8 == 0 && (size_t)(P / 8) * cols * 16 * tensors <= kSmCap) return SmPick{cols, 8};
     return SmPick{0, 1};
 }
 template <typename... KA, typename... A>

@@ -126,9 +126,9 @@ def test_conv_large_splitk(dev, ref):
     both(dev, ref, "conv_bwd_weight", [x, dy], [(4, 4, Ci, Co)], 2, 1, False, "simt", tol=5e-5)
 
 
-# (2, 32, 32, 128), (2, 16, 32, 128): 512 / 1024-pixel slabs -> split over thread-block clusters of 2-8 blocks (128-byte rows);
-# (1, 64, 64, 64), (2, 64, 64, 32): 4096 pixels, clusters of 8 with narrower rows; (1, 96, 96, 8): 9216 pixels, 8 channels;
-# (1, 128, 128, 8): fits at no width -> multi-pass kernels; (2, 4, 4, 40), (2, 5, 3, 6): odd channel counts
+# (2, 32, 32, 128): 1024-pixel slabs -> one block per slab with a narrower channel group; (1, 64, 64, 64), (2, 64, 64, 32),
+# (1, 96, 96, 8), (1, 128, 128, 8): 4096+ pixels -> slabs split over thread-block clusters of 4-8 blocks (with clusters off:
+# one big block per SM or the multi-pass kernels); (2, 4, 4, 40), (2, 5, 3, 6): odd channel counts -> multi-pass kernels
 @pytest.mark.parametrize("shape", [(3, 8, 8, 64), (2, 16, 32, 128), (2, 4, 4, 40), (1, 2, 2, 512), (2, 32, 32, 128),
                                    (1, 96, 96, 8), (2, 5, 3, 6), (1, 64, 64, 64), (2, 64, 64, 32), (1, 128, 128, 8),
                                    (3, 24, 24, 96)])
