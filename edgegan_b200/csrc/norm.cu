@@ -579,9 +579,10 @@ int launch_sm(void (*kern)(KA...), int groups, int N, int threads, size_t smem, 
     return 0;
 }
 // threads per block: about four rows per thread (small slabs are bound by the block-wide reductions, not by bytes)
+int g_sm_rows_cap = 64;
 int sm_threads(int P, int cols) {
     int rows = 4;
-    while (rows < 64 && rows * 4 < P) rows <<= 1;
+    while (rows < g_sm_rows_cap && rows * 4 < P) rows <<= 1;
     int t = rows * cols;
     if (t < 64) t = 64;
     if (t > kSmThreads) t = kSmThreads;
@@ -678,6 +679,7 @@ extern "C" {
 int eg_norm_debug(int value) {
     if (value == -2) g_in_cluster_off = 1;                   // one block per slab only
     else if (value == -3) g_in_cluster_off = 0;
+    else if (value <= -10) g_sm_rows_cap = -value;           // -64 (default) / -128 / -256: thread rows per block
     else g_in_stream = value;
     return 0;
 }
