@@ -133,9 +133,14 @@ def test_train_loop_graph_step_equals_eager_step(dev):
         # difference -- stale alpha, a missed buffer refill -- moves their weights by several lr; measured run-to-run
         # scatter from the reordering of fp32 atomics, amplified by the penalty: up to 0.12 lr).  G1 / G2 / E are updated
         # AFTER the critics moved, which amplifies that noise once more: 1.5 lr.
+        worst = {"critics": 0.0, "G/E": 0.0}
         for n in w_eager:
             assert np.isfinite(w_graph[n]).all(), n
-            tol = 1e-4 if n.startswith(("D/", "D_patch2/", "D_patch3/", "D2/")) else 3e-4
-            assert np.abs(w_graph[n] - w_eager[n]).max() <= tol, (k, n, np.abs(w_graph[n] - w_eager[n]).max())
+            crit = n.startswith(("D/", "D_patch2/", "D_patch3/", "D2/"))
+            tol = 1e-4 if crit else 3e-4
+            dev_ = float(np.abs(w_graph[n] - w_eager[n]).max())
+            worst["critics" if crit else "G/E"] = max(worst["critics" if crit else "G/E"], dev_)
+            assert dev_ <= tol, (k, n, dev_)
+        print(f"graph vs eager, iteration {k}: worst weight deviation critics {worst['critics']:.2e} (bar 1e-4), G/E {worst['G/E']:.2e} (bar 3e-4)")
         for n in l_eager:
             assert abs(l_graph[n] - l_eager[n]) <= 5e-3 * max(1.0, abs(l_eager[n])), (k, n, l_graph[n], l_eager[n])
