@@ -129,18 +129,35 @@ def test_train_loop_graph_step_equals_eager_step(dev):
         m.update_model(*batches[k])                             # ... and the same iteration launched eagerly
         torch.cuda.synchronize()
         w_eager, l_eager = m.export_variables("var"), m.read_losses()
-        # The critics and the classifier are updated first (runs 1-4), from the snapshot: half a learning rate (a functional
-        # difference -- stale alpha, a missed buffer refill -- moves their weights by several lr; measured run-to-run
-        # scatter from the reordering of fp32 atomics, amplified by the penalty: up to 0.12 lr).  G1 / G2 / E are updated
-        # AFTER the critics moved, which amplifies that noise once more: 1.5 lr.
-        worst = {"critics": 0.0, "G/E": 0.0}
+        # What separates a functional difference (stale alpha, a missed buffer refill: RMSProp then moves MOST weights of
+        # the networks behind it by a sizeable part of a learning rate, 2e-4) from the reordering of fp32 atomics (filter
+        # gradients, the thin layers' scattered input gradient), which the penalty and the later runs amplify in a FEW
+        # weights (measured over 12 repetitions: worst single weight up to 0.14 lr in the critics, 0.54 lr in G / E, the
+        # distribution is heavy-tailed): the 99th percentile of the element-wise deviation must stay below 0.05 lr, the
+        # worst single weight below 5 lr.
+        lr = 2e-4
+        groups = {"critics": [], "G/E": []}
         for n in w_eager:
             assert np.isfinite(w_graph[n]).all(), n
             crit = n.startswith(("D/", "D_patch2/", "D_patch3/", "D2/"))
-            tol = 1e-4 if crit else 3e-4
-            dev_ = float(np.abs(w_graph[n] - w_eager[n]).max())
-            worst["critics" if crit else "G/E"] = max(worst["critics" if crit else "G/E"], dev_)
-            assert dev_ <= tol, (k, n, dev_)
-        print(f"graph vs eager, iteration {k}: worst weight deviation critics {worst['critics']:.2e} (bar 1e-4), G/E {worst['G/E']:.2e} (bar 3e-4)")
+            groups["critics" if crit else "G/E"].append(np.abs(w_graph[n] - w_eager[n]).ravel())
+        for g, parts in groups.items():
+            d = np.concatenate(parts)
+            p99, worst = float(np.quantile(d, 0.99)), float(d.max())
+            print(f"graph vs eager, iteration {k}, {g}: 99th percentile of |dw| {p99 / lr:.2e} lr (bar 0.05), worst {worst / lr:.2e} lr (bar 5)")
+            assert p99 <= 0.05 * lr and worst <= 5 * lr, (k, g, p99 / lr, worst / lr)
         for n in l_eager:
             assert abs(l_graph[n] - l_eager[n]) <= 5e-3 * max(1.0, abs(l_eager[n])), (k, n, l_graph[n], l_eager[n])
+    # negative control: the check has power -- the same iteration with OTHER host draws of alpha / eps (what a stale
+    # buffer would amount to) is far outside the bar
+    m.load_variables(var)
+    for st in m.stores.values():
+        st.load({n: ms[n] for n in st.offsets}, strict=True, what="ms")
+    m._rs = np.random.RandomState(12345)
+    m.update_model(*batches[3])
+    torch.cuda.synchronize()
+    w_other = m.export_variables("var")
+    d = np.concatenate([np.abs(w_other[n] - w_eager[n]).ravel() for n in w_eager if n.startswith(("D/", "D_patch2/", "D_patch3/"))])
+    p99 = float(np.quantile(d, 0.99))
+    print(f"negative control (other alpha / eps draws), critics: 99th percentile of |dw| {p99 / lr:.2e} lr")
+    assert p99 > 0.25 * lr, p99 / lr
