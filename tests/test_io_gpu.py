@@ -132,9 +132,10 @@ def test_train_loop_graph_step_equals_eager_step(dev):
         # What separates a functional difference (stale alpha, a missed buffer refill: RMSProp then moves MOST weights of
         # the networks behind it by a sizeable part of a learning rate, 2e-4) from the reordering of fp32 atomics (filter
         # gradients, the thin layers' scattered input gradient), which the penalty and the later runs amplify in a FEW
-        # weights (measured over 12 repetitions: worst single weight up to 0.14 lr in the critics, 0.54 lr in G / E, the
-        # distribution is heavy-tailed): the 99th percentile of the element-wise deviation must stay below 0.05 lr, the
-        # worst single weight below 5 lr.
+        # weights (measured over 20 repetitions: worst single weight up to 0.14 lr in the critics, 0.54 lr in G / E, heavy-
+        # tailed; 99th percentile of the element-wise deviation 3e-7 ... 3e-4 lr in the critics, 2e-6 ... 1.7e-2 lr in
+        # G / E; the negative control below gives 1.4 lr): the 99th percentile must stay below 0.15 lr, the worst single
+        # weight below 5 lr.
         lr = 2e-4
         groups = {"critics": [], "G/E": []}
         for n in w_eager:
@@ -144,8 +145,8 @@ def test_train_loop_graph_step_equals_eager_step(dev):
         for g, parts in groups.items():
             d = np.concatenate(parts)
             p99, worst = float(np.quantile(d, 0.99)), float(d.max())
-            print(f"graph vs eager, iteration {k}, {g}: 99th percentile of |dw| {p99 / lr:.2e} lr (bar 0.05), worst {worst / lr:.2e} lr (bar 5)")
-            assert p99 <= 0.05 * lr and worst <= 5 * lr, (k, g, p99 / lr, worst / lr)
+            print(f"graph vs eager, iteration {k}, {g}: 99th percentile of |dw| {p99 / lr:.2e} lr (bar 0.15), worst {worst / lr:.2e} lr (bar 5)")
+            assert p99 <= 0.15 * lr and worst <= 5 * lr, (k, g, p99 / lr, worst / lr)
         for n in l_eager:
             assert abs(l_graph[n] - l_eager[n]) <= 5e-3 * max(1.0, abs(l_eager[n])), (k, n, l_graph[n], l_eager[n])
     # negative control: the check has power -- the same iteration with OTHER host draws of alpha / eps (what a stale
@@ -160,4 +161,4 @@ def test_train_loop_graph_step_equals_eager_step(dev):
     d = np.concatenate([np.abs(w_other[n] - w_eager[n]).ravel() for n in w_eager if n.startswith(("D/", "D_patch2/", "D_patch3/"))])
     p99 = float(np.quantile(d, 0.99))
     print(f"negative control (other alpha / eps draws), critics: 99th percentile of |dw| {p99 / lr:.2e} lr")
-    assert p99 > 0.25 * lr, p99 / lr
+    assert p99 > 0.5 * lr, p99 / lr
