@@ -255,7 +255,7 @@ def test_prepared_filter_set_thin_filters(dev, ref, Ci, Co, k, st, H):
     assert dev.filter_set_hits() == h0 + 2, "thin filter not served from the set"
     assert dev.launches - l0 == unmanaged - 3            # gather copy; transpose + operand preparation of the input gradient
     np.testing.assert_array_equal(dev.to_numpy(y), y_un)
-    assert relerr(dev.to_numpy(dx), dx_un) < 1e-6        # scattered by red.add: same terms, order-dependent last bits
+    assert relerr(dev.to_numpy(dx), dx_un) < 1e-5        # scattered by red.add: same terms, order-dependent last bits
     assert relerr(y_un, run(ref, "conv_fwd", [x, w1, None], (N, OH, OH, Co), st, p)) < 2e-5
     assert relerr(dx_un, run(ref, "conv_bwd_data", [dy, w1, None], (N, H, H, Ci), st, p)) < 2e-5
     dev.upload(wd, w2)
