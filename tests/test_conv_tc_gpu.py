@@ -30,6 +30,8 @@ CASES = [
     (2, 9, 9, 3, 64, 3, 1, 1, 9, 9),           # stride 1, odd extent
     (2, 8, 8, 1, 128, 4, 2, 1, 4, 4),          # single channel
     (2, 12, 12, 8, 128, 3, 1, 1, 12, 12),      # classifier first layer (8 channels, 72 -> 96 / 128 columns)
+    (2, 12, 12, 8, 128, 1, 1, 0, 12, 12),      # the first MRU block's 1x1 `Conv_3` (8 -> 128): streaming kernels of conv_small.cu
+    (3, 7, 5, 8, 128, 1, 1, 0, 7, 5),          # the same, pixel count not a multiple of anything
     # filter gradient whose row side is below 128 channels (TMA zero-fills the missing rows)
     (2, 16, 16, 64, 64, 3, 1, 1, 16, 16),
     (2, 8, 8, 192, 64, 1, 1, 0, 8, 8),         # 1.5 row tiles
@@ -84,7 +86,8 @@ def test_tc_conv_trio(dev, ref, case, algo, request):
     # (b) everything through the patch matrix, col2im pass for the input gradient.  Default (2 | 4 | 32): gathered forward,
     # input gradient scattered by the dense product's epilogue, filter gradient through the patch matrix; the FFMA filter
     # gradient of these layers is covered by test_ops_gpu.py.
-    routes = [2 | 16 | 32, 7 | 8] if Ci <= 8 else [2]
+    # bit 6 = the dedicated 1x1 8 <-> 128 streaming kernels OFF (so that those shapes also run the routes above)
+    routes = [2 | 16 | 32 | 64, 7 | 8 | 64, 2 | 4 | 32] if Ci <= 8 else [2 | 4 | 32]
     for route in routes:
         dev.lib.eg_debug_set(5, route)
         used = [dev.lib.eg_conv2d_algo_for(C.byref(cs), i, 2) for i in range(3)]

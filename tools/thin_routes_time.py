@@ -25,7 +25,7 @@ def timeit(f, n=4):
         e0.record(); f(); e1.record(); torch.cuda.synchronize()
         tot += e0.elapsed_time(e1)
     return tot / n * 1e3
-D = 2 | 4          # + 32 = the scatter epilogue (the default since this measurement)
+D = 2 | 4 | 64     # + 32 = the scatter epilogue (the default since this measurement); 64 = dedicated 1x1 kernels OFF
 for name, N, H, W, Ci, Co, k, s, p, OH in CASES:
     OW = OH
     x, w, dy = rnd(N, H, W, Ci), rnd(k, k, Ci, Co), rnd(N, OH, OW, Co)
@@ -40,6 +40,11 @@ for name, N, H, W, Ci, Co, k, s, p, OH in CASES:
     for key, mask, algo in (("wgrad patch", D, "tc3x"), ("wgrad ffma", D, "simt")):
         dev.lib.eg_debug_set(5, mask)
         r[key] = timeit(lambda: dev.conv_bwd_weight(x, dy, dw, s, p, False, algo))
-    dev.lib.eg_debug_set(5, D | 32)
+    if k == 1:
+        dev.lib.eg_debug_set(5, 2 | 4 | 32)          # default: the streaming 1x1 kernels of conv_small.cu
+        r["1x1 fwd"] = timeit(lambda: dev.conv_fwd(x, w, None, y, s, p, "tc3x"))
+        r["1x1 dgrad"] = timeit(lambda: dev.conv_bwd_data(dy, w, None, dx, s, p, "tc3x"))
+        r["1x1 wgrad"] = timeit(lambda: dev.conv_bwd_weight(x, dy, dw, s, p, False, "tc3x"))
+    dev.lib.eg_debug_set(5, 2 | 4 | 32)
     floor = 4.0 * (x.numel() + dy.numel()) / 6.5e12 * 1e6
     print(f"{name:30s} HBM floor {floor:5.1f} us | " + " | ".join(f"{k_} {v:6.1f}" for k_, v in r.items()), flush=True)
