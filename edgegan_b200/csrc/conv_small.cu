@@ -285,8 +285,9 @@ int eg_small_conv2d_bwd_weight(const eg_conv_shape* s, const float* x, const flo
 
 // ---- 1x1 convolution between 8 and 128 channels (the first MRU block's `Conv_3`, nn/modules/conv.py:215-221) ----------
 // Pure streaming (17 MB + 268 MB per pass at batch 128): one warp per pixel, a lane owns 4 of the 128 wide-side channels
-// and keeps its 8 x 4 filter slice in registers; exact fp32 (FFMA).  The gathered tcgen05 route took 95-108 us per pass
-// (one K = 32 stage of which 8 columns are real), the HBM floor is 44 us.
+// and keeps its 8 x 4 filter slice in registers; exact fp32 (FFMA).  Measured (tools/thin_routes_time.py, cold inputs):
+// forward 69-79 us against 94 us gathered on the tensor cores (one K = 32 stage of which 8 columns are real), input
+// gradient 87-90 us against 98 us with the scatter epilogue; the HBM floor is 44 us.
 namespace {
 
 constexpr int kW1 = 128;       // wide-side channels (one warp x float4)
@@ -301,17 +302,27 @@ thin1x1_fwd_k(const float* __restrict__ x, const float* __restrict__ w, const fl
     for (int c = 0; c < kN1; ++c) wr[c] = __ldg(reinterpret_cast<const float4*>(w + c * kW1) + lane);
     const float4 b = bias ? __ldg(reinterpret_cast<const float4*>(bias) + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
     const long long warps = (long long)gridDim.x * 8, w0 = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
-#pragma unroll 2
-    for (long long p = w0; p < P; p += warps) {
-        const float4 x0 = __ldg(reinterpret_cast<const float4*>(x + p * kN1)), x1 = __ldg(reinterpret_cast<const float4*>(x + p * kN1) + 1);
-        const float xs[kN1] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
-        float4 a = b;
+    for (long long p0 = w0; p0 < P; p0 += 4 * warps) {
+        float4 xa[4], xb[4];
 #pragma unroll
-        for (int c = 0; c < kN1; ++c) {
-            a.x = fmaf(xs[c], wr[c].x, a.x); a.y = fmaf(xs[c], wr[c].y, a.y);
-            a.z = fmaf(xs[c], wr[c].z, a.z); a.w = fmaf(xs[c], wr[c].w, a.w);
+        for (int j = 0; j < 4; ++j) {
+            const long long p = p0 + j * warps;
+            const bool ok = p < P;
+            xa[j] = ok ? __ldg(reinterpret_cast<const float4*>(x + p * kN1)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            xb[j] = ok ? __ldg(reinterpret_cast<const float4*>(x + p * kN1) + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        reinterpret_cast<float4*>(y + p * kW1)[lane] = a;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const long long p = p0 + j * warps;
+            const float xs[kN1] = {xa[j].x, xa[j].y, xa[j].z, xa[j].w, xb[j].x, xb[j].y, xb[j].z, xb[j].w};
+            float4 a = b;
+#pragma unroll
+            for (int c = 0; c < kN1; ++c) {
+                a.x = fmaf(xs[c], wr[c].x, a.x); a.y = fmaf(xs[c], wr[c].y, a.y);
+                a.z = fmaf(xs[c], wr[c].z, a.z); a.w = fmaf(xs[c], wr[c].w, a.w);
+            }
+            if (p < P) reinterpret_cast<float4*>(y + p * kW1)[lane] = a;
+        }
     }
 }
 
@@ -326,59 +337,37 @@ thin1x1_dgrad_k(const float* __restrict__ dy, const float* __restrict__ w, const
     const float bv = (bias && (lane & 3) == 0) ? __ldg(bias + (lane >> 2)) : 0.f;
     const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
     const long long warps = (long long)gridDim.x * 8, w0 = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
-#pragma unroll 2
-    for (long long p = w0; p < P; p += warps) {
-        const float4 d = __ldg(reinterpret_cast<const float4*>(dy + p * kW1) + lane);
-        float s[kN1];
+    for (long long p0 = w0; p0 < P; p0 += 4 * warps) {          // 4 pixels per iteration: the loads are issued before the sums
+        float4 d4[4];
 #pragma unroll
-        for (int c = 0; c < kN1; ++c) s[c] = fmaf(d.x, wr[c].x, fmaf(d.y, wr[c].y, fmaf(d.z, wr[c].z, d.w * wr[c].w)));
-        float t[4], u[2];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const float send = b4 ? s[i] : s[4 + i];
-            t[i] = (b4 ? s[4 + i] : s[i]) + __shfl_xor_sync(0xffffffffu, send, 16);
+        for (int j = 0; j < 4; ++j) {
+            const long long p = p0 + j * warps;
+            d4[j] = p < P ? __ldg(reinterpret_cast<const float4*>(dy + p * kW1) + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
 #pragma unroll
-        for (int i = 0; i < 2; ++i) {
-            const float send = b3 ? t[i] : t[2 + i];
-            u[i] = (b3 ? t[2 + i] : t[i]) + __shfl_xor_sync(0xffffffffu, send, 8);
-        }
-        float v = (b2 ? u[1] : u[0]) + __shfl_xor_sync(0xffffffffu, b2 ? u[0] : u[1], 4);
-        v += __shfl_xor_sync(0xffffffffu, v, 2);
-        v += __shfl_xor_sync(0xffffffffu, v, 1);
-        if ((lane & 3) == 0) dx[p * kN1 + (lane >> 2)] = v + bv;
-    }
-}
-
-// dw[ci][co] (+)= sum_p x[p][ci] dy[p][co]: persistent blocks, 32 accumulators per lane, block sums in shared memory
-__global__ void __launch_bounds__(256)
-thin1x1_wgrad_k(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dw, long long P) {
-    __shared__ float red[kN1 * kW1];
-    const int lane = threadIdx.x & 31;
-    for (int i = threadIdx.x; i < kN1 * kW1; i += blockDim.x) red[i] = 0.f;
-    float4 acc[kN1];
+        for (int j = 0; j < 4; ++j) {
+            const long long p = p0 + j * warps;
+            const float4 d = d4[j];
+            float s[kN1];
 #pragma unroll
-    for (int c = 0; c < kN1; ++c) acc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
-    const long long warps = (long long)gridDim.x * 8, w0 = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
-#pragma unroll 2
-    for (long long p = w0; p < P; p += warps) {
-        const float4 d = __ldg(reinterpret_cast<const float4*>(dy + p * kW1) + lane);
-        const float4 x0 = __ldg(reinterpret_cast<const float4*>(x + p * kN1)), x1 = __ldg(reinterpret_cast<const float4*>(x + p * kN1) + 1);
-        const float xs[kN1] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+            for (int c = 0; c < kN1; ++c) s[c] = fmaf(d.x, wr[c].x, fmaf(d.y, wr[c].y, fmaf(d.z, wr[c].z, d.w * wr[c].w)));
+            float t[4], u[2];
 #pragma unroll
-        for (int c = 0; c < kN1; ++c) {
-            acc[c].x = fmaf(xs[c], d.x, acc[c].x); acc[c].y = fmaf(xs[c], d.y, acc[c].y);
-            acc[c].z = fmaf(xs[c], d.z, acc[c].z); acc[c].w = fmaf(xs[c], d.w, acc[c].w);
+            for (int i = 0; i < 4; ++i) {
+                const float send = b4 ? s[i] : s[4 + i];
+                t[i] = (b4 ? s[4 + i] : s[i]) + __shfl_xor_sync(0xffffffffu, send, 16);
+            }
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const float send = b3 ? t[i] : t[2 + i];
+                u[i] = (b3 ? t[2 + i] : t[i]) + __shfl_xor_sync(0xffffffffu, send, 8);
+            }
+            float v = (b2 ? u[1] : u[0]) + __shfl_xor_sync(0xffffffffu, b2 ? u[0] : u[1], 4);
+            v += __shfl_xor_sync(0xffffffffu, v, 2);
+            v += __shfl_xor_sync(0xffffffffu, v, 1);
+            if ((lane & 3) == 0 && p < P) dx[p * kN1 + (lane >> 2)] = v + bv;
         }
     }
-    __syncthreads();
-#pragma unroll
-    for (int c = 0; c < kN1; ++c) {
-        float* r = red + c * kW1 + lane * 4;
-        atomicAdd(r + 0, acc[c].x); atomicAdd(r + 1, acc[c].y); atomicAdd(r + 2, acc[c].z); atomicAdd(r + 3, acc[c].w);
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < kN1 * kW1; i += blockDim.x) atomicAdd(dw + i, red[i]);
 }
 
 bool thin1x1_shape(const eg_conv_shape* s) {
@@ -393,23 +382,16 @@ unsigned thin1x1_grid(long long P, int sms) {
 
 }  // namespace
 
-// which: 0 forward (a = x, out = y), 1 input gradient (a = dy, out = dx), 2 filter gradient (a = x, b = dy, out = dw);
-// -100 = shape not covered
-int eg_thin1x1(const eg_conv_shape* s, int which, const float* a, const float* b, const float* w, const float* bias, float* out,
-               int accumulate, int sms, cudaStream_t st) {
+// which: 0 forward (a = x, out = y), 1 input gradient (a = dy, out = dx); -100 = shape not covered.  (A filter-gradient
+// kernel of the same kind measured 140 us against 109 us for the patch-matrix route on the tcgen05 kernel and was dropped.)
+int eg_thin1x1(const eg_conv_shape* s, int which, const float* a, const float* w, const float* bias, float* out, int sms,
+               cudaStream_t st) {
     if (g_eg_small_off || !thin1x1_shape(s)) return -100;
-    if ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(out) |
+    if ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(out) |
          reinterpret_cast<uintptr_t>(bias)) & 15) return -100;
     const long long P = (long long)s->N * s->H * s->W;
     if (which == 0) thin1x1_fwd_k<<<thin1x1_grid(P, sms), 256, 0, st>>>(a, w, bias, out, P);
-    else if (which == 1) thin1x1_dgrad_k<<<thin1x1_grid(P, sms), 256, 0, st>>>(a, w, bias, out, P);
-    else {
-        if (!accumulate) {
-            cudaError_t e = cudaMemsetAsync(out, 0, sizeof(float) * kN1 * kW1, st);
-            if (e != cudaSuccess) return eg_fail(e, __FILE__, __LINE__);
-        }
-        thin1x1_wgrad_k<<<(unsigned)std::min<long long>(2ll * sms, (P + 31) / 32), 256, 0, st>>>(a, b, out, P);
-    }
+    else thin1x1_dgrad_k<<<thin1x1_grid(P, sms), 256, 0, st>>>(a, w, bias, out, P);
     EG_CHECK_LAUNCH();
     return 0;
 }

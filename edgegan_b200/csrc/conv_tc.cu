@@ -1675,13 +1675,13 @@ static int tc_conv2d_fwd_gather(const eg_conv_shape* s, const float* x, const fl
 // `scatter` (conv_thin.cu): the product is not stored as y[P, Co] but col2im-scattered into y = dx of the conv `scatter`
 // describes (s is then the dense [P pixels] x [Ci] . [Ci x Npad] product, Npad = one column tile)
 // conv_small.cu: streaming kernels of the 1x1 convolution between 8 and 128 channels (-100 = other shape / switched off)
-int eg_thin1x1(const eg_conv_shape* s, int which, const float* a, const float* b, const float* w, const float* bias, float* out,
-               int accumulate, int sms, cudaStream_t st);
+int eg_thin1x1(const eg_conv_shape* s, int which, const float* a, const float* w, const float* bias, float* out, int sms,
+               cudaStream_t st);
 
 int eg_tc_conv2d_fwd(const eg_conv_shape* s, const float* x, const float* w, const float* bias, float* y, int three_x,
                      cudaStream_t st, const EgEpi* epi, const eg_conv_shape* scatter) {
     if (scatter == nullptr && !(g_dbg[5] & 64)) {
-        const int r = eg_thin1x1(s, 0, x, nullptr, w, bias, y, 0, g_sms, st);
+        const int r = eg_thin1x1(s, 0, x, w, bias, y, g_sms, st);
         if (r != -100) return r ? r : ((epi && epi->mode != EG_EPI_NONE) ? 1 : 0);
     }
     if (scatter == nullptr && gather_fwd(s)) return tc_conv2d_fwd_gather(s, x, w, bias, y, three_x, st, epi);
@@ -1753,7 +1753,7 @@ int eg_tc_scatter_supported(const eg_conv_shape* c) {
 int eg_tc_conv2d_bwd_data(const eg_conv_shape* s, const float* dy, const float* w, const float* bias, float* dx,
                           int three_x, cudaStream_t st, const EgEpi* epi) {
     if (!(g_dbg[5] & 64)) {
-        const int r = eg_thin1x1(s, 1, dy, nullptr, w, bias, dx, 0, g_sms, st);
+        const int r = eg_thin1x1(s, 1, dy, w, bias, dx, g_sms, st);
         if (r != -100) return r ? r : ((epi && epi->mode != EG_EPI_NONE) ? 1 : 0);
     }
     if (thin_bwd_data(s)) {
@@ -1869,10 +1869,6 @@ static int tc_conv2d_bwd_weight_gather(const eg_conv_shape* s, const float* x, c
 
 int eg_tc_conv2d_bwd_weight(const eg_conv_shape* s, const float* x, const float* dy, float* dw, int accumulate,
                             int three_x, cudaStream_t st) {
-    if (!(g_dbg[5] & 64)) {
-        const int r = eg_thin1x1(s, 2, x, dy, nullptr, nullptr, dw, accumulate, g_sms, st);
-        if (r != -100) return r;
-    }
     if (gather_wgrad(s)) {
         if (three_x) return tc_conv2d_bwd_weight_gather(s, x, dy, dw, accumulate, st);
         if (!thin_bwd_weight(s)) return eg_simt_conv2d_bwd_weight(s, x, dy, dw, accumulate, g_sms, st);

@@ -44,7 +44,6 @@ for name, N, H, W, Ci, Co, k, s, p, OH in CASES:
         dev.lib.eg_debug_set(5, 2 | 4 | 32)          # default: the streaming 1x1 kernels of conv_small.cu
         r["1x1 fwd"] = timeit(lambda: dev.conv_fwd(x, w, None, y, s, p, "tc3x"))
         r["1x1 dgrad"] = timeit(lambda: dev.conv_bwd_data(dy, w, None, dx, s, p, "tc3x"))
-        r["1x1 wgrad"] = timeit(lambda: dev.conv_bwd_weight(x, dy, dw, s, p, False, "tc3x"))
     dev.lib.eg_debug_set(5, 2 | 4 | 32)
     floor = 4.0 * (x.numel() + dy.numel()) / 6.5e12 * 1e6
     print(f"{name:30s} HBM floor {floor:5.1f} us | " + " | ".join(f"{k_} {v:6.1f}" for k_, v in r.items()), flush=True)
