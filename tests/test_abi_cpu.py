@@ -60,3 +60,21 @@ def test_library_has_no_unresolved_internal_symbols():
     import os
     from edgegan_b200 import _lib
     ctypes.CDLL(_lib.LIB_PATH, mode=os.RTLD_NOW | os.RTLD_LOCAL)
+
+
+def test_descriptor_struct_layouts_match_the_header():
+    """ctypes mirrors of the descriptor structs (include/edgegan_b200.h: eg_filter_desc, eg_sn_desc, eg_conv_shape) have the
+    C layout: field order, offsets and total size"""
+    import ctypes as C
+    from edgegan_b200 import _lib
+    assert C.sizeof(_lib.FilterDesc) == 24 and _lib.FilterDesc.taps.offset == 8 and _lib.FilterDesc.Co.offset == 16
+    names = ["W", "u", "Wbar", "ws", "G", "gW", "Wa", "Wi", "Ga", "Gi"]
+    assert [f[0] for f in _lib.SnDesc._fields_] == names + ["K", "C", "cin", "hd"]
+    assert C.sizeof(_lib.SnDesc) == 10 * 8 + 4 * 4
+    for i, n in enumerate(names):
+        assert getattr(_lib.SnDesc, n).offset == 8 * i
+    assert _lib.SnDesc.K.offset == 80 and _lib.SnDesc.hd.offset == 92
+    hdr = open(os.path.join(ROOT, "include", "edgegan_b200.h")).read()
+    body = hdr[hdr.index("typedef struct {\n    const float* W;"):hdr.index("} eg_sn_desc;")]
+    order = re.findall(r"\b(W|u|Wbar|ws|G|gW|Wa|Wi|Ga|Gi|K|C|cin|hd)\b[;,]", body)
+    assert order == names + ["K", "C", "cin", "hd"], order
