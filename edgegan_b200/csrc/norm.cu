@@ -350,7 +350,7 @@ instnorm_fwd_sm(const float* __restrict__ x, float* __restrict__ y, float* __res
     cl_exit(CL);
 }
 
-__global__ void __launch_bounds__(kSmThreads)
+__global__ void __maxnreg__(80)        // 80 registers: three 256-thread blocks per SM instead of two (ptxas: no spills / 8 bytes)
 instnorm_bwd_sm(const float* __restrict__ x, const float* __restrict__ stats, const float* __restrict__ gy,
                 const float* __restrict__ addend, float* __restrict__ gx, int Pall, int C, float eps, int act, int cols, int CL) {
     extern __shared__ float4 slab[];                         // [2][P][cols]: centred x, masked cotangent
@@ -402,7 +402,7 @@ instnorm_bwd_sm(const float* __restrict__ x, const float* __restrict__ stats, co
 }
 
 // second-order term of the gradient penalty (same formulas as instnorm_bwd2_k: centred second moments)
-__global__ void __launch_bounds__(kSmThreads)
+__global__ void __maxnreg__(80)        // 80 registers: three 256-thread blocks per SM instead of two (ptxas: no spills / 8 bytes)
 instnorm_bwd2_sm(const float* __restrict__ x, const float* __restrict__ stats, const float* __restrict__ gy,
                  const float* __restrict__ t, float* __restrict__ out_gy, float* __restrict__ out_x, int Pall, int C,
                  float eps, int act, int cols, int CL) {
@@ -578,11 +578,16 @@ int launch_sm(void (*kern)(KA...), int groups, int N, int threads, size_t smem, 
     if (e != cudaSuccess) return eg_fail(e, __FILE__, __LINE__);
     return 0;
 }
-// threads per block: about four rows per thread (small slabs are bound by the block-wide reductions, not by bytes)
-int g_sm_rows_cap = 64;
+// threads per block: about four rows per thread (small slabs are bound by the block-wide reductions, not by bytes), at
+// most 256 threads whatever the row width (rows = 256 / cols): with 80 registers three such blocks share an SM, while a
+// 512-thread block is alone on it.  Measured, same position in the sweep (tools/norm_time.py with ROWS=1; the sweep's
+// first configuration is favoured by ~30 %, so only like positions are compared): [384, 16x16, 256] forward 75 -> 53 us,
+// backward 130 -> 88 us with 256 instead of 512 threads; [384, 32x32, 128] (32-byte rows) backward 275 -> 257 us with 256
+// instead of 128 threads.
+int g_sm_threads_target = 256;
 int sm_threads(int P, int cols) {
     int rows = 4;
-    while (rows < g_sm_rows_cap && rows * 4 < P) rows <<= 1;
+    while (rows * cols < g_sm_threads_target && rows * 4 < P) rows <<= 1;
     int t = rows * cols;
     if (t < 64) t = 64;
     if (t > kSmThreads) t = kSmThreads;
@@ -679,7 +684,7 @@ extern "C" {
 int eg_norm_debug(int value) {
     if (value == -2) g_in_cluster_off = 1;                   // one block per slab only
     else if (value == -3) g_in_cluster_off = 0;
-    else if (value <= -10) g_sm_rows_cap = -value;           // -64 (default) / -128 / -256: thread rows per block
+    else if (value <= -10) g_sm_threads_target = -value;     // -256 (default) / -128 / -512: threads per block
     else g_in_stream = value;
     return 0;
 }

@@ -40,11 +40,11 @@ for shape in SHAPES:
     t1, t2, t3 = timeit(fwd, ncopy), timeit(bwd, ncopy), timeit(bwd2, ncopy)
     if os.environ.get("ROWS"):
         res = []
-        for cap in (64, 128, 256):
+        for cap in (256, 128, 512):
             dev.lib.eg_norm_debug(-cap)
             res.append((cap, timeit(fwd, ncopy) * 1e3, timeit(bwd, ncopy) * 1e3, timeit(bwd2, ncopy) * 1e3))
-        dev.lib.eg_norm_debug(-64)
-        print(f"IN {str(shape):22s} rows cap -> fwd / bwd / bwd2 us: " + " | ".join(f"{c}: {a:6.1f} {b:6.1f} {d:6.1f}" for c, a, b, d in res), flush=True)
+        dev.lib.eg_norm_debug(-256)
+        print(f"IN {str(shape):22s} threads per block -> fwd / bwd / bwd2 us: " + " | ".join(f"{c}: {a:6.1f} {b:6.1f} {d:6.1f}" for c, a, b, d in res), flush=True)
     print(f"IN {str(shape):22s} {mb:6.1f} MB/tensor | fwd {o1*1e3:6.1f} -> {t1*1e3:6.1f} us {2*mb/t1/1e3:5.2f} TB/s | bwd {o2*1e3:6.1f} -> {t2*1e3:6.1f} us "
           f"{3*mb/t2/1e3:5.2f} TB/s | bwd2 {o3*1e3:6.1f} -> {t3*1e3:6.1f} us {5*mb/t3/1e3:5.2f} TB/s   (one block per slab -> clusters)", flush=True)
     del xs, gs, ys
