@@ -350,7 +350,7 @@ instnorm_fwd_sm(const float* __restrict__ x, float* __restrict__ y, float* __res
     cl_exit(CL);
 }
 
-__global__ void __maxnreg__(80)        // 80 registers: three 256-thread blocks per SM instead of two (ptxas: no spills / 8 bytes)
+__global__ void __maxnreg__(80)        // 80 registers (ptxas: no spills): three 256-thread blocks per SM instead of two
 instnorm_bwd_sm(const float* __restrict__ x, const float* __restrict__ stats, const float* __restrict__ gy,
                 const float* __restrict__ addend, float* __restrict__ gx, int Pall, int C, float eps, int act, int cols, int CL) {
     extern __shared__ float4 slab[];                         // [2][P][cols]: centred x, masked cotangent
@@ -402,7 +402,7 @@ instnorm_bwd_sm(const float* __restrict__ x, const float* __restrict__ stats, co
 }
 
 // second-order term of the gradient penalty (same formulas as instnorm_bwd2_k: centred second moments)
-__global__ void __maxnreg__(80)        // 80 registers: three 256-thread blocks per SM instead of two (ptxas: no spills / 8 bytes)
+__global__ void __launch_bounds__(kSmThreads)     // (its three slabs leave room for two blocks per SM at most: no register cap)
 instnorm_bwd2_sm(const float* __restrict__ x, const float* __restrict__ stats, const float* __restrict__ gy,
                  const float* __restrict__ t, float* __restrict__ out_gy, float* __restrict__ out_x, int Pall, int C,
                  float eps, int act, int cols, int CL) {
